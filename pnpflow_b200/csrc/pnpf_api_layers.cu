@@ -1,0 +1,74 @@
+// C-ABI: layer-level entry points (used by the parity tests; they drive the very same kernels as the U-Net plan).
+#include "../../include/pnpflow_b200.h"
+#include "pnpf_ops.h"
+
+#include <vector>
+
+using namespace pnpf;
+
+extern "C" int pnpf_abi_version(void) { return PNPF_ABI_VERSION; }
+extern "C" const char* pnpf_last_error(void) { return get_error(); }
+
+static int round_up_n(int cout) {
+    if (cout <= 16) return 16;
+    if (cout <= 32) return 32;
+    if (cout <= 64) return 64;
+    if (cout <= 128) return 128;
+    return (cout + 255) / 256 * 256;
+}
+
+extern "C" int pnpf_conv2d_nhwc(const void* x, int B, int Hin, int Win, int Cin, const float* host_w, const float* host_bias,
+                                int Cout, int ksize, int stride, const void* x2, int C2, const float* host_w2,
+                                const void* residual, void* out, int out_f32, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PNPF_REQUIRE(x && host_w && out, "null pointer");
+    PNPF_REQUIRE(Cout % 16 == 0, "layer-level conv needs Cout %% 16 == 0 (got %d)", Cout);
+    const int N_pad = round_up_n(Cout);
+    const int Hout = (Hin + 2 * (ksize / 2) - ksize) / stride + 1;
+    const int Wout = (Win + 2 * (ksize / 2) - ksize) / stride + 1;
+    const long long Ktot = (long long)ksize * ksize * Cin + (x2 ? C2 : 0);
+    std::vector<bf16> wp((size_t)N_pad * Ktot);
+    pack_conv_weight(wp.data(), host_w, Cout, Cin, ksize, N_pad, Cin, x2 ? host_w2 : nullptr, x2 ? C2 : 0, 1.0f);
+    std::vector<float> bp(N_pad, 0.f);
+    if (host_bias)
+        for (int i = 0; i < Cout; ++i) bp[i] = host_bias[i];
+    bf16* dw = nullptr;
+    float* db = nullptr;
+    PNPF_CHECK_CUDA(cudaMalloc(&dw, wp.size() * sizeof(bf16)));
+    PNPF_CHECK_CUDA(cudaMalloc(&db, bp.size() * sizeof(float)));
+    PNPF_CHECK_CUDA(cudaMemcpyAsync(dw, wp.data(), wp.size() * sizeof(bf16), cudaMemcpyHostToDevice, s));
+    PNPF_CHECK_CUDA(cudaMemcpyAsync(db, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    ConvDesc d;
+    d.x = static_cast<const bf16*>(x);
+    d.B = B; d.Hin = Hin; d.Win = Win; d.Cin = Cin; d.x_pitch = Cin;
+    d.x2 = static_cast<const bf16*>(x2); d.C2 = C2; d.x2_pitch = C2;
+    d.w = dw; d.N_pad = N_pad; d.ksize = ksize; d.stride = stride; d.Hout = Hout; d.Wout = Wout;
+    d.out = out; d.out_mode = out_f32 ? 1 : 0;
+    d.out_img_stride = (long long)Hout * Wout * Cout; d.out_row_stride = Cout; d.n_valid = Cout;
+    d.bias = db;
+    d.residual = static_cast<const bf16*>(residual);
+    d.res_img_stride = (long long)Hout * Wout * Cout; d.res_row_stride = Cout;
+    TcOp op;
+    int rc = prepare_conv(op, d);
+    if (!rc) rc = launch_tc(op, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(dw);
+    cudaFree(db);
+    if (rc) return rc;
+    PNPF_CHECK_CUDA(e);
+    return 0;
+}
+
+extern "C" int pnpf_gemm_nt(const void* A, const void* Bm, void* out, int batch, int M, int N, int K, int out_f32, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    GemmDesc d;
+    d.A = static_cast<const bf16*>(A); d.lda = K; d.a_bstride = (long long)M * K; d.a_batched = 1;
+    d.Bm = static_cast<const bf16*>(Bm); d.ldb = K; d.b_bstride = (long long)N * K; d.b_batched = 1;
+    d.batch = batch; d.M = M; d.N = N; d.K = K;
+    d.out = out; d.out_mode = out_f32 ? 1 : 0; d.out_img_stride = (long long)M * N; d.out_row_stride = N;
+    TcOp op;
+    if (int rc = prepare_gemm(op, d)) return rc;
+    if (int rc = launch_tc(op, s)) return rc;
+    PNPF_CHECK_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}

@@ -1,0 +1,263 @@
+// Implicit-GEMM convolution / batched GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+//   D[128 pixels x BN] (+)= sum_{tap, cin-chunk} A_tap[128 x BK] * W[BN x BK]^T
+//
+// * A (activations) lives in HBM as NHWC bf16 and is fetched with a 4-D TILED tensor map (C, W, H, B) whose box is
+//   {BK channels, TW, TH, 1}: one TMA per (tap, channel chunk) with the start coordinate shifted by (dw, dh).
+//   Out-of-bounds coordinates (including negative ones) are zero-filled by the TMA unit, which IS the conv's
+//   zero padding; the box lands in shared memory as 128 rows of BK*2 bytes with the hardware 128B/64B swizzle,
+//   i.e. exactly the canonical K-major UMMA operand layout.  Stride-2 convs use elementStrides = 2 in W and H.
+// * W (weights) is a [N_total, K_total] K-major bf16 matrix (K ordered tap-major then channel) fetched with a 3-D map.
+// * One elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM accumulator; 4 epilogue
+//   warps drain it with tcgen05.ld while the next tile's main loop runs (persistent CTAs, static tile striding).
+// * The same kernel runs the attention GEMMs (H=1, W=M rows, per-image B operand) and the fused 1x1 shortcut
+//   (extra K chunks read from a second activation map).
+#pragma once
+#include "pnpf_ptx.cuh"
+
+namespace pnpf {
+
+struct GemmParams {
+    int H, W;              // output extent in the A-box coordinate space (plain GEMM: H=1, W=M)
+    int TH, TW;            // tile box, TH*TW == 128
+    int tiles_h, tiles_w;
+    int n_img;
+    int n_tiles_n;         // N_total = n_tiles_n * BN
+    int a_batched, b_batched;
+    int in_stride;         // input coordinate = out * in_stride + d
+    int ntaps;
+    int dh[9], dw[9];
+    int kchunks;           // channel chunks per tap read through tmA
+    int c_base;            // first channel of tmA to read
+    int kchunks2;          // trailing 1x1 chunks read through tmA2 (0 = none)
+    // epilogue
+    void* out;
+    int out_mode;          // 0: bf16 [img][pix][col]   1: f32 [img][pix][col]   2: f32 [img][col][pix] (NCHW)
+    long long out_img_stride, out_row_stride, out_col_stride;   // elements
+    int n_valid;           // columns >= n_valid are not stored
+    const float* bias;     // [N_total] or nullptr
+    const float* bias_img; // [img][bias_img_stride] + col, or nullptr   (time-embedding projection)
+    long long bias_img_stride;
+    const __nv_bfloat16* residual;   // [img][pix][col] bf16 or nullptr
+    long long res_img_stride, res_row_stride;
+};
+
+template <int BK, int BN>
+struct GemmCfg {
+    static constexpr int kRowBytes = BK * 2;
+    static constexpr int A_BYTES = 128 * BK * 2;
+    static constexpr int B_BYTES_RAW = BN * BK * 2;
+    static constexpr int B_BYTES = (B_BYTES_RAW + 1023) / 1024 * 1024;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES_FIT = (196 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+    static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int THREADS = 192;
+    static_assert(BK == 32 || BK == 64, "BK");
+    static_assert(BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
+};
+
+__device__ __forceinline__ void decode_tile(const GemmParams& p, int t, int& img, int& h0, int& w0, int& nt) {
+    nt = t % p.n_tiles_n;
+    int r = t / p.n_tiles_n;
+    int twi = r % p.tiles_w;
+    r /= p.tiles_w;
+    int thi = r % p.tiles_h;
+    img = r / p.tiles_h;
+    h0 = thi * p.TH;
+    w0 = twi * p.TW;
+}
+
+template <int BK, int BN>
+__global__ void __launch_bounds__(GemmCfg<BK, BN>::THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
+    using Cfg = GemmCfg<BK, BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;     // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = p.n_img * p.tiles_h * p.tiles_w * p.n_tiles_n;
+    const int nk_main = p.ntaps * p.kchunks;
+    const int nk = nk_main + p.kchunks2;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (p.kchunks2) tma_prefetch_desc(&tmA2);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one lane) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                int img, h0, w0, nt;
+                decode_tile(p, t, img, h0, w0, nt);
+                const int ab = p.a_batched ? img : 0;
+                const int bb = p.b_batched ? img : 0;
+                for (int i = 0; i < nk; ++i) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES_RAW);
+                    if (i < nk_main) {
+                        const int tap = i / p.kchunks;
+                        const int ch = i - tap * p.kchunks;
+                        tma_load_4d(sa, &tmA, &full_bar[stage], p.c_base + ch * BK, w0 * p.in_stride + p.dw[tap],
+                                    h0 * p.in_stride + p.dh[tap], ab);
+                    } else {
+                        tma_load_4d(sa, &tmA2, &full_bar[stage], (i - nk_main) * BK, w0, h0, ab);
+                    }
+                    tma_load_3d(sb, &tmB, &full_bar[stage], i * BK, nt * BN, bb);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one lane) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int i = 0; i < nk; ++i) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t adesc = make_smem_desc<Cfg::kRowBytes>(sa);
+                    const uint64_t bdesc = make_smem_desc<Cfg::kRowBytes>(sa + Cfg::A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr>>4) field
+                        umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);                     // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue warps 2..5 =====================
+        const int quarter = warp & 3;                             // TMEM lane quarter this warp may access
+        const int m = quarter * 32 + lane;                        // accumulator row == pixel within the tile
+        const int th = m / p.TW, tw = m - th * p.TW;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            int img, h0, w0, nt;
+            decode_tile(p, t, img, h0, w0, nt);
+            const int h = h0 + th, w = w0 + tw;
+            const bool valid = (h < p.H) && (w < p.W);
+            const long long pix = static_cast<long long>(h) * p.W + w;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld_x16(t_addr + c0, r);
+                tmem_ld_wait();
+                const int col0 = nt * BN + c0;
+                if (valid && col0 < p.n_valid) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    }
+                    if (p.bias_img) {
+                        const float* bi = p.bias_img + img * p.bias_img_stride + col0;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bi + j));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    }
+                    if (p.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + img * p.res_img_stride +
+                                                                         pix * p.res_row_stride + col0);
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const uint4 u = __ldg(rp + q);
+                            const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                v[q * 8 + 2 * j] += __uint_as_float(uu[j] << 16);
+                                v[q * 8 + 2 * j + 1] += __uint_as_float(uu[j] & 0xFFFF0000u);
+                            }
+                        }
+                    }
+                    if (p.out_mode == 0) {
+                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + img * p.out_img_stride +
+                                            pix * p.out_row_stride + col0;
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                            pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+                        }
+                        uint4* o4 = reinterpret_cast<uint4*>(op);
+                        o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    } else if (p.out_mode == 1) {
+                        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + img * p.out_img_stride +
+                                                               pix * p.out_row_stride + col0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+                        float* op = reinterpret_cast<float*>(p.out) + img * p.out_img_stride + pix;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (col0 + j < p.n_valid) op[(col0 + j) * p.out_col_stride] = v[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+}  // namespace pnpf

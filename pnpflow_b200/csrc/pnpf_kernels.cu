@@ -1,0 +1,495 @@
+// SIMT kernels of the engine (everything that is not a tensor-core contraction).  sm_100a.
+#include "pnpf_kernels.cuh"
+
+namespace pnpf {
+
+// =================================================================================================
+// helpers
+// =================================================================================================
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        f[2 * j] = __uint_as_float(w[j] << 16);
+        f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&b);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ const bf16* src_ptr(const GnSrc& s, int img, long long pix, int HW, int c0) {
+    if (c0 < s.C1) return s.p1 + ((long long)img * HW + pix) * s.pitch1 + c0;
+    return s.p2 + ((long long)img * HW + pix) * s.pitch2 + (c0 - s.C1);
+}
+
+constexpr int GN_PIX_PER_BLOCK = 1024;
+
+// =================================================================================================
+// GroupNorm statistics: per (image, channel) sum and sum of squares, fp32 in-block, fp64 atomics across blocks
+// =================================================================================================
+__global__ void gn_stats_kernel(GnSrc s, int HW, double* __restrict__ stats) {
+    extern __shared__ float red[];                    // [ppb][C][2]
+    const int C = s.C1 + s.C2;
+    const int nvec = C >> 3;
+    const int ppb = blockDim.x / nvec;
+    const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+    const int img = blockIdx.y;
+    const int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
+    const int p1 = min(p0 + GN_PIX_PER_BLOCK, HW);
+    float sum[8], sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+    for (int p = p0 + pl; p < p1; p += ppb) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src_ptr(s, img, p, HW, v * 8)));
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sum[j] += f[j];
+            sq[j] = fmaf(f[j], f[j], sq[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        red[(pl * C + v * 8 + j) * 2] = sum[j];
+        red[(pl * C + v * 8 + j) * 2 + 1] = sq[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int q = 0; q < ppb; ++q) {
+            a += red[(q * C + c) * 2];
+            b += red[(q * C + c) * 2 + 1];
+        }
+        atomicAdd(&stats[((long long)img * C + c) * 2], (double)a);
+        atomicAdd(&stats[((long long)img * C + c) * 2 + 1], (double)b);
+    }
+}
+
+static inline int gn_threads(int C) {
+    const int nvec = C / 8;
+    int ppb = 256 / nvec;
+    if (ppb < 1) ppb = 1;
+    return nvec * ppb;
+}
+
+int launch_gn_stats(const GnSrc& s, int B, int HW, double* stats, cudaStream_t st) {
+    const int C = s.C1 + s.C2;
+    PNPF_REQUIRE(C % 32 == 0 && s.C1 % 8 == 0 && C <= 2048, "GroupNorm channels (%d+%d) unsupported", s.C1, s.C2);
+    const int threads = gn_threads(C);
+    const int ppb = threads / (C / 8);
+    const size_t smem = (size_t)ppb * C * 2 * sizeof(float);
+    dim3 grid((HW + GN_PIX_PER_BLOCK - 1) / GN_PIX_PER_BLOCK, B);
+    gn_stats_kernel<<<grid, threads, smem, st>>>(s, HW, stats);
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =================================================================================================
+// GroupNorm apply (+ SiLU) -> bf16 NHWC conv operand; optional raw concat copy
+// =================================================================================================
+__global__ void gn_apply_kernel(GnSrc s, int HW, const double* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int gs, int silu, bf16* __restrict__ dst,
+                                bf16* __restrict__ raw_dst) {
+    extern __shared__ float ss[];                     // scale[C], shift[C]
+    const int C = s.C1 + s.C2;
+    const int img = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g0 = (c / gs) * gs;
+        double S = 0, Q = 0;
+        for (int j = 0; j < gs; ++j) {
+            S += stats[((long long)img * C + g0 + j) * 2];
+            Q += stats[((long long)img * C + g0 + j) * 2 + 1];
+        }
+        const double n = (double)gs * HW;
+        const double mean = S / n;
+        double var = Q / n - mean * mean;
+        if (var < 0) var = 0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float sc = rstd * gamma[c];
+        ss[c] = sc;
+        ss[C + c] = beta[c] - (float)mean * sc;
+    }
+    __syncthreads();
+    const int nvec = C >> 3;
+    const int ppb = blockDim.x / nvec;
+    const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+    const int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
+    const int p1 = min(p0 + GN_PIX_PER_BLOCK, HW);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = ss[v * 8 + j];
+        sh[j] = ss[C + v * 8 + j];
+    }
+    for (int p = p0 + pl; p < p1; p += ppb) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src_ptr(s, img, p, HW, v * 8)));
+        const long long o = ((long long)img * HW + p) * C + v * 8;
+        if (raw_dst) *reinterpret_cast<uint4*>(raw_dst + o) = u;
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float y = fmaf(f[j], sc[j], sh[j]);
+            if (silu) y = y / (1.f + __expf(-y));
+            f[j] = y;
+        }
+        *reinterpret_cast<uint4*>(dst + o) = pack8(f);
+    }
+}
+
+int launch_gn_apply(const GnSrc& s, int B, int HW, const double* stats, const float* gamma, const float* beta, float eps,
+                    int groups, int silu, bf16* dst, bf16* raw_dst, cudaStream_t st) {
+    const int C = s.C1 + s.C2;
+    PNPF_REQUIRE(C % groups == 0 && C % 8 == 0 && s.C1 % 8 == 0, "GroupNorm channels (%d+%d) unsupported", s.C1, s.C2);
+    const int threads = gn_threads(C);
+    dim3 grid((HW + GN_PIX_PER_BLOCK - 1) / GN_PIX_PER_BLOCK, B);
+    gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), st>>>(s, HW, stats, gamma, beta, eps, C / groups, silu, dst, raw_dst);
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =================================================================================================
+// row softmax: one warp per row, fp32 in, bf16 out
+// =================================================================================================
+__global__ void softmax_rows_kernel(const float* __restrict__ S, bf16* __restrict__ P, long long rows, int L) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* s = S + row * L;
+    float m = -INFINITY;
+    for (int i = lane * 4; i < L; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(s + i);
+        m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int i = lane * 4; i < L; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(s + i);
+        sum += __expf(v.x - m) + __expf(v.y - m) + __expf(v.z - m) + __expf(v.w - m);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    bf16* p = P + row * L;
+    for (int i = lane * 4; i < L; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(s + i);
+        __nv_bfloat162 a = __floats2bfloat162_rn(__expf(v.x - m) * inv, __expf(v.y - m) * inv);
+        __nv_bfloat162 b = __floats2bfloat162_rn(__expf(v.z - m) * inv, __expf(v.w - m) * inv);
+        uint2 o2;
+        o2.x = *reinterpret_cast<uint32_t*>(&a);
+        o2.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(p + i) = o2;
+    }
+}
+
+int launch_softmax_rows(const float* S, bf16* P, long long rows, int L, cudaStream_t st) {
+    PNPF_REQUIRE(L % 4 == 0, "softmax length %d must be a multiple of 4", L);
+    const int wpb = 8;
+    softmax_rows_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(S, P, rows, L);
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =================================================================================================
+// time embedding: sincos -> dense -> swish -> dense -> swish -> all temb_proj layers
+// =================================================================================================
+__device__ __forceinline__ float swishf(float x) { return x / (1.f + expf(-x)); }
+
+__global__ void temb_kernel(TembWeights w, const float* __restrict__ t, float* __restrict__ out) {
+    extern __shared__ float sm[];                     // emb[ch] | h[temb_ch] | s[temb_ch]
+    float* emb = sm;
+    float* h = sm + w.ch;
+    float* sv = h + w.temb_ch;
+    const int img = blockIdx.x;
+    const float tt = t[img];
+    const int half = w.ch / 2;
+    for (int i = threadIdx.x; i < w.ch; i += blockDim.x) {
+        const float a = tt * w.freqs[i % half];
+        emb[i] = (i < half) ? sinf(a) : cosf(a);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < w.temb_ch; o += blockDim.x) {
+        float acc = w.b0[o];
+        for (int k = 0; k < w.ch; ++k) acc = fmaf(w.w0[o * w.ch + k], emb[k], acc);
+        h[o] = swishf(acc);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < w.temb_ch; o += blockDim.x) {
+        float acc = w.b2[o];
+        for (int k = 0; k < w.temb_ch; ++k) acc = fmaf(w.w2[o * w.temb_ch + k], h[k], acc);
+        sv[o] = swishf(acc);                          // ResidualBlock applies act(temb) before temb_proj (models.py:101)
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < w.total_proj; o += blockDim.x) {
+        float acc = w.bp[o];
+        for (int k = 0; k < w.temb_ch; ++k) acc = fmaf(w.wp_t[(long long)k * w.total_proj + o], sv[k], acc);
+        out[(long long)img * w.total_proj + o] = acc;
+    }
+}
+
+int launch_temb(const TembWeights& w, const float* t, int B, float* out, cudaStream_t st) {
+    const size_t smem = (w.ch + 2 * w.temb_ch) * sizeof(float);
+    temb_kernel<<<B, 256, smem, st>>>(w, t, out);
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =================================================================================================
+// layout shims
+// =================================================================================================
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, int C, int HW, bf16* __restrict__ dst, int Cpad,
+                                        long long total_pix) {
+    const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gp >= total_pix) return;
+    const long long img = gp / HW, p = gp - img * HW;
+    bf16* o = dst + gp * Cpad;
+    for (int c0 = 0; c0 < Cpad; c0 += 8) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = (c0 + j < C) ? __ldg(x + (img * C + c0 + j) * HW + p) : 0.f;
+        *reinterpret_cast<uint4*>(o + c0) = pack8(f);
+    }
+}
+int launch_nchw_to_nhwc_pad(const float* x, int B, int C, int HW, bf16* dst, int Cpad, cudaStream_t st) {
+    const long long n = (long long)B * HW;
+    nchw_to_nhwc_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, C, HW, dst, Cpad, n);
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void nhwc_to_nchw_f32_kernel(const bf16* __restrict__ src, long long pitch, int C, int HW, float* __restrict__ dst,
+                                        long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over [B][C][HW]
+    if (i >= total) return;
+    const long long p = i % HW;
+    const long long bc = i / HW;
+    const long long c = bc % C, b = bc / C;
+    dst[i] = __bfloat162float(src[(b * HW + p) * pitch + c]);
+}
+int launch_nhwc_to_nchw_f32(const bf16* src, long long pitch, int B, int C, int HW, float* dst, cudaStream_t st) {
+    const long long n = (long long)B * C * HW;
+    nhwc_to_nchw_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, pitch, C, HW, dst, n);
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void upsample2x_kernel(const uint4* __restrict__ src, int H, int W, int Cv, uint4* __restrict__ dst, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over [B][2H][2W][Cv]
+    if (i >= total) return;
+    const int cv = (int)(i % Cv);
+    long long r = i / Cv;
+    const int ow = (int)(r % (2 * W));
+    r /= (2 * W);
+    const int oh = (int)(r % (2 * H));
+    const long long b = r / (2 * H);
+    dst[i] = __ldg(src + ((b * H + (oh >> 1)) * W + (ow >> 1)) * Cv + cv);
+}
+int launch_upsample2x(const bf16* src, int B, int H, int W, int C, bf16* dst, cudaStream_t st) {
+    PNPF_REQUIRE(C % 8 == 0, "upsample channels %d", C);
+    const long long n = (long long)B * 4 * H * W * (C / 8);
+    upsample2x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src), H, W, C / 8,
+                                                                   reinterpret_cast<uint4*>(dst), n);
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =================================================================================================
+// PnP-Flow per-pixel kernels
+// =================================================================================================
+__device__ __forceinline__ bool keep_pixel(const OpDesc& op, int b, int h, int w, int H, int W) {
+    if (op.kind == 1) {                               // box: zero the square [d-hs, d+hs)^2, d = H//2 (utils.py:331-335)
+        const int d = H / 2;
+        const bool in = (h >= d - op.half_size) && (h < d + op.half_size) && (w >= d - op.half_size) && (w < d + op.half_size);
+        return !in;
+    }
+    if (op.kind == 2) return op.mask[((long long)b * H + h) * W + w] != 0;
+    return true;
+}
+
+// H / H_adj for identity, box, mask (y = m*x) and SR (gather / zero-fill scatter)
+__global__ void apply_diag_kernel(OpDesc op, const float* __restrict__ x, float* __restrict__ y, int C, int H, int W,
+                                  long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int w = (int)(i % W);
+    long long r = i / W;
+    const int h = (int)(r % H);
+    r /= H;
+    const int b = (int)(r / C);
+    y[i] = keep_pixel(op, b, h, w, H, W) ? x[i] : 0.f * x[i];
+}
+__global__ void sr_down_kernel(const float* __restrict__ x, float* __restrict__ y, int sf, int H, int W, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over [BC][H/sf][W/sf]
+    if (i >= total) return;
+    const int Ws = W / sf, Hs = H / sf;
+    const int w = (int)(i % Ws);
+    long long r = i / Ws;
+    const int h = (int)(r % Hs);
+    const long long bc = r / Hs;
+    y[i] = x[(bc * H + (long long)h * sf) * W + (long long)w * sf];
+}
+__global__ void sr_up_kernel(const float* __restrict__ y, float* __restrict__ x, int sf, int H, int W, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over [BC][H][W]
+    if (i >= total) return;
+    const int w = (int)(i % W);
+    long long r = i / W;
+    const int h = (int)(r % H);
+    const long long bc = r / H;
+    x[i] = ((h % sf) == 0 && (w % sf) == 0) ? y[(bc * (H / sf) + h / sf) * (W / sf) + w / sf] : 0.f;
+}
+
+// Separable circular Gaussian blur of one (b,c) plane tile.  mode 0: out = G*in ; 1: out = G*in - aux ; 2: out = aux - gamma*(G*in)
+constexpr int BLUR_TILE = 32;
+__global__ void blur_kernel(const float* __restrict__ in, const float* __restrict__ aux, float* __restrict__ out,
+                            const float* __restrict__ taps, int ksize, int H, int W, int mode, float gamma) {
+    extern __shared__ float sm[];
+    const int R = (ksize - 1) / 2;
+    const int HT = BLUR_TILE + 2 * R;                 // halo tile side
+    float* tile = sm;                                 // [HT][HT]
+    float* tmp = tile + HT * HT;                      // [HT][BLUR_TILE]  (row pass result)
+    float* g = tmp + HT * BLUR_TILE;                  // [ksize]
+    const long long plane = blockIdx.z;
+    const int h0 = blockIdx.y * BLUR_TILE, w0 = blockIdx.x * BLUR_TILE;
+    const float* src = in + plane * H * W;
+    for (int i = threadIdx.x; i < ksize; i += blockDim.x) g[i] = taps[i];
+    for (int i = threadIdx.x; i < HT * HT; i += blockDim.x) {
+        const int th = i / HT, tw = i - th * HT;
+        int hh = (h0 + th - R) % H; if (hh < 0) hh += H;
+        int ww = (w0 + tw - R) % W; if (ww < 0) ww += W;
+        tile[i] = src[(long long)hh * W + ww];
+    }
+    __syncthreads();
+    // out[i] = sum_k g[k] * x[i - (k - R)]  (circular; degradations.py:62-68,78-79)
+    for (int i = threadIdx.x; i < HT * BLUR_TILE; i += blockDim.x) {
+        const int th = i / BLUR_TILE, tw = i - th * BLUR_TILE;
+        float acc = 0.f;
+        for (int k = 0; k < ksize; ++k) acc = fmaf(g[k], tile[th * HT + (tw + 2 * R - k)], acc);
+        tmp[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BLUR_TILE * BLUR_TILE; i += blockDim.x) {
+        const int th = i / BLUR_TILE, tw = i - th * BLUR_TILE;
+        const int h = h0 + th, w = w0 + tw;
+        if (h >= H || w >= W) continue;
+        float acc = 0.f;
+        for (int k = 0; k < ksize; ++k) acc = fmaf(g[k], tmp[(th + 2 * R - k) * BLUR_TILE + tw], acc);
+        const long long o = plane * H * W + (long long)h * W + w;
+        if (mode == 1) acc = acc - aux[o];
+        else if (mode == 2) acc = aux[o] - gamma * acc;
+        out[o] = acc;
+    }
+}
+static int launch_blur(const OpDesc& op, const float* in, const float* aux, float* out, int planes, int H, int W, int mode,
+                       float gamma, cudaStream_t st) {
+    PNPF_REQUIRE(op.taps && op.ksize % 2 == 1 && op.ksize <= H && op.ksize <= W, "blur kernel size %d vs image %dx%d", op.ksize, H, W);
+    const int R = (op.ksize - 1) / 2, HT = BLUR_TILE + 2 * R;
+    const size_t smem = ((size_t)HT * HT + (size_t)HT * BLUR_TILE + op.ksize) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        PNPF_CHECK_CUDA(cudaFuncSetAttribute(blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr = true;
+    }
+    PNPF_REQUIRE(smem <= 160 * 1024, "blur kernel too large for shared memory");
+    dim3 grid((W + BLUR_TILE - 1) / BLUR_TILE, (H + BLUR_TILE - 1) / BLUR_TILE, planes);
+    blur_kernel<<<grid, 256, smem, st>>>(in, aux, out, op.taps, op.ksize, H, W, mode, gamma);
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_apply_H(const OpDesc& op, const float* x, float* y, int B, int C, int H, int W, bool adjoint, cudaStream_t st) {
+    const long long n = (long long)B * C * H * W;
+    if (op.kind == 3) {
+        PNPF_REQUIRE(op.sf >= 1 && H % op.sf == 0 && W % op.sf == 0, "SR factor %d vs %dx%d", op.sf, H, W);
+        if (!adjoint) {
+            const long long m = n / (op.sf * op.sf);
+            sr_down_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(x, y, op.sf, H, W, m);
+        } else {
+            sr_up_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, op.sf, H, W, n);
+        }
+    } else if (op.kind == 4) {
+        return launch_blur(op, x, nullptr, y, B * C, H, W, 0, 0.f, st);
+    } else {
+        PNPF_REQUIRE(op.kind != 2 || op.mask, "mask operator without a device mask");
+        apply_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, x, y, C, H, W, n);
+    }
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// z = x - gamma * A^T(Ax - y) for the diagonal operators and SR, one pass (12 N bytes)
+__global__ void datafit_diag_kernel(OpDesc op, const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ z,
+                                    float gamma, int C, int H, int W, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int w = (int)(i % W);
+    long long r = i / W;
+    const int h = (int)(r % H);
+    r /= H;                                           // r = b*C + c
+    const float xv = x[i];
+    float out = xv;
+    if (op.kind == 3) {
+        if ((h % op.sf) == 0 && (w % op.sf) == 0) {
+            const float yv = y[(r * (H / op.sf) + h / op.sf) * (W / op.sf) + w / op.sf];
+            out = __fsub_rn(xv, __fmul_rn(gamma, __fsub_rn(xv, yv)));
+        }
+    } else {
+        const int b = (int)(r / C);
+        if (keep_pixel(op, b, h, w, H, W)) out = __fsub_rn(xv, __fmul_rn(gamma, __fsub_rn(xv, y[i])));
+    }
+    z[i] = out;
+}
+
+int launch_datafit(const OpDesc& op, const float* x, const float* y, float* z, float gamma, int B, int C, int H, int W,
+                   cudaStream_t st) {
+    const long long n = (long long)B * C * H * W;
+    if (op.kind == 4) {
+        PNPF_REQUIRE(op.scratch, "blur data-fidelity step needs pnpf_operator.scratch");
+        if (int e = launch_blur(op, x, y, op.scratch, B * C, H, W, 1, 0.f, st)) return e;   // r = Gx - y
+        return launch_blur(op, op.scratch, x, z, B * C, H, W, 2, gamma, st);                 // z = x - gamma G r
+    }
+    PNPF_REQUIRE(op.kind >= 0 && op.kind <= 3, "unknown operator kind %d", op.kind);
+    PNPF_REQUIRE(op.kind != 2 || op.mask, "mask operator without a device mask");
+    PNPF_REQUIRE(op.kind != 3 || (op.sf >= 1 && H % op.sf == 0 && W % op.sf == 0), "SR factor %d vs %dx%d", op.sf, H, W);
+    datafit_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, x, y, z, gamma, C, H, W, n);
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// zt[s] = t*z + eps[s]*(1-t): three separately rounded ops like the eager reference (pnp_flow.py:48)
+__global__ void interp_kernel(const float* __restrict__ z, const float* __restrict__ eps, float t, float omt,
+                              float* __restrict__ zt, long long n, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) zt[i] = __fadd_rn(__fmul_rn(t, __ldg(z + i % n)), __fmul_rn(eps[i], omt));
+}
+int launch_interp(const float* z, const float* eps, float t, float* zt, long long n, int S, cudaStream_t st) {
+    const long long total = n * S;
+    interp_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(z, eps, t, 1.0f - t, zt, n, total);
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// x_new = (sum_s (zt_s + (1-t) v_s)) * (1/S), summed in draw order with separately rounded ops (pnp_flow.py:114-121)
+__global__ void push_accum_kernel(const float* __restrict__ zt, const float* __restrict__ v, float omt, int S, float invS,
+                                  float* __restrict__ x_new, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc = __fadd_rn(acc, __fadd_rn(zt[s * n + i], __fmul_rn(omt, v[s * n + i])));
+    x_new[i] = __fmul_rn(acc, invS);
+}
+int launch_push_accum(const float* zt, const float* v, float t, int S, float* x_new, long long n, cudaStream_t st) {
+    PNPF_REQUIRE(S >= 1, "num_samples %d", S);
+    push_accum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(zt, v, 1.0f - t, S, 1.0f / (float)S, x_new, n);
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace pnpf

@@ -1,0 +1,68 @@
+// Internal op layer: prepared (tensor maps encoded once) tensor-core ops and launchers of the SIMT kernels.
+#pragma once
+#include "pnpf_host.h"
+
+namespace pnpf {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ tensor-core ops
+struct TcOp {               // a prepared conv_gemm launch
+    CUtensorMap tmA, tmA2, tmB;
+    GemmParams p;
+    int BK = 0, BN = 0;
+    double flops = 0;       // algorithmic 2*M*N*K (for reporting)
+};
+
+struct ConvDesc {
+    // input: bf16 NHWC [B][Hin][Win][x_pitch], channels [c_base, c_base+Cin) are read
+    const bf16* x = nullptr;
+    int B = 0, Hin = 0, Win = 0, Cin = 0;
+    long long x_pitch = 0;
+    int c_base = 0;
+    // optional second source for a fused 1x1 (extra K) at OUTPUT resolution: bf16 NHWC [B][Hout][Wout][x2_pitch]
+    const bf16* x2 = nullptr;
+    int C2 = 0;
+    long long x2_pitch = 0;
+    // weights: packed bf16 [N_pad][Ktot], Ktot = ksize*ksize*Cin + C2 (pack_conv_weight)
+    const bf16* w = nullptr;
+    int N_pad = 0;
+    int ksize = 3, stride = 1;
+    int Hout = 0, Wout = 0;
+    // epilogue
+    void* out = nullptr;
+    int out_mode = 0;
+    long long out_img_stride = 0, out_row_stride = 0, out_col_stride = 1;
+    int n_valid = 0;
+    const float* bias = nullptr;
+    const float* bias_img = nullptr;
+    long long bias_img_stride = 0;
+    const bf16* residual = nullptr;
+    long long res_img_stride = 0, res_row_stride = 0;
+};
+int prepare_conv(TcOp& op, const ConvDesc& d);
+
+struct GemmDesc {           // out[b][m][n] = sum_k A[b|0][m][k] * Bm[b|0][n][k]  (+bias[n]) (+residual)
+    const bf16* A = nullptr;
+    long long lda = 0, a_bstride = 0;
+    int a_batched = 1;
+    const bf16* Bm = nullptr;
+    long long ldb = 0, b_bstride = 0;
+    int b_batched = 1;
+    int batch = 1, M = 0, N = 0, K = 0;
+    void* out = nullptr;
+    int out_mode = 0;
+    long long out_img_stride = 0, out_row_stride = 0;
+    const float* bias = nullptr;
+    const bf16* residual = nullptr;
+    long long res_img_stride = 0, res_row_stride = 0;
+};
+int prepare_gemm(TcOp& op, const GemmDesc& d);
+int launch_tc(const TcOp& op, cudaStream_t s);
+
+// host-side weight repack: OIHW fp32 (reference layout) -> [N_pad][k*k*Cin_pad + C2] bf16, K ordered (kh, kw, cin),
+// optionally followed by the 1x1 shortcut weights w2 [O][C2]; rows >= O and channels >= Cin are zero.
+void pack_conv_weight(bf16* dst, const float* w, int O, int Cin, int ks, int N_pad, int Cin_pad, const float* w2, int C2,
+                      float scale);
+
+}  // namespace pnpf

@@ -1,0 +1,232 @@
+"""PNP_FLOW: drop-in for the reference's method plugin (pnpflow/methods/pnp_flow.py:10-188) on the sm_100a engine.
+
+Same constructor ``PNP_FLOW(model, device, args)``, same ``run_method / solve_ip`` and the same public helper
+methods and ``args`` keys.  ``model`` may be the reference's ``pnpflow.models.UNet`` module (its
+state_dict is repacked into the engine), an ``oracle``-style ``(cfg, state_dict)`` pair, or a ready ``UNetEngine``.
+
+Per outer step (pnp_flow.py:102-121) the engine runs
+    1. one fused data-fidelity kernel          z = x - gamma_t * A^T(Ax - y)            (:29-45,111-112)
+    2. one interpolation kernel for all S draws  z~_s = t z + (1-t) eps_s               (:47-48)
+    3. ONE U-Net evaluation on the S*B batch    v_s = v_theta(z~_s, t)                  (:19-21)  [CUDA-graph replay]
+    4. one push+average kernel                 x = (1/S) sum_s (z~_s + (1-t) v_s)       (:50-52,114-121)
+The noise eps_s comes from ``torch.randn_like`` in the reference's call order (one call per draw), so a run with the
+same seed consumes the same Philox stream as the reference's GPU path; ``noise=`` injects explicit draws instead.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from time import perf_counter
+from typing import Callable, Iterable, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .degradations import as_engine_operator
+from .engine import UNetEngine
+
+
+def gamma_schedule(lr_pnp: float, t: float, gamma_style: str, alpha: float) -> float:
+    """lr_t / sigma^2 of the reference (pnp_flow.py:29-37 with the sigma^2 of :60-62 cancelled against :41),
+    evaluated in fp32 like the reference's tensor arithmetic."""
+    omt = np.float32(1.0) - np.float32(t)
+    if gamma_style == '1_minus_t':
+        g = omt
+    elif gamma_style == 'sqrt_1_minus_t':
+        g = np.sqrt(omt)
+    elif gamma_style == 'alpha_1_minus_t':
+        g = np.power(omt, np.float32(alpha))
+    else:                                           # 'constant' and unknown styles (dict.get default, :37)
+        g = np.float32(1.0)
+    return float(np.float32(lr_pnp) * np.float32(g))
+
+
+def psnr(rec: torch.Tensor, clean: torch.Tensor) -> torch.Tensor:
+    """Per-image PSNR (dB) on (x+1)/2, data_range 1 — the reference's definition (utils.py:560-577,594-610)."""
+    a = (rec.double() + 1) / 2
+    b = (clean.to(rec.device).double() + 1) / 2
+    return 10 * torch.log10(1.0 / ((a - b) ** 2).flatten(1).mean(dim=1))
+
+
+def restore(engine: UNetEngine, y: torch.Tensor, degradation, sigma_noise: float, *, steps_pnp: int = 100,
+            lr_pnp: float = 1.0, alpha: float = 1.0, gamma_style: str = 'alpha_1_minus_t', num_samples: int = 5,
+            noise_type: str = 'gaussian', noise: Optional[Iterable[torch.Tensor]] = None,
+            trace: Optional[Callable[[int, torch.Tensor], None]] = None, use_cuda_graph: bool = True) -> torch.Tensor:
+    """The T-step PnP-Flow loop for one batch of measurements ``y`` (CUDA fp32); returns the restored x.
+
+    Mirrors pnp_flow.py:93,102-121.  ``noise``: optional iterable of eps tensors [B,C,H,W], one per (step, draw).
+    """
+    if noise_type != 'gaussian':
+        if noise_type == 'laplace':
+            raise NotImplementedError("laplace data term (pnp_flow.py:42-43) is not implemented on the engine yet")
+        raise ValueError('Noise type not supported')                     # pnp_flow.py:45,68,87
+    lib = _lib.load()
+    op = as_engine_operator(degradation)
+    dev = y.device
+    y = y.contiguous().float()
+    x = op.H_adj(torch.ones_like(y))                                       # :93
+    B, Cc, Hh, Ww = x.shape
+    n = x.numel()
+    S = int(num_samples)
+    steps = int(steps_pnp)
+    delta = 1 / steps_pnp
+    noise_it = iter(noise) if noise is not None else None
+    z = torch.empty_like(x)
+    eps = torch.empty((S,) + tuple(x.shape), device=dev)
+    x_new = torch.empty_like(x)
+    if use_cuda_graph:
+        zt, tb, v, replay = engine.graphed(S * B)
+        zt5, v5 = zt.view(S, B, Cc, Hh, Ww), v.view(S, B, Cc, Hh, Ww)
+    else:
+        zt5 = torch.empty_like(eps)
+        v5 = torch.empty_like(eps)
+        tb = torch.empty(S * B, device=dev)
+    sp = _lib.stream_ptr
+    with torch.no_grad(), torch.cuda.device(dev):
+        for it in range(steps):
+            t = float(np.float32(delta * it))                               # :107-108 (python double -> fp32 tensor)
+            gamma = gamma_schedule(lr_pnp, t, gamma_style, alpha)
+            op.datafit_step(x, y, gamma, out=z)
+            for s in range(S):
+                if noise_it is not None:
+                    eps[s].copy_(next(noise_it))
+                else:
+                    eps[s].copy_(torch.randn_like(z))                       # one Philox call per draw, like :48
+            _lib.check(lib.pnpf_interp(z.data_ptr(), eps.data_ptr(), t, zt5.data_ptr(), n, S, sp()))
+            tb.fill_(t)
+            if use_cuda_graph:
+                replay()
+            else:
+                engine.forward(zt5.view(S * B, Cc, Hh, Ww), tb, out=v5.view(S * B, Cc, Hh, Ww))
+            _lib.check(lib.pnpf_push_accum(zt5.data_ptr(), v5.data_ptr(), t, S, x_new.data_ptr(), n, sp()))
+            x, x_new = x_new, x
+            if trace is not None:
+                trace(it, x)
+    return x.clone()
+
+
+class PNP_FLOW(object):
+    """Reference-compatible method plugin (pnp_flow.py:10-188)."""
+
+    def __init__(self, model, device, args):
+        self.device = torch.device(device) if not isinstance(device, torch.device) else device
+        self.args = args
+        self.method = args.method
+        self.coupling = self.args.model
+        if self.coupling not in {"ot", "indep"}:
+            raise ValueError("pnpflow_b200 implements the Flow-Matching U-Net prior (args.model in {'ot','indep'}); "
+                             f"got {self.coupling!r}")
+        if isinstance(model, UNetEngine):
+            self.model = model
+        elif isinstance(model, tuple):
+            self.model = UNetEngine(model[0], model[1], device=self.device)
+        else:
+            self.model = UNetEngine(model, None, device=self.device)
+        self.results = []                     # (clean, noisy, restored) per batch — the reference only writes files
+
+    # ---- public helpers with the reference's signatures -----------------------------------------------------
+    def model_forward(self, x, t):
+        return self.model(x, t)               # pnp_flow.py:19-21 ('ot' / 'indep')
+
+    def learning_rate_strat(self, lr, t):
+        t = t.view(-1, 1, 1, 1)
+        style, a = self.args.gamma_style, self.args.alpha
+        if style == '1_minus_t':
+            return lr * (1 - t)
+        if style == 'sqrt_1_minus_t':
+            return lr * torch.sqrt(1 - t)
+        if style == 'alpha_1_minus_t':
+            return lr * (1 - t) ** a
+        return lr
+
+    def grad_datafit(self, x, y, H, H_adj):
+        if self.args.noise_type == 'gaussian':
+            return H_adj(H(x) - y) / (self.args.sigma_noise ** 2)
+        elif self.args.noise_type == 'laplace':
+            return H_adj(2 * torch.heaviside(H(x) - y, torch.zeros_like(H(x))) - 1) / self.args.sigma_noise
+        else:
+            raise ValueError('Noise type not supported')
+
+    def interpolation_step(self, x, t):
+        eps = torch.randn_like(x)
+        x = x.contiguous()
+        tt = float(t.flatten()[0]) if torch.is_tensor(t) else float(t)
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().pnpf_interp(x.data_ptr(), eps.data_ptr(), tt, out.data_ptr(), x.numel(), 1, _lib.stream_ptr()))
+        return out
+
+    def denoiser(self, x, t):
+        v = self.model_forward(x, t)
+        tt = float(t.flatten()[0])
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().pnpf_push_accum(x.contiguous().data_ptr(), v.data_ptr(), tt, 1, out.data_ptr(), x.numel(),
+                                                   _lib.stream_ptr()))
+        return out
+
+    def should_save_image(self, iteration, steps):
+        return iteration % (steps // 10) == 0
+
+    # ---- the solver ------------------------------------------------------------------------------------------
+    def solve_ip(self, test_loader, degradation, sigma_noise, H_funcs=None):
+        a = self.args
+        a.sigma_noise = sigma_noise
+        if a.noise_type == 'gaussian':
+            lr_eff = a.lr_pnp                       # gamma_t = lr_pnp (1-t)^alpha: sigma^2 cancels (:41 vs :61)
+            a.lr_pnp = sigma_noise ** 2 * a.lr_pnp  # keep the reference's observable side effect on args (:61)
+        elif a.noise_type == 'laplace':
+            raise NotImplementedError("laplace data term (pnp_flow.py:42-43,64-66) is not implemented on the engine yet")
+        else:
+            raise ValueError('Noise type not supported')
+        op = as_engine_operator(degradation)
+        loader = iter(test_loader)
+        times = []
+        for batch in range(a.max_batch):
+            (clean_img, labels) = next(loader)
+            a.batch = batch
+            clean_dev = clean_img.clone().to(self.device).float()
+            noisy_img = op.H(clean_dev)
+            torch.manual_seed(batch)                                         # :79
+            noisy_img = noisy_img + torch.randn_like(noisy_img) * sigma_noise
+            if getattr(a, 'compute_time', False):
+                torch.cuda.synchronize()
+                t0 = perf_counter()
+            if getattr(a, 'compute_memory', False):
+                torch.cuda.reset_peak_memory_stats(self.device)
+            x = restore(self.model, noisy_img, op, sigma_noise, steps_pnp=a.steps_pnp, lr_pnp=lr_eff, alpha=a.alpha,
+                        gamma_style=a.gamma_style, num_samples=a.num_samples, noise_type=a.noise_type)
+            if getattr(a, 'compute_time', False):
+                torch.cuda.synchronize()
+                times.append(perf_counter() - t0)
+                self._append_stat('time_stats.txt', {"batch": batch, "time_per_batch": times[-1]})
+            if getattr(a, 'compute_memory', False):
+                self._append_stat('memory_stats.txt', {"batch": batch, "max_allocated": torch.cuda.max_memory_allocated(self.device)})
+            self.results.append((clean_img.cpu(), noisy_img.cpu(), x.cpu()))
+            if getattr(a, 'save_results', False):
+                p = psnr(x, clean_dev).cpu()
+                self._append_lines(f'psnr_rec_batch{batch}.txt', [f'{v:.6f}' for v in p.tolist()])
+        return self.results
+
+    def _append_stat(self, fname, d):
+        path = getattr(self.args, 'save_path_ip', None)
+        if path:
+            os.makedirs(path, exist_ok=True)
+            with open(os.path.join(path, fname), "a") as f:
+                f.write(str(d) + '\n')
+
+    def _append_lines(self, fname, lines):
+        path = getattr(self.args, 'save_path_ip', None)
+        if path:
+            os.makedirs(path, exist_ok=True)
+            with open(os.path.join(path, fname), "a") as f:
+                f.write('\n'.join(lines) + '\n')
+
+    def run_method(self, data_loaders, degradation, sigma_noise, H_funcs=None):
+        folder = ""
+        for key, value in getattr(self.args, 'dict_cfg_method', {}).items():      # utils.py:1112-1120
+            folder = os.path.join(folder, f"{key}={value}")
+        self.args.save_path_ip = os.path.join(self.args.save_path, folder)
+        os.makedirs(self.args.save_path_ip, exist_ok=True)
+        return self.solve_ip(data_loaders[self.args.eval_split], degradation, sigma_noise, H_funcs)

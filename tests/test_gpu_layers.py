@@ -1,0 +1,94 @@
+"""GPU parity of the tcgen05 implicit-GEMM kernel (through the C ABI) against torch fp32 conv2d / bmm on the same
+bf16-rounded operands.  Inputs and weights are exactly representable in bf16, so the only differences are the fp32
+accumulation order (and bf16 rounding of the output when out is bf16)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from pnpflow_b200 import _lib
+    return _lib.load(), _lib
+
+
+def _conv_case(B, H, W, Cin, Cout, k, s, C2=0, res=False, bf16out=False, seed=0):
+    lib, L = _lib()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(seed)
+    dev = "cuda"
+    x = torch.randn(B, Cin, H, W, generator=g).to(dev).bfloat16()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).bfloat16().float().contiguous()
+    b = torch.randn(Cout, generator=g).contiguous()
+    Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    x2n = w2 = rn = None
+    ref = F.conv2d(x.float(), w.to(dev), b.to(dev), stride=s, padding=k // 2)
+    if C2:
+        x2 = torch.randn(B, C2, Ho, Wo, generator=g).to(dev).bfloat16()
+        w2 = (torch.randn(Cout, C2, 1, 1, generator=g) / C2 ** 0.5).bfloat16().float().contiguous()
+        x2n = x2.permute(0, 2, 3, 1).contiguous()
+        ref = ref + F.conv2d(x2.float(), w2.to(dev))
+    if res:
+        r = torch.randn(B, Cout, Ho, Wo, generator=g).to(dev).bfloat16()
+        rn = r.permute(0, 2, 3, 1).contiguous()
+        ref = ref + r.float()
+    out = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.bfloat16 if bf16out else torch.float32)
+    L.check(lib.pnpf_conv2d_nhwc(xn.data_ptr(), B, H, W, Cin, w.data_ptr(), b.data_ptr(), Cout, k, s,
+                                 x2n.data_ptr() if C2 else None, C2, w2.data_ptr() if C2 else None,
+                                 rn.data_ptr() if res else None, out.data_ptr(), 0 if bf16out else 1, None))
+    got = out.float().permute(0, 3, 1, 2)
+    tol = 3e-2 if bf16out else 2e-3
+    err = (got - ref).abs().max().item()
+    assert err < tol, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s", [
+    (1, 16, 16, 64, 64, 1, 1), (2, 16, 16, 64, 64, 3, 1), (1, 128, 128, 32, 32, 3, 1), (2, 64, 64, 96, 64, 3, 1),
+    (2, 32, 32, 256, 256, 3, 1), (2, 16, 16, 512, 256, 3, 1), (1, 64, 64, 32, 16, 3, 1), (1, 256, 256, 32, 32, 3, 1),
+    (2, 16, 16, 256, 512, 1, 1),
+])
+def test_conv_stride1(B, H, W, Cin, Cout, k, s):
+    _conv_case(B, H, W, Cin, Cout, k, s)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 32, 64, 64), (1, 256, 256, 32, 32), (2, 64, 64, 128, 128)])
+def test_conv_stride2(B, H, W, Cin, Cout):
+    _conv_case(B, H, W, Cin, Cout, 3, 2)
+
+
+def test_conv_ragged_edges():
+    _conv_case(2, 28, 28, 32, 32, 3, 1)
+    _conv_case(2, 14, 14, 64, 64, 3, 1)
+
+
+def test_conv_fused_shortcut_residual_bf16():
+    _conv_case(2, 32, 32, 128, 128, 3, 1, C2=192, res=True, bf16out=True)
+    _conv_case(2, 64, 64, 32, 32, 3, 1, C2=96)
+    _conv_case(2, 32, 32, 64, 64, 3, 1, res=True)
+
+
+@pytest.mark.parametrize("batch,M,N,K", [(1, 128, 64, 64), (2, 256, 256, 256), (2, 256, 512, 128), (3, 1024, 1024, 256), (2, 64, 256, 64)])
+def test_gemm_nt(batch, M, N, K):
+    lib, L = _lib()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn(batch, M, K, generator=g).cuda().bfloat16()
+    Bm = torch.randn(batch, N, K, generator=g).cuda().bfloat16()
+    out = torch.full((batch, M, N), float("nan"), device="cuda")
+    L.check(lib.pnpf_gemm_nt(A.data_ptr(), Bm.data_ptr(), out.data_ptr(), batch, M, N, K, 1, None))
+    ref = torch.bmm(A.float(), Bm.float().transpose(1, 2))
+    assert (out - ref).abs().max().item() < 2e-3 * K ** 0.5
+
+
+def test_unsupported_shape_is_an_error_not_a_fallback():
+    lib, L = _lib()
+    x = torch.zeros(1, 8, 8, 24, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(16, 24, 3, 3)
+    out = torch.zeros(1, 8, 8, 16, device="cuda")
+    rc = lib.pnpf_conv2d_nhwc(x.data_ptr(), 1, 8, 8, 24, w.data_ptr(), None, 16, 3, 1, None, 0, None, None, out.data_ptr(), 1, None)
+    assert rc != 0 and b"multiples of 32" in lib.pnpf_last_error()

@@ -1,0 +1,111 @@
+"""GPU parity of the per-pixel PnP kernels and of the whole restoration loop against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import make_golden as mg
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _ops():
+    import pnpflow_b200 as P
+    return {
+        'denoising': (P.Denoising(), oracle.Denoising()),
+        'box': (P.BoxInpainting(10), oracle.BoxInpainting(10)),
+        'random': (P.RandomInpainting(0.7), oracle.RandomInpainting(0.7)),
+        'paintbrush': (P.PaintbrushInpainting(), oracle.PaintbrushInpainting()),
+        'blur': (P.GaussianDeblurring(1.0, 61, "fft", 3, 64, "cuda"), oracle.GaussianDeblurring(1.0, 61, "fft", 3, 64, "cpu")),
+        'sr2': (P.Superresolution(2, 64), oracle.Superresolution(2, 64)),
+    }
+
+
+def test_operators_match_reference_golden():
+    ref = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, "operators_64.npz")).items()}
+    x = mg.operator_input().cuda()
+    for name, (eng, _) in _ops().items():
+        y = eng.H(x)
+        z = eng.H_adj(y)
+        tol = 2e-6 if name == 'blur' else 0.0        # separable fp32 conv vs the reference's FFT
+        assert (y.cpu() - ref[name + "_H_ref"]).abs().max() <= tol, name
+        assert (z.cpu() - ref[name + "_Hadj_ref"]).abs().max() <= 2 * tol, name
+
+
+def test_datafit_interp_push_vs_oracle():
+    from pnpflow_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    sigma, lr_pnp, alpha, t = 0.05, 1.0, 0.5, 0.37
+    for name, (eng, orc) in _ops().items():
+        y = orc.H(x) + 0.05 * torch.randn(orc.H(x).shape, generator=g)
+        t1 = torch.ones(2) * t
+        lr_t = oracle.learning_rate(sigma ** 2 * lr_pnp, t1, 'alpha_1_minus_t', alpha)
+        z_ref = x - lr_t * oracle.loop.grad_datafit(x, y, orc.H, orc.H_adj, sigma)
+        import pnpflow_b200 as P
+        z = eng.datafit_step(x.cuda(), y.float().cuda(), P.gamma_schedule(lr_pnp, t, 'alpha_1_minus_t', alpha))
+        assert (z.cpu() - z_ref).abs().max() < (5e-6 if name == 'blur' else 2e-6), name
+    S, n = 3, x.numel()
+    z = x.cuda()
+    eps = torch.randn(S, *x.shape, generator=g).cuda()
+    zt = torch.empty_like(eps)
+    _lib.check(lib.pnpf_interp(z.data_ptr(), eps.data_ptr(), t, zt.data_ptr(), n, S, None))
+    tb = torch.full((2, 1, 1, 1), t).cuda()
+    for s in range(S):
+        assert torch.equal(zt[s], tb * z + eps[s] * (1 - tb))               # bit-exact vs eager torch
+    v = torch.randn(S, *x.shape, generator=g).cuda()
+    out = torch.empty_like(z)
+    _lib.check(lib.pnpf_push_accum(zt.data_ptr(), v.data_ptr(), t, S, out.data_ptr(), n, None))
+    acc = torch.zeros_like(z)
+    for s in range(S):
+        acc += zt[s] + (1 - tb) * v[s]
+    acc /= S
+    assert (out - acc).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("problem,alpha", [("box", 0.5), ("random", 0.01), ("sr2", 0.3), ("blur", 0.01), ("paintbrush", 0.5), ("denoising", 0.8)])
+def test_loop_vs_oracle_injected_noise(problem, alpha):
+    """10 steps x 2 draws on a small 64x64 net, identical y / weights / noise: final x and PSNR agree."""
+    import pnpflow_b200 as P
+    cfg = oracle.UNetConfig(3, 64, 32, (1, 2), 1, (16,))
+    sd = oracle.init_state_dict(cfg, seed=2)
+    eng_op, orc_op = _ops()[problem]
+    g = torch.Generator().manual_seed(77)
+    clean = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    y = oracle.loop.synthesize_measurement(clean, orc_op.H, 0.05, 0).float()
+    T, S = 10, 2
+    noise = [torch.randn(2, 3, 64, 64, generator=g) for _ in range(T * S)]
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x_ref = oracle.pnp_flow_restore(lambda a, b: oracle.unet_forward(sd, cfg, a, b), y, orc_op, 0.05,
+                                    steps_pnp=T, num_samples=S, alpha=alpha, noise=noise)
+    eng = P.UNetEngine(cfg, sd, max_batch=2 * S)
+    for graph in (False, True):
+        x = P.restore(eng, y.cuda(), eng_op, 0.05, steps_pnp=T, num_samples=S, alpha=alpha,
+                      noise=[n.cuda() for n in noise], use_cuda_graph=graph).cpu()
+        rel = ((x - x_ref).norm() / x_ref.norm()).item()
+        dpsnr = (oracle.psnr(x, clean) - oracle.psnr(x_ref, clean)).abs().max().item()
+        assert rel < 1e-2, (problem, graph, rel)
+        assert dpsnr < 0.01, (problem, graph, dpsnr)
+
+
+def test_method_plugin_surface():
+    """PNP_FLOW(model, device, args).run_method(loaders, degradation, sigma) like main.py:197-212."""
+    import pnpflow_b200 as P
+    from oracle.ref_shim import RefArgs
+    cfg = oracle.UNetConfig(3, 64, 32, (1, 2), 1, (16,))
+    sd = oracle.init_state_dict(cfg, seed=2)
+    args = RefArgs(steps_pnp=10, num_samples=2, alpha=0.5, dim_image=64, save_path='/tmp/pnpflow_b200_test', max_batch=2)
+    m = P.PNP_FLOW((cfg, sd), torch.device('cuda'), args)
+    g = torch.Generator().manual_seed(5)
+    loader = [(torch.rand(2, 3, 64, 64, generator=g) * 2 - 1, torch.zeros(2)) for _ in range(2)]
+    res = m.run_method({'test': loader}, P.BoxInpainting(10), 0.05)
+    assert len(res) == 2 and res[0][2].shape == (2, 3, 64, 64)
+    assert abs(args.lr_pnp - 0.05 ** 2) < 1e-12           # reference side effect on args (pnp_flow.py:61)
+    args.noise_type = 'poisson'
+    with pytest.raises(ValueError, match='Noise type not supported'):
+        m.solve_ip(loader, P.BoxInpainting(10), 0.05)
