@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — restored images/sec of the PnP-Flow hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--config cfg4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is ONE outer PnP-Flow iteration (pnp_flow.py:107-121: data-fidelity step + S x (noise draw, interpolate,
+U-Net velocity, Euler push) + MC average) over the per-GPU batch of synthetic measurements.  Restoring an image
+costs T such steps, so   images/sec = (N * B_per_gpu) / (T * seconds_per_step).
+Workload at every N: cfg4 of BASELINE.json (AFHQ-Cat 256x256x3, 4x super-resolution, T=100, S=5 MC draws, the
+reference default of config/method_config/pnp_flow.yaml), 16 images per GPU (128 over 8) -> weak scaling.
+
+engine arm:      pnpflow_b200 (hand-written sm_100a CUDA behind the C ABI), bf16 tensor-core operands / fp32 accumulate.
+reference arm:   the reference algorithm on the host CPU cores (oracle port; the reference itself is pure PyTorch and
+                 its tree does not exist on the GPU box), rank 0 only, a bounded sample extrapolated linearly.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: net, problem, images per GPU, T, S, sigma, alpha   (BASELINE.json configs 2-5; main.py:120-179 constants)
+    "cfg2": dict(net="celeba128", problem="inpainting", b_per_gpu=64, T=100, S=5, sigma=0.05, alpha=0.5),
+    "cfg3": dict(net="celeba128", problem="gaussian_deblurring_FFT", b_per_gpu=32, T=100, S=5, sigma=0.05, alpha=0.01),
+    "cfg4": dict(net="afhq256", problem="superresolution", b_per_gpu=16, T=100, S=5, sigma=0.05, alpha=0.3),
+    "cfg5": dict(net="afhq256", problem="random_inpainting", b_per_gpu=32, T=200, S=5, sigma=0.01, alpha=0.01),
+}
+METRIC = "restored images/sec at 100 PnP steps, 256x256x3"
+UNIT = "images/s"
+
+
+def make_operator(P, problem, side):
+    if problem == "inpainting":
+        return P.BoxInpainting(20 if side == 128 else 40)
+    if problem == "random_inpainting":
+        return P.RandomInpainting(0.7)
+    if problem == "superresolution":
+        return P.Superresolution(2 if side == 128 else 4, side)
+    if problem == "gaussian_deblurring_FFT":
+        return P.GaussianDeblurring(1.0 if side == 128 else 3.0, 61, "fft", 3, side)
+    if problem == "denoising":
+        return P.Denoising()
+    raise KeyError(problem)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(float(r[0])) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [int(float(r[1])) for r in self.rows if r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(self.rows), reasons=sorted(reasons))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d.get("bf16_tflops_sustained", d.get("bf16_tflops")), hbm=d.get("hbm_gbs"), src="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm (the oracle port of the reference algorithm) — the only place bench.py executes oracle/
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference(cfgname, steps, warmup):
+    import oracle
+    c = CONFIGS[cfgname]
+    ocfg = oracle.AFHQ_256 if c["net"] == "afhq256" else oracle.CELEBA_128
+    side = ocfg.input_height
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    sd = oracle.init_state_dict(ocfg, seed=0)
+    deg, sigma, alpha = oracle.make_degradation(c["problem"], side, 3, "cpu")
+    Bs = 2 if side == 256 else 4                      # bounded sample
+    g = torch.Generator().manual_seed(1234)
+    clean = torch.rand(Bs, 3, side, side, generator=g) * 2 - 1
+    y = oracle.loop.synthesize_measurement(clean, deg.H, sigma, 0)
+    times = []
+
+    def trace(it, x):
+        times.append(time.perf_counter())
+
+    t0 = time.perf_counter()
+    times.append(t0)
+    # steps_pnp=T keeps t = it/T small like the first iterations of the real run; only warmup+steps iterations execute
+    class _Stop(Exception):
+        pass
+
+    def trace2(it, x):
+        trace(it, x)
+        if it + 1 >= warmup + steps:
+            raise _Stop()
+    try:
+        oracle.pnp_flow_restore(lambda a, b: oracle.unet_forward(sd, ocfg, a, b), y, deg, sigma, steps_pnp=c["T"],
+                                num_samples=c["S"], alpha=alpha, trace=trace2)
+    except _Stop:
+        pass
+    per_step = (times[-1] - times[warmup]) / steps
+    value = Bs / (c["T"] * per_step)
+    sample = (f"{steps} PnP steps (after {warmup} warm-up) of {cfgname} at batch {Bs} with S={c['S']} on the host CPU, "
+              f"extrapolated linearly to T={c['T']} steps")
+    return dict(value=value, per_step_s=per_step, cores=cores, sample=sample, batch=Bs)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    a = ap.parse_args()
+    K, W = a.steps, max(a.warmup, 3 if a.impl == "engine" else 1)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    c = CONFIGS[a.config]
+    cfg_desc = {"workload": f"{a.config}: {c['net']} {c['problem']} T={c['T']} S={c['S']} {c['b_per_gpu']} images/GPU",
+                "global_batch": c["b_per_gpu"] * max(world, a.gpus if world == 1 else world), "parallelism": f"batch-sharded dp{world}",
+                "l2": "per-step working set (activations of the S*B U-Net batch, GBs) >> 126 MB L2; no explicit flush"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference(a.config, max(1, min(K, a.cpu_steps)), 1)   # bounded sample: <= cpu_steps CPU steps
+        line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": K, "warmup": W,
+                "ms_per_step": r["per_step_s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "impl": "reference", "config": cfg_desc,
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch.distributed as dist
+    import pnpflow_b200 as P
+    from pnpflow_b200 import sharding, synth
+    assert torch.cuda.is_available(), "engine arm needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    net = synth.NETS[c["net"]]
+    side, B, S, T = net["input_height"], c["b_per_gpu"], c["S"], c["T"]
+    Btot = B * world
+    sd = synth.random_state_dict(net, seed=0)
+    eng = P.UNetEngine(net, sd, device=dev, max_batch=S * B)
+    op_full = make_operator(P, c["problem"], side)
+    lo, hi = sharding.shard_bounds(Btot, world, rank)
+    op = sharding.shard_operator(op_full, lo, hi, Btot)
+    # measurements: rank 0 synthesises the full batch on its GPU and scatters the shards over NCCL (outside the timed region)
+    if rank == 0:
+        clean = synth.synthetic_clean(Btot, 3, side, 1234 + 4).to(dev)
+        y_full = op_full.H(clean)
+        torch.manual_seed(0)
+        y_full = y_full + torch.randn_like(y_full) * c["sigma"]
+        y_shape = tuple(y_full.shape)
+    else:
+        y_full = None
+        y_shape = None
+    if world > 1:
+        obj = [y_shape]
+        dist.broadcast_object_list(obj, src=0)
+        y_shape = obj[0]
+        t_sc0 = time.perf_counter()
+        y = sharding.scatter_batch(y_full, y_shape, torch.float32, dev)
+        torch.cuda.synchronize()
+        scatter_ms = (time.perf_counter() - t_sc0) * 1e3
+    else:
+        y, scatter_ms = y_full, 0.0
+    sess = P.PnPFlowSession(eng, op, tuple(y.shape), steps_pnp=T, lr_pnp=1.0, alpha=c["alpha"], num_samples=S, device=dev)
+    torch.manual_seed(1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (value) ----------------
+    x = sess.initial_state(y)
+    for i in range(W):
+        x = sess.step(x, y, i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        x = sess.step(x, y, W + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    ms_per_step = ms / K
+    value = Btot / (T * ms_per_step / 1e3)
+    finite = bool(torch.isfinite(x).all())
+
+    # ---------------- end-to-end through the public API with HOST buffers (e2e) ----------------
+    y_host = y.cpu().pin_memory()
+    x_host = torch.empty(sess.shape, dtype=torch.float32).pin_memory()
+    y_dev = torch.empty_like(y)
+    xe = sess.initial_state(y)
+    for i in range(3):
+        y_dev.copy_(y_host, non_blocking=True)
+        xe = sess.step(xe, y_dev, i)
+        x_host.copy_(xe, non_blocking=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        y_dev.copy_(y_host, non_blocking=True)          # H2D of the step's input (pinned)
+        xe = sess.step(xe, y_dev, 3 + i)
+        x_host.copy_(xe, non_blocking=True)             # D2H of the step's result
+    e1.record()
+    barrier()
+    ms_e = e0.elapsed_time(e1)
+    if world > 1:
+        tms = torch.tensor([ms_e], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms_e = float(tms.item())
+    e2e_value = Btot / (T * (ms_e / K) / 1e3)
+    if world > 1:
+        t_g0 = time.perf_counter()
+        full = sharding.gather_batch(x, Btot)
+        torch.cuda.synchronize()
+        gather_ms = (time.perf_counter() - t_g0) * 1e3
+        assert full.shape[0] == Btot
+    else:
+        gather_ms = 0.0
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel class (tcgen05 implicit-GEMM), per-op CUDA events ----------------
+    prof = eng.profile(S * B)
+    tc = [o for o in prof if o["kind"] == "tc"]
+    simt = [o for o in prof if o["kind"] == "simt"]
+    tc_ms, tc_fl = sum(o["ms"] for o in tc), sum(o["flops"] for o in tc)
+    simt_ms, simt_by = sum(o["ms"] for o in simt), sum(o["bytes"] for o in simt)
+    pk = peaks()
+    ach = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_conv_gemm_dram_bytes.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch_mean")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<BK,BN> (all tensor-core launches of one U-Net evaluation)",
+                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"] if pk["tflops"] else None,
+                "traffic": traffic, "peak_source": pk["src"], "launches": len(tc),
+                "flops_per_eval_batch": tc_fl, "tc_ms_per_eval": tc_ms, "tc_share_of_eval": tc_ms / (tc_ms + simt_ms) if tc_ms + simt_ms > 0 else None,
+                "simt": {"achieved_gbs": simt_by / (simt_ms * 1e-3) / 1e9 if simt_ms > 0 else None, "peak_gbs": pk["hbm"],
+                         "ms_per_eval": simt_ms, "algorithmic_bytes": simt_by},
+                "whole_step_conv_gemm_frac": (value * T * S * eng.flops_per_image / world) / (pk["tflops"] * 1e12) if pk["tflops"] else None}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        r = cpu_reference(a.config, a.cpu_steps, 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "impl": "engine", "config": cfg_desc, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": y_host.numel() * 4, "d2h_bytes_per_step": x_host.numel() * 4,
+                    "ms_per_step": ms_e / K},
+            "gpu_launches": K * sess.launches_per_step, "roofline": roofline, "cpu_baseline": cpu,
+            "finite": finite, "unet_flops_per_image": eng.flops_per_image, "unet_launches_per_eval": eng.num_launches,
+            "scatter_ms": scatter_ms, "gather_ms": gather_ms, "workspace_gb": eng.workspace_bytes / 2 ** 30}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,7 @@ int pnpf_load_weight(pnpf_engine* e, const char* name, const float* host_data, c
 /* Number of state_dict entries the plan expects, and the i-th expected name (for the loader / tests). */
 int pnpf_num_weights(pnpf_engine* e);
 const char* pnpf_weight_name(pnpf_engine* e, int i);
+int pnpf_weight_shape(pnpf_engine* e, int i, int64_t shape[4], int* ndim);
 /* Repack all loaded weights to the engine layout (bf16 K-major GEMM operands, folded attention scale/bias)
  * and upload them.  Fails if any expected entry is missing.  Synchronous (allocates device memory). */
 int pnpf_finalize_weights(pnpf_engine* e);
@@ -77,6 +78,11 @@ const char* pnpf_debug_op_name(pnpf_engine* e, int i);
 int pnpf_debug_forward_partial(pnpf_engine* e, const float* x, const float* t, int batch, int n_ops, void* stream);
 /* copies op i's output as fp32 NCHW [batch,C,H,W] into dst (device); writes C,H,W to dims[3] */
 int pnpf_debug_read_op_output(pnpf_engine* e, int i, int batch, float* dst, size_t dst_elems, int dims[3], void* stream);
+/* per-op accounting (per image): kind 1 = tensor-core conv/GEMM op, 0 = SIMT; algorithmic FLOPs and HBM bytes */
+int pnpf_debug_op_info(pnpf_engine* e, int i, int* kind, double* flops, double* bytes);
+/* one forward with CUDA events around every op: host_ms[n], n == pnpf_debug_num_ops(). Synchronous (bench/roofline). */
+int pnpf_profile_forward(pnpf_engine* e, const float* x, const float* t, float* v, int batch, float* host_ms, int n,
+                         void* stream);
 double pnpf_unet_flops_per_image(pnpf_engine* e);  /* algorithmic 2*MAC of all tensor-core ops, per image */
 int pnpf_unet_num_launches(pnpf_engine* e);        /* kernels launched by one pnpf_unet_forward */
 

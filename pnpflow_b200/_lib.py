@@ -37,6 +37,7 @@ SYMBOLS = {
     "pnpf_load_weight": (_I, [_VP, C.c_char_p, _VP, C.POINTER(C.c_int64), _I]),
     "pnpf_num_weights": (_I, [_VP]),
     "pnpf_weight_name": (C.c_char_p, [_VP, _I]),
+    "pnpf_weight_shape": (_I, [_VP, _I, C.POINTER(C.c_int64 * 4), C.POINTER(_I)]),
     "pnpf_finalize_weights": (_I, [_VP]),
     "pnpf_workspace_bytes": (_SZ, [_VP, _I]),
     "pnpf_bind_workspace": (_I, [_VP, _VP, _SZ, _I]),
@@ -45,6 +46,8 @@ SYMBOLS = {
     "pnpf_debug_op_name": (C.c_char_p, [_VP, _I]),
     "pnpf_debug_forward_partial": (_I, [_VP, _VP, _VP, _I, _I, _VP]),
     "pnpf_debug_read_op_output": (_I, [_VP, _I, _I, _VP, _SZ, C.POINTER(C.c_int * 3), _VP]),
+    "pnpf_debug_op_info": (_I, [_VP, _I, C.POINTER(_I), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "pnpf_profile_forward": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _I, _VP]),
     "pnpf_unet_flops_per_image": (C.c_double, [_VP]),
     "pnpf_unet_num_launches": (_I, [_VP]),
     "pnpf_apply_H": (_I, [C.POINTER(OperatorC), _VP, _VP, _I, _I, _I, _I, _VP]),

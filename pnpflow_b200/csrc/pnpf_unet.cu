@@ -56,6 +56,8 @@ struct Op {
     int L = 0;
     const bf16* up_src = nullptr; // upsample
     int up_side = 0, up_C = 0;
+    double flops = 0;             // algorithmic 2*MAC per image (tensor-core ops)
+    double bytes = 0;             // algorithmic HBM bytes per image: every operand read once + every output written once
     // debug view of the output (bf16 NHWC), C == 0 -> not readable
     const bf16* out_p = nullptr;
     int out_C = 0, out_side = 0;
@@ -231,6 +233,13 @@ extern "C" void pnpf_destroy(pnpf_engine* e) {
 extern "C" int pnpf_num_weights(pnpf_engine* e) { return e ? (int)e->weights.size() : 0; }
 extern "C" const char* pnpf_weight_name(pnpf_engine* e, int i) {
     return (e && i >= 0 && i < (int)e->weights.size()) ? e->weights[i].name.c_str() : nullptr;
+}
+
+extern "C" int pnpf_weight_shape(pnpf_engine* e, int i, int64_t shape[4], int* ndim) {
+    PNPF_REQUIRE(e && shape && ndim && i >= 0 && i < (int)e->weights.size(), "bad argument");
+    *ndim = (int)e->weights[i].shape.size();
+    for (int k = 0; k < *ndim && k < 4; ++k) shape[k] = e->weights[i].shape[k];
+    return 0;
 }
 
 extern "C" int pnpf_load_weight(pnpf_engine* e, const char* name, const float* host_data, const int64_t* shape, int ndim) {
@@ -515,11 +524,13 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
         double* st = new_stats(C);
         Op s;
         s.kind = Op::GN_STATS; s.name = name + ".stats"; s.gsrc = src; s.HW = side * side; s.stats = st;
+        s.bytes = 2.0 * C * side * side;
         ops.push_back(s);
         Op a;
         a.kind = Op::GN_APPLY; a.name = name; a.gsrc = src; a.HW = side * side; a.stats = st;
         if (real) { a.gamma = wptr<float>(e, wname + ".gamma"); a.beta = wptr<float>(e, wname + ".beta"); }
         a.silu = silu; a.dst = dst; a.raw_dst = raw;
+        a.bytes = (raw ? 6.0 : 4.0) * C * side * side;
         set_out(a, dst, C, side);
         ops.push_back(a);
     };
@@ -528,7 +539,11 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
         o.kind = Op::TC; o.name = name;
         d.B = Bm;
         if (real) { if (int rc = prepare_conv(o.tc, d)) return rc; }
-        flops += 2.0 * d.Hout * d.Wout * (double)d.n_valid * ((double)d.ksize * d.ksize * d.Cin + (d.x2 ? d.C2 : 0));
+        o.flops = 2.0 * d.Hout * d.Wout * (double)d.n_valid * ((double)d.ksize * d.ksize * d.Cin + (d.x2 ? d.C2 : 0));
+        o.bytes = 2.0 * d.Hin * d.Win * d.Cin + (d.x2 ? 2.0 * d.Hout * d.Wout * d.C2 : 0.0) +
+                  (d.residual ? 2.0 * d.Hout * d.Wout * d.n_valid : 0.0) +
+                  (d.out_mode == 0 ? 2.0 : 4.0) * d.Hout * d.Wout * d.n_valid;
+        flops += o.flops;
         if (dbg_out) set_out(o, dbg_out, dbg_C, dbg_side);
         ops.push_back(o);
         return 0;
@@ -538,13 +553,17 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
         o.kind = Op::TC; o.name = name;
         d.batch = Bm;
         if (real) { if (int rc = prepare_gemm(o.tc, d)) return rc; }
-        flops += 2.0 * (double)d.M * d.N * d.K;
+        o.flops = 2.0 * (double)d.M * d.N * d.K;
+        o.bytes = 2.0 * ((double)d.M * d.K * (d.a_batched ? 1 : 0) + (double)d.N * d.K * (d.b_batched ? 1 : 0)) +
+                  (d.out_mode == 0 ? 2.0 : 4.0) * d.M * d.N;
+        flops += o.flops;
         ops.push_back(o);
         return 0;
     };
 
     { Op o; o.kind = Op::MEMSET; o.name = "zero_gn_stats"; ops.push_back(o); }
-    { Op o; o.kind = Op::IN_SHIM; o.name = "input_nchw_to_nhwc"; set_out(o, in_nhwc, CIN_PAD, side0); ops.push_back(o); }
+    { Op o; o.kind = Op::IN_SHIM; o.name = "input_nchw_to_nhwc"; o.bytes = (4.0 * c.input_channels + 2.0 * CIN_PAD) * side0 * side0;
+      set_out(o, in_nhwc, CIN_PAD, side0); ops.push_back(o); }
     { Op o; o.kind = Op::TEMB; o.name = "time_embedding"; ops.push_back(o); }
 
     std::vector<Act> hs;
@@ -629,6 +648,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 {
                     Op o;
                     o.kind = Op::SOFTMAX; o.name = p + ".softmax"; o.S = t_S; o.P = t_P; o.rows_per_img = Lk; o.L = Lk;
+                    o.bytes = 6.0 * Lk * Lk;
                     ops.push_back(o);
                 }
                 GemmDesc go;                                   // O[b] (L x C) = P[b] (L x L) * V^T[b]^T
@@ -665,6 +685,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 {
                     Op o;
                     o.kind = Op::UPSAMPLE; o.name = p + ".nearest2x"; o.up_src = h.p; o.up_side = side; o.up_C = L.in_ch; o.dst = t_up;
+                    o.bytes = 10.0 * L.in_ch * side * side;
                     set_out(o, t_up, L.in_ch, so);
                     ops.push_back(o);
                 }
@@ -808,3 +829,43 @@ extern "C" int pnpf_debug_read_op_output(pnpf_engine* e, int i, int batch, float
 }
 extern "C" double pnpf_unet_flops_per_image(pnpf_engine* e) { return e ? e->flops_per_img : 0.0; }
 extern "C" int pnpf_unet_num_launches(pnpf_engine* e) { return e ? (int)e->ops.size() : 0; }
+
+// Per-op device time of one forward, CUDA events on `stream` around every op (synchronous; not graph-capturable).
+extern "C" int pnpf_profile_forward(pnpf_engine* e, const float* x, const float* t, float* v, int batch, float* host_ms,
+                                    int n, void* stream) {
+    PNPF_REQUIRE(e && host_ms && n == (int)e->ops.size(), "host_ms must hold pnpf_debug_num_ops() floats");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& q : ev) PNPF_CHECK_CUDA(cudaEventCreate(&q));
+    int rc = 0;
+    PNPF_CHECK_CUDA(cudaEventRecord(ev[0], st));
+    // run op by op through the same dispatcher (n_ops = i+1 would re-run the prefix, so replicate the loop here)
+    for (int i = 0; i < n && !rc; ++i) {
+        std::vector<Op> one(1, e->ops[i]);
+        std::swap(one, e->ops);
+        const int end_saved = e->end_op;
+        e->end_op = (i == end_saved) ? 0 : -1;
+        rc = run_ops(e, x, t, v, batch, 1, st);
+        e->end_op = end_saved;
+        std::swap(one, e->ops);
+        cudaEventRecord(ev[i + 1], st);
+    }
+    cudaError_t err = cudaStreamSynchronize(st);
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        if (!rc && err == cudaSuccess) cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        host_ms[i] = ms;
+    }
+    for (auto& q : ev) cudaEventDestroy(q);
+    if (rc) return rc;
+    PNPF_CHECK_CUDA(err);
+    return 0;
+}
+// kind: 1 = tensor-core (conv_gemm) op, 0 = SIMT / memset; flops and algorithmic HBM bytes are PER IMAGE
+extern "C" int pnpf_debug_op_info(pnpf_engine* e, int i, int* kind, double* flops, double* bytes) {
+    PNPF_REQUIRE(e && i >= 0 && i < (int)e->ops.size() && kind && flops && bytes, "bad argument");
+    *kind = e->ops[i].kind == Op::TC ? 1 : 0;
+    *flops = e->ops[i].flops;
+    *bytes = e->ops[i].bytes;
+    return 0;
+}

@@ -144,6 +144,29 @@ class UNetEngine:
     def num_launches(self) -> int:
         return int(self.lib.pnpf_unet_num_launches(self._h))
 
+    def profile(self, batch: int):
+        """One forward with CUDA events around every op.  Returns a list of dicts
+        {name, kind ('tc'|'simt'), ms, flops, bytes} with flops/bytes already multiplied by ``batch``."""
+        self.ensure_batch(batch)
+        Cc, Hh = self.cfg["input_channels"], self.cfg["input_height"]
+        names = self.op_names()
+        n = len(names)
+        with torch.cuda.device(self.device):
+            x = torch.randn(batch, Cc, Hh, Hh, device=self.device)
+            t = torch.full((batch,), 0.5, device=self.device)
+            v = torch.empty_like(x)
+            ms = (C.c_float * n)()
+            for _ in range(2):
+                _lib.check(self.lib.pnpf_profile_forward(self._h, x.data_ptr(), t.data_ptr(), v.data_ptr(), batch, ms, n,
+                                                         _lib.stream_ptr()))
+        out = []
+        for i, name in enumerate(names):
+            kind, fl, by = C.c_int(), C.c_double(), C.c_double()
+            _lib.check(self.lib.pnpf_debug_op_info(self._h, i, C.byref(kind), C.byref(fl), C.byref(by)))
+            out.append(dict(name=name, kind="tc" if kind.value == 1 else "simt", ms=float(ms[i]),
+                            flops=fl.value * batch, bytes=by.value * batch))
+        return out
+
     def op_names(self):
         n = self.lib.pnpf_debug_num_ops(self._h)
         return [self.lib.pnpf_debug_op_name(self._h, i).decode() for i in range(n)]

@@ -57,53 +57,87 @@ def restore(engine: UNetEngine, y: torch.Tensor, degradation, sigma_noise: float
 
     Mirrors pnp_flow.py:93,102-121.  ``noise``: optional iterable of eps tensors [B,C,H,W], one per (step, draw).
     """
-    if noise_type != 'gaussian':
-        if noise_type == 'laplace':
-            raise NotImplementedError("laplace data term (pnp_flow.py:42-43) is not implemented on the engine yet")
-        raise ValueError('Noise type not supported')                     # pnp_flow.py:45,68,87
-    lib = _lib.load()
-    op = as_engine_operator(degradation)
-    dev = y.device
+    sess = PnPFlowSession(engine, degradation, tuple(y.shape), steps_pnp=steps_pnp, lr_pnp=lr_pnp, alpha=alpha,
+                          gamma_style=gamma_style, num_samples=num_samples, noise_type=noise_type,
+                          use_cuda_graph=use_cuda_graph, device=y.device)
     y = y.contiguous().float()
-    x = op.H_adj(torch.ones_like(y))                                       # :93
-    B, Cc, Hh, Ww = x.shape
-    n = x.numel()
-    S = int(num_samples)
-    steps = int(steps_pnp)
-    delta = 1 / steps_pnp
+    x = sess.initial_state(y)                                              # :93
     noise_it = iter(noise) if noise is not None else None
-    z = torch.empty_like(x)
-    eps = torch.empty((S,) + tuple(x.shape), device=dev)
-    x_new = torch.empty_like(x)
-    if use_cuda_graph:
-        zt, tb, v, replay = engine.graphed(S * B)
-        zt5, v5 = zt.view(S, B, Cc, Hh, Ww), v.view(S, B, Cc, Hh, Ww)
-    else:
-        zt5 = torch.empty_like(eps)
-        v5 = torch.empty_like(eps)
-        tb = torch.empty(S * B, device=dev)
-    sp = _lib.stream_ptr
-    with torch.no_grad(), torch.cuda.device(dev):
-        for it in range(steps):
-            t = float(np.float32(delta * it))                               # :107-108 (python double -> fp32 tensor)
-            gamma = gamma_schedule(lr_pnp, t, gamma_style, alpha)
-            op.datafit_step(x, y, gamma, out=z)
+    for it in range(int(steps_pnp)):
+        x = sess.step(x, y, it, noise_it)
+        if trace is not None:
+            trace(it, x)
+    return x.clone()
+
+
+class PnPFlowSession:
+    """Static buffers + captured U-Net graph for repeated PnP-Flow steps on measurements of a fixed shape.
+
+    ``step(x, y, it)`` is ONE iteration of pnp_flow.py:107-121 at t = it/steps_pnp: data-fidelity kernel, S noise
+    draws, one interpolation kernel, one U-Net evaluation on the S*B batch, one push+average kernel."""
+
+    def __init__(self, engine: UNetEngine, degradation, y_shape, *, steps_pnp=100, lr_pnp=1.0, alpha=1.0,
+                 gamma_style='alpha_1_minus_t', num_samples=5, noise_type='gaussian', use_cuda_graph=True, device="cuda"):
+        if noise_type != 'gaussian':
+            if noise_type == 'laplace':
+                raise NotImplementedError("laplace data term (pnp_flow.py:42-43) is not implemented on the engine yet")
+            raise ValueError('Noise type not supported')                     # pnp_flow.py:45,68,87
+        self.lib = _lib.load()
+        self.engine = engine
+        self.op = as_engine_operator(degradation)
+        self.dev = torch.device(device)
+        self.steps, self.lr_pnp, self.alpha, self.gamma_style = int(steps_pnp), lr_pnp, alpha, gamma_style
+        self.delta = 1 / steps_pnp
+        self.S = S = int(num_samples)
+        B, Cc = y_shape[0], y_shape[1]
+        Hh = Ww = engine.cfg["input_height"]
+        self.shape = (B, Cc, Hh, Ww)
+        self.n = B * Cc * Hh * Ww
+        self.use_cuda_graph = use_cuda_graph
+        with torch.cuda.device(self.dev):
+            self.z = torch.empty(self.shape, device=self.dev)
+            self.eps = torch.empty((S,) + self.shape, device=self.dev)
+            self.xbuf = [torch.empty(self.shape, device=self.dev) for _ in range(2)]
+            if use_cuda_graph:
+                zt, self.tb, v, self.replay = engine.graphed(S * B)
+            else:
+                zt = torch.empty((S * B, Cc, Hh, Ww), device=self.dev)
+                v = torch.empty_like(zt)
+                self.tb = torch.empty(S * B, device=self.dev)
+        self.zt, self.v = zt, v
+        self._flip = 0
+        # kernels of OUR library launched by one step (bench.py's gpu_launches): data-fit (2 for blur), interp,
+        # every U-Net op except the stats memset, push
+        self.launches_per_step = (2 if type(self.op).__name__ == "GaussianDeblurring" else 1) + 1 + (engine.num_launches - 1) + 1
+
+    def initial_state(self, y):
+        return self.op.H_adj(torch.ones_like(y))                             # pnp_flow.py:93
+
+    def step(self, x, y, it: int, noise_it=None):
+        S, n = self.S, self.n
+        sp = _lib.stream_ptr
+        t = float(np.float32(self.delta * it))                               # :107-108 (python double -> fp32 tensor)
+        gamma = gamma_schedule(self.lr_pnp, t, self.gamma_style, self.alpha)
+        with torch.no_grad(), torch.cuda.device(self.dev):
+            self.op.datafit_step(x, y, gamma, out=self.z)
             for s in range(S):
                 if noise_it is not None:
-                    eps[s].copy_(next(noise_it))
+                    self.eps[s].copy_(next(noise_it))
                 else:
-                    eps[s].copy_(torch.randn_like(z))                       # one Philox call per draw, like :48
-            _lib.check(lib.pnpf_interp(z.data_ptr(), eps.data_ptr(), t, zt5.data_ptr(), n, S, sp()))
-            tb.fill_(t)
-            if use_cuda_graph:
-                replay()
+                    self.eps[s].copy_(torch.randn_like(self.z))              # one Philox call per draw, like :48
+            _lib.check(self.lib.pnpf_interp(self.z.data_ptr(), self.eps.data_ptr(), t, self.zt.data_ptr(), n, S, sp()))
+            self.tb.fill_(t)
+            if self.use_cuda_graph:
+                self.replay()
             else:
-                engine.forward(zt5.view(S * B, Cc, Hh, Ww), tb, out=v5.view(S * B, Cc, Hh, Ww))
-            _lib.check(lib.pnpf_push_accum(zt5.data_ptr(), v5.data_ptr(), t, S, x_new.data_ptr(), n, sp()))
-            x, x_new = x_new, x
-            if trace is not None:
-                trace(it, x)
-    return x.clone()
+                self.engine.forward(self.zt, self.tb, out=self.v)
+            x_new = self.xbuf[self._flip]
+            if x_new.data_ptr() == x.data_ptr():
+                self._flip ^= 1
+                x_new = self.xbuf[self._flip]
+            self._flip ^= 1
+            _lib.check(self.lib.pnpf_push_accum(self.zt.data_ptr(), self.v.data_ptr(), t, S, x_new.data_ptr(), n, sp()))
+        return x_new
 
 
 class PNP_FLOW(object):
