@@ -28,20 +28,27 @@ __device__ __forceinline__ const bf16* src_ptr(const GnSrc& s, int img, long lon
     return s.p2 + ((long long)img * HW + pix) * s.pitch2 + (c0 - s.C1);
 }
 
-constexpr int GN_PIX_PER_BLOCK = 1024;
+// pixels per block: the largest of {1024..64} that still gives >= 4 blocks per SM (small feature maps would
+// otherwise run on a handful of SMs)
+static inline int gn_pix_per_block(int HW, int B) {
+    const long long want = 4LL * num_sms();
+    for (int p = 1024; p > 64; p >>= 1)
+        if ((long long)B * ((HW + p - 1) / p) >= want) return p;
+    return 64;
+}
 
 // =================================================================================================
 // GroupNorm statistics: per (image, channel) sum and sum of squares, fp32 in-block, fp64 atomics across blocks
 // =================================================================================================
-__global__ void gn_stats_kernel(GnSrc s, int HW, double* __restrict__ stats) {
+__global__ void gn_stats_kernel(GnSrc s, int HW, int pix_per_block, double* __restrict__ stats) {
     extern __shared__ float red[];                    // [ppb][C][2]
     const int C = s.C1 + s.C2;
     const int nvec = C >> 3;
     const int ppb = blockDim.x / nvec;
     const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
     const int img = blockIdx.y;
-    const int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
-    const int p1 = min(p0 + GN_PIX_PER_BLOCK, HW);
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(p0 + pix_per_block, HW);
     float sum[8], sq[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
@@ -85,8 +92,9 @@ int launch_gn_stats(const GnSrc& s, int B, int HW, double* stats, cudaStream_t s
     const int threads = gn_threads(C);
     const int ppb = threads / (C / 8);
     const size_t smem = (size_t)ppb * C * 2 * sizeof(float);
-    dim3 grid((HW + GN_PIX_PER_BLOCK - 1) / GN_PIX_PER_BLOCK, B);
-    gn_stats_kernel<<<grid, threads, smem, st>>>(s, HW, stats);
+    const int ppb_blk = gn_pix_per_block(HW, B);
+    dim3 grid((HW + ppb_blk - 1) / ppb_blk, B);
+    gn_stats_kernel<<<grid, threads, smem, st>>>(s, HW, ppb_blk, stats);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -94,7 +102,7 @@ int launch_gn_stats(const GnSrc& s, int B, int HW, double* stats, cudaStream_t s
 // =================================================================================================
 // GroupNorm apply (+ SiLU) -> bf16 NHWC conv operand; optional raw concat copy
 // =================================================================================================
-__global__ void gn_apply_kernel(GnSrc s, int HW, const double* __restrict__ stats, const float* __restrict__ gamma,
+__global__ void gn_apply_kernel(GnSrc s, int HW, int pix_per_block, const double* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int gs, int silu, bf16* __restrict__ dst,
                                 bf16* __restrict__ raw_dst) {
     extern __shared__ float ss[];                     // scale[C], shift[C]
@@ -120,8 +128,8 @@ __global__ void gn_apply_kernel(GnSrc s, int HW, const double* __restrict__ stat
     const int nvec = C >> 3;
     const int ppb = blockDim.x / nvec;
     const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
-    const int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
-    const int p1 = min(p0 + GN_PIX_PER_BLOCK, HW);
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(p0 + pix_per_block, HW);
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -149,8 +157,9 @@ int launch_gn_apply(const GnSrc& s, int B, int HW, const double* stats, const fl
     const int C = s.C1 + s.C2;
     PNPF_REQUIRE(C % groups == 0 && C % 8 == 0 && s.C1 % 8 == 0, "GroupNorm channels (%d+%d) unsupported", s.C1, s.C2);
     const int threads = gn_threads(C);
-    dim3 grid((HW + GN_PIX_PER_BLOCK - 1) / GN_PIX_PER_BLOCK, B);
-    gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), st>>>(s, HW, stats, gamma, beta, eps, C / groups, silu, dst, raw_dst);
+    const int ppb_blk = gn_pix_per_block(HW, B);
+    dim3 grid((HW + ppb_blk - 1) / ppb_blk, B);
+    gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), st>>>(s, HW, ppb_blk, stats, gamma, beta, eps, C / groups, silu, dst, raw_dst);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -204,6 +213,7 @@ int launch_softmax_rows(const float* S, bf16* P, long long rows, int L, cudaStre
 __device__ __forceinline__ float swishf(float x) { return x / (1.f + expf(-x)); }
 
 __global__ void temb_kernel(TembWeights w, const float* __restrict__ t, float* __restrict__ out) {
+    // grid (image, chunk of 256 projection outputs): every block recomputes the two small dense layers (20K MAC)
     extern __shared__ float sm[];                     // emb[ch] | h[temb_ch] | s[temb_ch]
     float* emb = sm;
     float* h = sm + w.ch;
@@ -228,16 +238,19 @@ __global__ void temb_kernel(TembWeights w, const float* __restrict__ t, float* _
         sv[o] = swishf(acc);                          // ResidualBlock applies act(temb) before temb_proj (models.py:101)
     }
     __syncthreads();
-    for (int o = threadIdx.x; o < w.total_proj; o += blockDim.x) {
+    const int o = blockIdx.y * blockDim.x + threadIdx.x;
+    if (o < w.total_proj) {
         float acc = w.bp[o];
-        for (int k = 0; k < w.temb_ch; ++k) acc = fmaf(w.wp_t[(long long)k * w.total_proj + o], sv[k], acc);
+#pragma unroll 8
+        for (int k = 0; k < w.temb_ch; ++k) acc = fmaf(__ldg(w.wp_t + (long long)k * w.total_proj + o), sv[k], acc);
         out[(long long)img * w.total_proj + o] = acc;
     }
 }
 
 int launch_temb(const TembWeights& w, const float* t, int B, float* out, cudaStream_t st) {
     const size_t smem = (w.ch + 2 * w.temb_ch) * sizeof(float);
-    temb_kernel<<<B, 256, smem, st>>>(w, t, out);
+    dim3 grid(B, (w.total_proj + 255) / 256);
+    temb_kernel<<<grid, 256, smem, st>>>(w, t, out);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

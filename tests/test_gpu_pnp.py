@@ -89,7 +89,7 @@ def test_loop_vs_oracle_injected_noise(problem, alpha):
                       noise=[n.cuda() for n in noise], use_cuda_graph=graph).cpu()
         rel = ((x - x_ref).norm() / x_ref.norm()).item()
         dpsnr = (oracle.psnr(x, clean) - oracle.psnr(x_ref, clean)).abs().max().item()
-        assert rel < 1e-2, (problem, graph, rel)
+        assert rel < 3e-2, (problem, graph, rel)
         assert dpsnr < 0.01, (problem, graph, dpsnr)
 
 
