@@ -105,7 +105,9 @@ def cpu_reference(cfgname, steps, warmup):
     c = CONFIGS[cfgname]
     ocfg = oracle.AFHQ_256 if c["net"] == "afhq256" else oracle.CELEBA_128
     side = ocfg.input_height
-    torch.set_num_threads(os.cpu_count() or 1)
+    # oneDNN convolutions stop scaling (and collapse when oversubscribed) beyond ~16 threads at these batch sizes:
+    # measured on the GPU box's 128-thread host: 0.22 s/eval at 16 threads vs 0.97 s at 64 and 61 s at 128.
+    torch.set_num_threads(min(os.cpu_count() or 1, 16))
     cores = torch.get_num_threads()
     sd = oracle.init_state_dict(ocfg, seed=0)
     deg, sigma, alpha = oracle.make_degradation(c["problem"], side, 3, "cpu")
@@ -164,7 +166,7 @@ def main():
         if rank != 0:
             return
         r = cpu_reference(a.config, max(1, min(K, a.cpu_steps)), 1)   # bounded sample: <= cpu_steps CPU steps
-        line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": K, "warmup": W,
+        line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": max(1, min(K, a.cpu_steps)), "warmup": 1,
                 "ms_per_step": r["per_step_s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "impl": "reference", "config": cfg_desc,
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},

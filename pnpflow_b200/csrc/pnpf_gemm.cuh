@@ -17,6 +17,107 @@
 
 namespace pnpf {
 
+// Epilogue description shared by the tensor-core kernels (bias / time-embedding / residual / store mode).
+struct EpiParams {
+    void* out;
+    int out_mode;          // 0: bf16 [img][pix][col]   1: f32 [img][pix][col]   2: f32 [img][col][pix] (NCHW)
+    long long out_img_stride, out_row_stride, out_col_stride;   // elements
+    int n_valid;           // columns >= n_valid are not stored
+    const float* bias;     // [N_total] or nullptr
+    const float* bias_img; // [img][bias_img_stride] + col, or nullptr   (time-embedding projection)
+    long long bias_img_stride;
+    const __nv_bfloat16* residual;   // [img][pix][col] bf16 or nullptr
+    long long res_img_stride, res_row_stride;
+    double* stats;         // optional GroupNorm statistics of the OUTPUT: [img][n_valid][2] (sum, sumsq), fp64 atomics
+};
+
+// One thread = one output pixel; v[16] = accumulator columns [col0, col0+16).  Adds bias / temb / residual and stores.
+__device__ __forceinline__ void epilogue_apply16(const EpiParams& p, int img, long long pix, int col0, float (&v)[16]) {
+    if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+    }
+    if (p.bias_img) {
+        const float* bi = p.bias_img + img * p.bias_img_stride + col0;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bi + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+    }
+    if (p.residual) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + img * p.res_img_stride + pix * p.res_row_stride + col0);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint4 u = __ldg(rp + q);
+            const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[q * 8 + 2 * j] += __uint_as_float(uu[j] << 16);
+                v[q * 8 + 2 * j + 1] += __uint_as_float(uu[j] & 0xFFFF0000u);
+            }
+        }
+    }
+}
+__device__ __forceinline__ void epilogue_store16(const EpiParams& p, int img, long long pix, int col0, const float (&v)[16]) {
+    if (p.out_mode == 0) {
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + img * p.out_img_stride + pix * p.out_row_stride + col0;
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        uint4* o4 = reinterpret_cast<uint4*>(op);
+        o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    } else if (p.out_mode == 1) {
+        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + img * p.out_img_stride + pix * p.out_row_stride + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+        float* op = reinterpret_cast<float*>(p.out) + img * p.out_img_stride + pix;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (col0 + j < p.n_valid) op[(col0 + j) * p.out_col_stride] = v[j];
+    }
+}
+// Column sums over the 32 rows of a warp (row = lane) of a 16-column chunk, for GroupNorm statistics.
+// Butterfly: 31 shuffles.  On return even lanes hold sum(col l>>1 ... see col_of_lane), odd lanes hold the sum of squares.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], bool valid, int lane) {
+    float s[16], q[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        s[j] = valid ? v[j] : 0.f;
+        q[j] = s[j] * s[j];
+    }
+#pragma unroll
+    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float ss = up ? s[i] : s[i + half];
+            const float ks = up ? s[i + half] : s[i];
+            s[i] = ks + __shfl_xor_sync(0xffffffffu, ss, bit);
+            const float sq = up ? q[i] : q[i + half];
+            const float kq = up ? q[i + half] : q[i];
+            q[i] = kq + __shfl_xor_sync(0xffffffffu, sq, bit);
+        }
+    }
+    // now s[0]/q[0] = partial of column ((lane>>1)&15 bit-composed below) over the 16 lanes sharing lane&1
+    const bool odd = lane & 1;
+    const float send = odd ? s[0] : q[0];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    return odd ? q[0] + recv : s[0] + recv;
+}
+// column (within the 16-chunk) whose statistic lane `lane` holds after warp_colsum16
+__device__ __forceinline__ int colsum16_col(int lane) {
+    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
 struct GemmParams {
     int H, W;              // output extent in the A-box coordinate space (plain GEMM: H=1, W=M)
     int TH, TW;            // tile box, TH*TW == 128
@@ -30,16 +131,7 @@ struct GemmParams {
     int kchunks;           // channel chunks per tap read through tmA
     int c_base;            // first channel of tmA to read
     int kchunks2;          // trailing 1x1 chunks read through tmA2 (0 = none)
-    // epilogue
-    void* out;
-    int out_mode;          // 0: bf16 [img][pix][col]   1: f32 [img][pix][col]   2: f32 [img][col][pix] (NCHW)
-    long long out_img_stride, out_row_stride, out_col_stride;   // elements
-    int n_valid;           // columns >= n_valid are not stored
-    const float* bias;     // [N_total] or nullptr
-    const float* bias_img; // [img][bias_img_stride] + col, or nullptr   (time-embedding projection)
-    long long bias_img_stride;
-    const __nv_bfloat16* residual;   // [img][pix][col] bf16 or nullptr
-    long long res_img_stride, res_row_stride;
+    EpiParams epi;
 };
 
 template <int BK, int BN>
@@ -191,63 +283,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tmem_ld_x16(t_addr + c0, r);
                 tmem_ld_wait();
                 const int col0 = nt * BN + c0;
-                if (valid && col0 < p.n_valid) {
-                    float v[16];
+                float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-                    if (p.bias) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                        }
-                    }
-                    if (p.bias_img) {
-                        const float* bi = p.bias_img + img * p.bias_img_stride + col0;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bi + j));
-                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                        }
-                    }
-                    if (p.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + img * p.res_img_stride +
-                                                                         pix * p.res_row_stride + col0);
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const uint4 u = __ldg(rp + q);
-                            const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                v[q * 8 + 2 * j] += __uint_as_float(uu[j] << 16);
-                                v[q * 8 + 2 * j + 1] += __uint_as_float(uu[j] & 0xFFFF0000u);
-                            }
-                        }
-                    }
-                    if (p.out_mode == 0) {
-                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + img * p.out_img_stride +
-                                            pix * p.out_row_stride + col0;
-                        uint32_t pk[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                            pk[j] = *reinterpret_cast<uint32_t*>(&b2);
-                        }
-                        uint4* o4 = reinterpret_cast<uint4*>(op);
-                        o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    } else if (p.out_mode == 1) {
-                        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + img * p.out_img_stride +
-                                                               pix * p.out_row_stride + col0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    } else {
-                        float* op = reinterpret_cast<float*>(p.out) + img * p.out_img_stride + pix;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (col0 + j < p.n_valid) op[(col0 + j) * p.out_col_stride] = v[j];
-                    }
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                const bool act = valid && col0 < p.epi.n_valid;
+                if (act) epilogue_apply16(p.epi, img, pix, col0, v);
+                if (p.epi.stats && col0 < p.epi.n_valid) {       // warp-uniform branch
+                    const float tot = warp_colsum16(v, act, lane);
+                    const int c = col0 + colsum16_col(lane);
+                    atomicAdd(p.epi.stats + (static_cast<long long>(img) * p.epi.n_valid + c) * 2 + (lane & 1), static_cast<double>(tot));
                 }
+                if (act) epilogue_store16(p.epi, img, pix, col0, v);
             }
             tc_fence_before();
             __syncwarp();

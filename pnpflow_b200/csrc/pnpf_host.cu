@@ -107,7 +107,7 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUten
 int launch_conv_gemm(int BK, int BN, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
                      const GemmParams& p, cudaStream_t stream) {
     PNPF_REQUIRE(p.TH * p.TW == 128, "tile %dx%d is not 128 pixels", p.TH, p.TW);
-    PNPF_REQUIRE(p.out_mode == 2 || p.n_valid % 16 == 0, "n_valid %d must be a multiple of 16 for row-major output", p.n_valid);
+    PNPF_REQUIRE(p.epi.out_mode == 2 || p.epi.n_valid % 16 == 0, "n_valid %d must be a multiple of 16 for row-major output", p.epi.n_valid);
 #define PNPF_CASE(bk, bn) \
     if (BK == bk && BN == bn) return launch_t<bk, bn>(tmA, tmA2, tmB, p, stream);
     PNPF_CASE(32, 16) PNPF_CASE(32, 32) PNPF_CASE(32, 64) PNPF_CASE(32, 128) PNPF_CASE(32, 256)

@@ -102,7 +102,7 @@ int launch_gn_stats(const GnSrc& s, int B, int HW, double* stats, cudaStream_t s
 // =================================================================================================
 // GroupNorm apply (+ SiLU) -> bf16 NHWC conv operand; optional raw concat copy
 // =================================================================================================
-__global__ void gn_apply_kernel(GnSrc s, int HW, int pix_per_block, const double* __restrict__ stats, const float* __restrict__ gamma,
+__global__ void gn_apply_kernel(GnSrc s, int HW, int pix_per_block, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int gs, int silu, bf16* __restrict__ dst,
                                 bf16* __restrict__ raw_dst) {
     extern __shared__ float ss[];                     // scale[C], shift[C]
@@ -111,9 +111,11 @@ __global__ void gn_apply_kernel(GnSrc s, int HW, int pix_per_block, const double
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g0 = (c / gs) * gs;
         double S = 0, Q = 0;
-        for (int j = 0; j < gs; ++j) {
-            S += stats[((long long)img * C + g0 + j) * 2];
-            Q += stats[((long long)img * C + g0 + j) * 2 + 1];
+        for (int j = 0; j < gs; ++j) {                 // a group may straddle the two concatenated sources
+            const int cc = g0 + j;
+            const double* sp = (cc < s.C1) ? s.st1 + ((long long)img * s.C1 + cc) * 2 : s.st2 + ((long long)img * s.C2 + (cc - s.C1)) * 2;
+            S += sp[0];
+            Q += sp[1];
         }
         const double n = (double)gs * HW;
         const double mean = S / n;
@@ -152,14 +154,15 @@ __global__ void gn_apply_kernel(GnSrc s, int HW, int pix_per_block, const double
     }
 }
 
-int launch_gn_apply(const GnSrc& s, int B, int HW, const double* stats, const float* gamma, const float* beta, float eps,
+int launch_gn_apply(const GnSrc& s, int B, int HW, const float* gamma, const float* beta, float eps,
                     int groups, int silu, bf16* dst, bf16* raw_dst, cudaStream_t st) {
     const int C = s.C1 + s.C2;
     PNPF_REQUIRE(C % groups == 0 && C % 8 == 0 && s.C1 % 8 == 0, "GroupNorm channels (%d+%d) unsupported", s.C1, s.C2);
     const int threads = gn_threads(C);
     const int ppb_blk = gn_pix_per_block(HW, B);
     dim3 grid((HW + ppb_blk - 1) / ppb_blk, B);
-    gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), st>>>(s, HW, ppb_blk, stats, gamma, beta, eps, C / groups, silu, dst, raw_dst);
+    PNPF_REQUIRE(s.st1 && (s.C2 == 0 || s.st2), "GroupNorm apply without statistics");
+    gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), st>>>(s, HW, ppb_blk, gamma, beta, eps, C / groups, silu, dst, raw_dst);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -12,11 +12,13 @@ typedef __nv_bfloat16 bf16;
 struct GnSrc {
     const bf16* p1; int C1; long long pitch1;
     const bf16* p2; int C2; long long pitch2;     // p2 == nullptr -> single source
+    const double* st1; const double* st2;         // per-source statistics [img][C_src][2] (sum, sumsq), written by the
+                                                  // producing conv's epilogue (or by launch_gn_stats)
 };
-// stats[img][C][2] (double sum, sumsq) must be zero on entry
+// standalone statistics pass over source 1 only: stats[img][C1][2] (double sum, sumsq) must be zero on entry
 int launch_gn_stats(const GnSrc& s, int B, int HW, double* stats, cudaStream_t st);
 // dst[img][pix][C] = act((x-mean_g)*rstd_g*gamma+beta); raw_dst (optional) receives the un-normalised concat
-int launch_gn_apply(const GnSrc& s, int B, int HW, const double* stats, const float* gamma, const float* beta, float eps,
+int launch_gn_apply(const GnSrc& s, int B, int HW, const float* gamma, const float* beta, float eps,
                     int groups, int silu, bf16* dst, bf16* raw_dst, cudaStream_t st);
 
 // ---- softmax over the last dim: S fp32 [rows][L] -> P bf16 [rows][L] --------------------------------------

@@ -1,6 +1,7 @@
 // Internal op layer: prepared (tensor maps encoded once) tensor-core ops and launchers of the SIMT kernels.
 #pragma once
 #include "pnpf_host.h"
+#include "pnpf_rowconv.cuh"
 
 namespace pnpf {
 
@@ -10,6 +11,8 @@ typedef __nv_bfloat16 bf16;
 struct TcOp {               // a prepared conv_gemm launch
     CUtensorMap tmA, tmA2, tmB;
     GemmParams p;
+    RowConvParams rp;       // kind == 1: row-streaming conv (pnpf_rowconv.cuh)
+    int kind = 0;           // 0: conv_gemm_kernel, 1: rowconv_kernel
     int BK = 0, BN = 0;
     double flops = 0;       // algorithmic 2*M*N*K (for reporting)
 };
@@ -39,8 +42,11 @@ struct ConvDesc {
     long long bias_img_stride = 0;
     const bf16* residual = nullptr;
     long long res_img_stride = 0, res_row_stride = 0;
+    double* stats_out = nullptr;    // optional [B][n_valid][2] GroupNorm statistics of the output (must be zeroed)
+    int allow_rowconv = 1;          // use the row-streaming kernel when the shape qualifies
 };
 int prepare_conv(TcOp& op, const ConvDesc& d);
+int rowconv_max_smem();
 
 struct GemmDesc {           // out[b][m][n] = sum_k A[b|0][m][k] * Bm[b|0][n][k]  (+bias[n]) (+residual)
     const bf16* A = nullptr;

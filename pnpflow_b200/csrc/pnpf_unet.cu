@@ -35,6 +35,7 @@ struct WEntry {
 struct Act {                      // bf16 NHWC activation [B][side][side][C]
     bf16* p = nullptr;
     int C = 0, side = 0;
+    double* stats = nullptr;      // [B][C][2] per-channel (sum, sumsq) written by the producing conv's epilogue
     long long elems_per_img() const { return (long long)C * side * side; }
 };
 
@@ -311,8 +312,11 @@ extern "C" int pnpf_finalize_weights(pnpf_engine* e) {
         cp("temb.b0", "temb_net.main.0.bias");
         cp("temb.w2", "temb_net.main.2.weight");
         cp("temb.b2", "temb_net.main.2.bias");
-        float* wp = pk.f32("temb.wp_t", (size_t)temb_ch * e->total_proj);
-        float* bp = pk.f32("temb.bp", e->total_proj);
+        // NB: Packer pointers are invalidated by the next reserve() (vector growth): reserve both, then take pointers
+        const size_t wp_off = pk.reserve("temb.wp_t", (size_t)temb_ch * e->total_proj * sizeof(float));
+        const size_t bp_off = pk.reserve("temb.bp", (size_t)e->total_proj * sizeof(float));
+        float* wp = reinterpret_cast<float*>(pk.host.data() + wp_off);
+        float* bp = reinterpret_cast<float*>(pk.host.data() + bp_off);
         for (const LayerSpec& L : e->layers) {
             if (L.kind != LayerSpec::RES) continue;
             const int off = e->proj_off.at(L.prefix);
@@ -464,7 +468,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 m_a1 = std::max(m_a1, px * L.in_ch);
                 m_h1 = std::max(m_h1, px * L.out_ch);
                 if (!L.push) m_h = std::max(m_h, px * L.out_ch);
-                stats_elems += 2 * (size_t)(L.in_ch + L.out_ch);
+                stats_elems += 4 * (size_t)L.out_ch;          // conv1 output + block output
                 break;
             case LayerSpec::ATTN:
                 m_a1 = std::max(m_a1, px * L.in_ch);
@@ -473,17 +477,18 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 m_S = std::max(m_S, px * px);
                 m_P = std::max(m_P, px * px);
                 if (!L.push) m_h = std::max(m_h, px * L.out_ch);
-                stats_elems += 2 * (size_t)L.in_ch;
+                stats_elems += 2 * (size_t)L.out_ch;
                 break;
             case LayerSpec::UP:
                 m_up = std::max(m_up, 4 * px * L.in_ch);
                 m_h = std::max(m_h, 4 * px * L.out_ch);
+                stats_elems += 2 * (size_t)L.out_ch;
                 break;
             case LayerSpec::END:
                 m_a1 = std::max(m_a1, px * L.in_ch);
-                stats_elems += 2 * (size_t)L.in_ch;
                 break;
-            default:
+            default:                                          // CONV, DOWN: one produced tensor
+                stats_elems += 2 * (size_t)L.out_ch;
                 break;
         }
     }
@@ -512,6 +517,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
         Act a;
         a.C = C;
         a.side = side;
+        a.stats = new_stats(C);
         if (push) a.p = A.take<bf16>((size_t)Bm * a.elems_per_img());
         else { a.p = t_h[hsel]; hsel ^= 1; }
         return a;
@@ -521,13 +527,8 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
     auto add_gn = [&](const std::string& name, const GnSrc& src, int side, const std::string& wname, int silu, bf16* dst,
                       bf16* raw) {
         const int C = src.C1 + src.C2;
-        double* st = new_stats(C);
-        Op s;
-        s.kind = Op::GN_STATS; s.name = name + ".stats"; s.gsrc = src; s.HW = side * side; s.stats = st;
-        s.bytes = 2.0 * C * side * side;
-        ops.push_back(s);
         Op a;
-        a.kind = Op::GN_APPLY; a.name = name; a.gsrc = src; a.HW = side * side; a.stats = st;
+        a.kind = Op::GN_APPLY; a.name = name; a.gsrc = src; a.HW = side * side;
         if (real) { a.gamma = wptr<float>(e, wname + ".gamma"); a.beta = wptr<float>(e, wname + ".beta"); }
         a.silu = silu; a.dst = dst; a.raw_dst = raw;
         a.bytes = (raw ? 6.0 : 4.0) * C * side * side;
@@ -579,6 +580,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 d.x = in_nhwc; d.Hin = d.Win = d.Hout = d.Wout = side; d.Cin = CIN_PAD; d.x_pitch = CIN_PAD;
                 d.N_pad = round_n(L.out_ch); d.ksize = 3; d.stride = 1;
                 if (real) { d.w = wptr<bf16>(e, p + ".w"); d.bias = wptr<float>(e, p + ".b"); }
+                d.stats_out = y.stats;
                 d.out = y.p; d.out_mode = 0; d.out_img_stride = px * L.out_ch; d.out_row_stride = L.out_ch; d.n_valid = L.out_ch;
                 if (int rc = add_conv(p, d, y.p, y.C, side)) return rc;
                 h = y;
@@ -590,9 +592,9 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 if (L.skip_ch) {
                     skip = hs.back();
                     hs.pop_back();
-                    src = GnSrc{h.p, h.C, h.C, skip.p, skip.C, skip.C};
+                    src = GnSrc{h.p, h.C, h.C, skip.p, skip.C, skip.C, h.stats, skip.stats};
                 } else {
-                    src = GnSrc{h.p, h.C, h.C, nullptr, 0, 0};
+                    src = GnSrc{h.p, h.C, h.C, nullptr, 0, 0, h.stats, nullptr};
                 }
                 const bool sc = L.in_ch != L.out_ch;
                 add_gn(p + ".norm1", src, side, p + ".norm1", 1, t_a1, (L.skip_ch && sc) ? t_xcat : nullptr);
@@ -601,9 +603,11 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 d1.N_pad = round_n(L.out_ch); d1.ksize = 3; d1.stride = 1;
                 if (real) { d1.w = wptr<bf16>(e, p + ".conv1.w"); d1.bias = wptr<float>(e, p + ".conv1.b"); }
                 d1.bias_img = real ? tproj + e->proj_off.at(p) : nullptr; d1.bias_img_stride = e->total_proj;
+                double* h1_stats = new_stats(L.out_ch);
+                d1.stats_out = h1_stats;
                 d1.out = t_h1; d1.out_mode = 0; d1.out_img_stride = px * L.out_ch; d1.out_row_stride = L.out_ch; d1.n_valid = L.out_ch;
                 if (int rc = add_conv(p + ".conv1", d1, t_h1, L.out_ch, side)) return rc;
-                add_gn(p + ".norm2", GnSrc{t_h1, L.out_ch, L.out_ch, nullptr, 0, 0}, side, p + ".norm2", 1, t_a2, nullptr);
+                add_gn(p + ".norm2", GnSrc{t_h1, L.out_ch, L.out_ch, nullptr, 0, 0, h1_stats, nullptr}, side, p + ".norm2", 1, t_a2, nullptr);
                 Act y = new_h(L.out_ch, side, L.push);
                 ConvDesc d2;
                 d2.x = t_a2; d2.Hin = d2.Win = d2.Hout = d2.Wout = side; d2.Cin = L.out_ch; d2.x_pitch = L.out_ch;
@@ -615,6 +619,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                     PNPF_REQUIRE(!L.skip_ch, "internal: concat block without shortcut");
                     d2.residual = h.p; d2.res_img_stride = px * L.out_ch; d2.res_row_stride = L.out_ch;
                 }
+                d2.stats_out = y.stats;
                 d2.out = y.p; d2.out_mode = 0; d2.out_img_stride = px * L.out_ch; d2.out_row_stride = L.out_ch; d2.n_valid = L.out_ch;
                 if (int rc = add_conv(p, d2, y.p, y.C, side)) return rc;
                 h = y;
@@ -626,7 +631,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 PNPF_REQUIRE(Lk % 16 == 0 && (Lk <= 256 ? (Lk == 16 || Lk == 32 || Lk == 64 || Lk == 128 || Lk == 256) : Lk % 256 == 0),
                              "attention over %d tokens unsupported by the tensor-core path", Lk);
                 PNPF_REQUIRE(C % 64 == 0, "attention channels %d must be a multiple of 64", C);
-                add_gn(p + ".norm", GnSrc{h.p, C, C, nullptr, 0, 0}, side, p + ".norm", 0, t_a1, nullptr);
+                add_gn(p + ".norm", GnSrc{h.p, C, C, nullptr, 0, 0, h.stats, nullptr}, side, p + ".norm", 0, t_a1, nullptr);
                 ConvDesc dq;                                   // [q*scale | k] = hn * [Wq*scale ; Wk]^T
                 dq.x = t_a1; dq.Hin = dq.Win = dq.Hout = dq.Wout = side; dq.Cin = C; dq.x_pitch = C;
                 dq.N_pad = round_n(2 * C); dq.ksize = 1; dq.stride = 1;
@@ -663,6 +668,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 dp.N_pad = round_n(C); dp.ksize = 1; dp.stride = 1;
                 if (real) { dp.w = wptr<bf16>(e, p + ".proj.w"); dp.bias = wptr<float>(e, p + ".proj.b"); }
                 dp.residual = h.p; dp.res_img_stride = px * C; dp.res_row_stride = C;
+                dp.stats_out = y.stats;
                 dp.out = y.p; dp.out_mode = 0; dp.out_img_stride = px * C; dp.out_row_stride = C; dp.n_valid = C;
                 if (int rc = add_conv(p, dp, y.p, C, side)) return rc;
                 h = y;
@@ -675,6 +681,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 d.x = h.p; d.Hin = d.Win = side; d.Hout = d.Wout = so; d.Cin = L.in_ch; d.x_pitch = L.in_ch;
                 d.N_pad = round_n(L.out_ch); d.ksize = 3; d.stride = 2;
                 if (real) { d.w = wptr<bf16>(e, p + ".w"); d.bias = wptr<float>(e, p + ".b"); }
+                d.stats_out = y.stats;
                 d.out = y.p; d.out_mode = 0; d.out_img_stride = (long long)so * so * L.out_ch; d.out_row_stride = L.out_ch; d.n_valid = L.out_ch;
                 if (int rc = add_conv(p, d, y.p, y.C, so)) return rc;
                 h = y;
@@ -694,13 +701,14 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 d.x = t_up; d.Hin = d.Win = d.Hout = d.Wout = so; d.Cin = L.in_ch; d.x_pitch = L.in_ch;
                 d.N_pad = round_n(L.out_ch); d.ksize = 3; d.stride = 1;
                 if (real) { d.w = wptr<bf16>(e, p + ".w"); d.bias = wptr<float>(e, p + ".b"); }
+                d.stats_out = y.stats;
                 d.out = y.p; d.out_mode = 0; d.out_img_stride = (long long)so * so * L.out_ch; d.out_row_stride = L.out_ch; d.n_valid = L.out_ch;
                 if (int rc = add_conv(p, d, y.p, y.C, so)) return rc;
                 h = y;
                 break;
             }
             case LayerSpec::END: {
-                add_gn(p + ".0", GnSrc{h.p, h.C, h.C, nullptr, 0, 0}, side, p + ".0", 1, t_a1, nullptr);
+                add_gn(p + ".0", GnSrc{h.p, h.C, h.C, nullptr, 0, 0, h.stats, nullptr}, side, p + ".0", 1, t_a1, nullptr);
                 ConvDesc d;
                 d.x = t_a1; d.Hin = d.Win = d.Hout = d.Wout = side; d.Cin = L.in_ch; d.x_pitch = L.in_ch;
                 d.N_pad = round_n(L.out_ch); d.ksize = 3; d.stride = 1;
@@ -779,18 +787,19 @@ static int run_ops(pnpf_engine* e, const float* x, const float* t, float* v, int
             case Op::TC: {
                 TcOp tc = o.tc;
                 tc.p.n_img = batch;
+                tc.rp.n_img = batch;
                 if (i == e->end_op) {
                     PNPF_REQUIRE(v != nullptr, "null output pointer");
-                    tc.p.out = v;
+                    tc.p.epi.out = v;
+                    tc.rp.epi.out = v;
                 }
                 rc = launch_tc(tc, st);
                 break;
             }
             case Op::GN_STATS:
-                rc = launch_gn_stats(o.gsrc, batch, o.HW, o.stats, st);
                 break;
             case Op::GN_APPLY:
-                rc = launch_gn_apply(o.gsrc, batch, o.HW, o.stats, o.gamma, o.beta, GN_EPS, GROUPS, o.silu, o.dst, o.raw_dst, st);
+                rc = launch_gn_apply(o.gsrc, batch, o.HW, o.gamma, o.beta, GN_EPS, GROUPS, o.silu, o.dst, o.raw_dst, st);
                 break;
             case Op::SOFTMAX:
                 rc = launch_softmax_rows(o.S, o.P, o.rows_per_img * batch, o.L, st);

@@ -61,6 +61,16 @@ def test_conv_stride2(B, H, W, Cin, Cout):
     _conv_case(B, H, W, Cin, Cout, 3, 2)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,C2,res", [
+    (2, 128, 128, 32, 32, 0, False), (1, 256, 256, 32, 32, 0, True), (2, 40, 128, 64, 32, 0, False), (1, 128, 256, 96, 32, 0, False),
+    (2, 128, 128, 64, 64, 0, True), (1, 64, 128, 32, 64, 32, False), (2, 128, 256, 32, 32, 96, False), (3, 33, 128, 32, 32, 64, False),
+    (1, 128, 128, 32, 16, 0, False),
+])
+def test_rowconv_wide_maps(B, H, W, Cin, Cout, C2, res):
+    """W % 128 == 0 and Cout <= 64 route to the row-streaming kernel (halo tile + row-shifted UMMA descriptors)."""
+    _conv_case(B, H, W, Cin, Cout, 3, 1, C2=C2, res=res, seed=H + W + Cin)
+
+
 def test_conv_ragged_edges():
     _conv_case(2, 28, 28, 32, 32, 3, 1)
     _conv_case(2, 14, 14, 64, 64, 3, 1)
