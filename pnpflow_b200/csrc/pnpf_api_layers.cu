@@ -2,6 +2,8 @@
 #include "../../include/pnpflow_b200.h"
 #include "pnpf_ops.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 using namespace pnpf;
@@ -50,8 +52,23 @@ extern "C" int pnpf_conv2d_nhwc(const void* x, int B, int Hin, int Win, int Cin,
     d.res_img_stride = (long long)Hout * Wout * Cout; d.res_row_stride = Cout;
     TcOp op;
     int rc = prepare_conv(op, d);
+    long long* dbg = nullptr;
+    if (!rc && op.kind == 1 && getenv("PNPF_ROWCONV_DBG")) {          // profiling experiment: cycle counters of CTA 0
+        cudaMalloc(&dbg, 16 * sizeof(long long));
+        cudaMemset(dbg, 0, 16 * sizeof(long long));
+        op.rp.dbg = dbg;
+    }
     if (!rc) rc = launch_tc(op, s);
     cudaError_t e = cudaStreamSynchronize(s);
+    if (dbg) {
+        long long h[16];
+        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("ROWCONV_DBG producer: total %lld wait_empty %lld rows %lld | mma: total %lld wait_full %lld wait_tempty %lld | "
+               "epi0: total %lld wait_tfull %lld rows %lld | epi1: total %lld wait_tfull %lld rows %lld\n",
+               h[0], h[1], h[2], h[4], h[5], h[6], h[8], h[9], h[10], h[12], h[13], h[14]);
+        fflush(stdout);
+        cudaFree(dbg);
+    }
     cudaFree(dw);
     cudaFree(db);
     if (rc) return rc;

@@ -274,7 +274,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int h = h0 + th, w = w0 + tw;
             const bool valid = (h < p.H) && (w < p.W);
             const long long pix = static_cast<long long>(h) * p.W + w;
-            mbar_wait(&tfull_bar[acc], acc_phase);
+            if (lane == 0) mbar_wait(&tfull_bar[acc], acc_phase);   // one lane polls, the warp follows
+            __syncwarp();
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1

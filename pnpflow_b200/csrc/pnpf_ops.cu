@@ -49,7 +49,9 @@ static int try_prepare_rowconv(TcOp& op, const ConvDesc& d) {
     const int halo_tile = (136 * rowb + 1023) / 1024 * 1024, x2_tile = 128 * rowb;
     const int w_tile = (BN * BK * 2 + 1023) / 1024 * 1024;
     const int kch = d.Cin / BK, kch2 = d.x2 ? d.C2 / BK : 0;
-    const int w_bytes = (9 * kch + kch2) * w_tile;
+    if (kch < 1 || kch > 3) return -1;
+    if ((BN * rowb) % 1024 != 0) return -1;       // stacked vertical-tap tiles must keep the swizzle phase
+    const int w_bytes = 3 * kch * (3 * BN * rowb) + kch2 * w_tile;
     const int slot_bytes = kch * halo_tile + kch2 * x2_tile;
     int nslot = (ROWCONV_SMEM_BUDGET - w_bytes) / slot_bytes;
     if (nslot > 8) nslot = 8;
@@ -171,28 +173,33 @@ int prepare_gemm(TcOp& op, const GemmDesc& d) {
     return 0;
 }
 
-template <int BK, int BN>
+template <int BK, int BN, int KCH>
 static int launch_row_t(const TcOp& op, cudaStream_t stream) {
     using Cfg = RowCfg<BK, BN>;
     const RowConvParams& r = op.rp;
-    const int smem = (9 * r.kchunks + r.kchunks2) * Cfg::W_TILE + r.nslot * r.slot_bytes + Cfg::BAR_BYTES + 1024;
+    const int smem = 3 * r.kchunks * Cfg::W_STACK + r.kchunks2 * Cfg::W_TILE + r.nslot * r.slot_bytes + Cfg::BAR_BYTES + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        PNPF_CHECK_CUDA(cudaFuncSetAttribute(rowconv_kernel<BK, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowconv_max_smem()));
+        PNPF_CHECK_CUDA(cudaFuncSetAttribute(rowconv_kernel<BK, BN, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowconv_max_smem()));
         attr_set = true;
     }
     PNPF_REQUIRE(smem <= rowconv_max_smem(), "row conv shared memory %d exceeds the budget", smem);
     const long long items = (long long)r.n_img * r.segs * r.strips;
     const int grid = (int)(items < num_sms() ? items : num_sms());
     if (grid < 1) return 0;
-    rowconv_kernel<BK, BN><<<grid, Cfg::THREADS, smem, stream>>>(op.tmA, op.tmA2, op.tmB, r);
+    rowconv_kernel<BK, BN, KCH><<<grid, Cfg::THREADS, smem, stream>>>(op.tmA, op.tmA2, op.tmB, r);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_tc(const TcOp& op, cudaStream_t s) {
     if (op.kind == 1) {
-#define PNPF_RCASE(bk, bn) if (op.BK == bk && op.BN == bn) return launch_row_t<bk, bn>(op, s);
+#define PNPF_RCASE(bk, bn)                                                                \
+    if (op.BK == bk && op.BN == bn) {                                                     \
+        if (op.rp.kchunks == 1) return launch_row_t<bk, bn, 1>(op, s);                    \
+        if (op.rp.kchunks == 2) return launch_row_t<bk, bn, 2>(op, s);                    \
+        if (op.rp.kchunks == 3) return launch_row_t<bk, bn, 3>(op, s);                    \
+    }
         PNPF_RCASE(32, 16) PNPF_RCASE(32, 32) PNPF_RCASE(32, 64) PNPF_RCASE(64, 16) PNPF_RCASE(64, 32) PNPF_RCASE(64, 64)
 #undef PNPF_RCASE
         set_error("no rowconv instantiation for BK=%d BN=%d", op.BK, op.BN);

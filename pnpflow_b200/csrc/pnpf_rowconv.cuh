@@ -5,20 +5,20 @@
 // A CTA owns a column strip of 128 output pixels and walks down a segment of rows.  Every INPUT row is fetched ONCE by TMA
 // as a 130-pixel halo tile (w0-1 .. w0+128, out-of-image pixels zero-filled by the TMA unit = the conv padding) and feeds
 // nine tensor-core taps:
-//   * the three vertical taps: the row is used for output rows j-1, j, j+1 (three TMEM accumulators are live at once);
-//   * the three horizontal taps: the UMMA A-descriptor simply starts 0, 1 or 2 pixel-rows into the swizzled halo tile
-//     (the 128B/64B swizzle is a function of the shared-memory address bits, so a row-shifted start address reads the
-//     right data with base_offset = 0 — verified on hardware by tools/probes/umma_offset_probe.cu).
-// The 3x3 weights (and the optional fused 1x1 shortcut weights) stay resident in shared memory for the CTA's lifetime.
-// Accumulators form a ring of NACC TMEM buffers, one per output row.
-//
-// These layers have only 16 tensor-core clocks of work per MMA instruction (N = 32), so instruction issue matters:
-//   * the single MMA-issuing thread keeps descriptor low words in registers and only adds immediates per instruction;
-//   * 8 epilogue warps: for C_out <= 32 two warp sets take alternate rows, for C_out = 64 they split the columns, so a
-//     thread never handles more than 32 columns; bias (+ time-embedding row) is staged in shared memory once per item;
-//   * GroupNorm statistics of the OUTPUT (sum, sum of squares per channel, for the next layer's GroupNorm) are
-//     accumulated per thread in registers across the rows of an item and reduced with warp shuffles + one fp64 atomic
-//     per lane once per item.
+//   * horizontal taps: the UMMA A-descriptor starts 0, 1 or 2 pixel-rows into the swizzled halo tile (the 128B/64B
+//     swizzle is a function of the shared-memory address bits, so a row-shifted start address reads the right data with
+//     base_offset = 0 — verified on hardware by tools/probes/umma_offset_probe.cu);
+//   * vertical taps: input row j feeds output rows j+1, j, j-1 with the SAME A operand, so the three taps are stacked
+//     along N: the resident weight tile of (kw, chunk) holds [kh][cout] rows and the accumulators of consecutive output
+//     rows occupy DEcreasing TMEM column blocks; one tcgen05.mma with N = 3*C_out updates three output rows.
+// With N = 32 an MMA is only 16 tensor clocks, so the kernel is organised around the single issuing thread:
+//   * every MMA accumulates (the epilogue re-zeroes an accumulator block with tcgen05.st after draining it), which
+//     removes all per-instruction special cases; descriptor words live in registers, the tap loops are fully unrolled
+//     (template KCH = channel chunks) and only add immediates;
+//   * waits are issued by one lane per warp; 8 epilogue warps (alternate rows for C_out <= 32, split columns for 64);
+//   * bias (+ the per-image time-embedding row) is staged in shared memory once per work item;
+//   * GroupNorm statistics of the OUTPUT tensor are accumulated per thread across the rows of an item and reduced with
+//     warp shuffles + one fp64 atomic per lane per item.
 #pragma once
 #include "pnpf_gemm.cuh"
 
@@ -28,10 +28,11 @@ struct RowConvParams {
     int H, W, n_img;
     int strips;            // W / 128
     int seg_rows, segs;    // rows per work item, ceil(H / seg_rows)
-    int kchunks;           // Cin / BK
+    int kchunks;           // Cin / BK (== template KCH)
     int kchunks2;          // C2 / BK of the fused 1x1 source (0 = none)
     int nslot;             // depth of the input-row ring
     int slot_bytes;
+    long long* dbg;        // optional [16] cycle counters of CTA 0 (profiling experiments), else nullptr
     EpiParams epi;
 };
 
@@ -42,7 +43,10 @@ struct RowCfg {
     static constexpr int HALO_TILE = (136 * kRowBytes + 1023) / 1024 * 1024;
     static constexpr int X2_TILE = 128 * kRowBytes;
     static constexpr int W_TILE_RAW = BN * BK * 2;
-    static constexpr int W_TILE = (W_TILE_RAW + 1023) / 1024 * 1024;
+    static constexpr int W_TILE = (W_TILE_RAW + 1023) / 1024 * 1024;      // fused 1x1 shortcut tile [BN][BK]
+    static constexpr int KH_BYTES = BN * kRowBytes;                         // one vertical tap inside a stacked tile
+    static constexpr int W_STACK = 3 * KH_BYTES;                            // [kh][BN][BK] weights of one (kw, chunk)
+    static_assert(KH_BYTES % 1024 == 0, "stacked tap tiles must keep the swizzle phase");
     static constexpr int NACC = (512 / BN) > 16 ? 16 : (512 / BN);
     static constexpr int TMEM_COLS = NACC * BN;              // 256 (BN=16) or 512
     static constexpr int MAX_SLOTS = 8;
@@ -53,20 +57,38 @@ struct RowCfg {
     static_assert(BN == 16 || BN == 32 || BN == 64, "row conv is for thin outputs");
 };
 
-// tcgen05.mma with descriptors given as (low word, shared high word)
-__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
-                                             uint32_t accumulate) {
+#define PNPF_TIMED_WAIT(bar, par, ctr)        \
+    do {                                      \
+        const long long _t0 = clock64();      \
+        mbar_wait(bar, par);                  \
+        ctr += clock64() - _t0;               \
+    } while (0)
+
+// tcgen05.mma, always accumulating, descriptors given as (low word, shared high word)
+__device__ __forceinline__ void umma_acc_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
         "mov.b64 da, {%1, %3};\n\t"
         "mov.b64 db, {%2, %3};\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
         : "memory");
 }
+// registers -> TMEM, 32 lanes x 16 columns of zeros (re-arms an accumulator block)
+__device__ __forceinline__ void tmem_zero_x16(uint32_t taddr) {
+    const uint32_t z = 0;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// one lane polls, the warp follows
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
 
-template <int BK, int BN>
+template <int BK, int BN, int KCH>
 __global__ void __launch_bounds__(RowCfg<BK, BN>::THREADS, 1)
 rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ RowConvParams p) {
@@ -75,9 +97,9 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int CPT = Cfg::CPT;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int n_wtiles = 9 * p.kchunks + p.kchunks2;
-    uint8_t* wsm = smem;
-    uint8_t* slots = smem + n_wtiles * Cfg::W_TILE;
+    uint8_t* wsm = smem;                                  // [kw][chunk] stacked tiles, then the shortcut tiles
+    const int w_bytes = 3 * KCH * Cfg::W_STACK + p.kchunks2 * Cfg::W_TILE;
+    uint8_t* slots = smem + w_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(slots + p.nslot * p.slot_bytes);
     uint64_t* wbar = bars;
     uint64_t* full_bar = bars + 1;
@@ -111,6 +133,14 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp >= 2 && warp < 6) {                      // zero every accumulator block once (all MMAs accumulate)
+        const uint32_t t0 = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        for (int c = 0; c < Cfg::TMEM_COLS; c += 16) tmem_zero_x16(t0 + c);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     auto decode = [&](int it, int& img, int& hb, int& he, int& w0) {
         const int strip = it % p.strips;
@@ -125,99 +155,122 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_arrive_expect_tx(wbar, n_wtiles * Cfg::W_TILE_RAW);
-            for (int i = 0; i < n_wtiles; ++i) tma_load_3d(wsm + i * Cfg::W_TILE, &tmB, wbar, i * BK, 0, 0);
+            mbar_arrive_expect_tx(wbar, (9 * KCH + p.kchunks2) * Cfg::W_TILE_RAW);
+            for (int kw = 0; kw < 3; ++kw)
+                for (int c = 0; c < KCH; ++c)
+                    for (int kh = 0; kh < 3; ++kh)      // packed K order is (kh, kw, cin): see pack_conv_weight
+                        tma_load_3d(wsm + (kw * KCH + c) * Cfg::W_STACK + kh * Cfg::KH_BYTES, &tmB, wbar,
+                                    ((kh * 3 + kw) * KCH + c) * BK, 0, 0);
+            for (int c = 0; c < p.kchunks2; ++c)
+                tma_load_3d(wsm + 3 * KCH * Cfg::W_STACK + c * Cfg::W_TILE, &tmB, wbar, (9 * KCH + c) * BK, 0, 0);
             int slot = 0;
             uint32_t phase = 0;
+            long long c_wait = 0, c_rows = 0;
+            const long long c_start = clock64();
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 int img, hb, he, w0;
                 decode(it, img, hb, he, w0);
                 const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
                 for (int j = j0; j <= j1; ++j) {
-                    mbar_wait(&empty_bar[slot], phase ^ 1);
+                    PNPF_TIMED_WAIT(&empty_bar[slot], phase ^ 1, c_wait);
+                    ++c_rows;
                     uint8_t* sp = slots + slot * p.slot_bytes;
                     const bool centre = (j >= hb) && (j < he) && p.kchunks2;
-                    mbar_arrive_expect_tx(&full_bar[slot], p.kchunks * Cfg::HALO_ROWS * Cfg::kRowBytes +
-                                                               (centre ? p.kchunks2 * Cfg::X2_TILE : 0));
-                    for (int c = 0; c < p.kchunks; ++c)
+                    mbar_arrive_expect_tx(&full_bar[slot], KCH * Cfg::HALO_ROWS * Cfg::kRowBytes + (centre ? p.kchunks2 * Cfg::X2_TILE : 0));
+#pragma unroll
+                    for (int c = 0; c < KCH; ++c)
                         tma_load_4d(sp + c * Cfg::HALO_TILE, &tmA, &full_bar[slot], c * BK, w0 - 1, j, img);
                     if (centre)
                         for (int c = 0; c < p.kchunks2; ++c)
-                            tma_load_4d(sp + p.kchunks * Cfg::HALO_TILE + c * Cfg::X2_TILE, &tmA2, &full_bar[slot], c * BK, w0, j, img);
+                            tma_load_4d(sp + KCH * Cfg::HALO_TILE + c * Cfg::X2_TILE, &tmA2, &full_bar[slot], c * BK, w0, j, img);
                     if (++slot == p.nslot) { slot = 0; phase ^= 1; }
                 }
             }
+            if (p.dbg && blockIdx.x == 0) { p.dbg[0] = clock64() - c_start; p.dbg[1] = c_wait; p.dbg[2] = c_rows; }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, BN);
             // descriptor words: hi is shared by every operand tile; lo = (addr >> 4) | LBO bit
             const uint64_t proto = make_smem_desc<Cfg::kRowBytes>(0);
             const uint32_t desc_hi = static_cast<uint32_t>(proto >> 32);
             const uint32_t lo_flags = static_cast<uint32_t>(proto);
-            constexpr uint32_t ROW16 = Cfg::kRowBytes / 16, HALO16 = Cfg::HALO_TILE / 16, X216 = Cfg::X2_TILE / 16, WT16 = Cfg::W_TILE / 16;
+            constexpr uint32_t ROW16 = Cfg::kRowBytes / 16, HALO16 = Cfg::HALO_TILE / 16, X216 = Cfg::X2_TILE / 16, WT16 = Cfg::W_TILE / 16,
+                               WS16 = Cfg::W_STACK / 16, KH16 = Cfg::KH_BYTES / 16;
+            constexpr uint32_t idesc1 = make_idesc_bf16(128, BN), idesc2 = make_idesc_bf16(128, 2 * BN), idesc3 = make_idesc_bf16(128, 3 * BN);
             mbar_wait(wbar, 0);
             tc_fence_after();
             const uint32_t w_lo0 = (smem_u32(wsm) >> 4) | lo_flags;
-            const uint32_t kch = p.kchunks, kch2 = p.kchunks2;
-            int slot = 0;
-            uint32_t phase = 0;
+            const uint32_t s_base_lo = (smem_u32(slots) >> 4) | lo_flags;
+            const uint32_t slot16 = static_cast<uint32_t>(p.slot_bytes) >> 4;
+            const uint32_t kch2 = p.kchunks2;
+            uint32_t slot = 0, phase = 0;
             uint32_t g0 = 0;                           // running output-row counter (selects the accumulator)
+            long long c_full = 0, c_tempty = 0;
+            const long long c_start = clock64();
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 int img, hb, he, w0;
                 decode(it, img, hb, he, w0);
                 const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
                 for (int j = j0; j <= j1; ++j) {
-                    mbar_wait(&full_bar[slot], phase);
+                    // taps kh = 0,1,2 feed output rows j+1, j, j-1; the valid ones are contiguous in kh
+                    const int k0 = (j + 1 < he) ? 0 : ((j < he) ? 1 : 2);
+                    const int k1 = (j - 1 >= hb) ? 2 : ((j >= hb) ? 1 : 0);
+                    // accumulator of output row (j + 1 - kh): ring index acc = g % NACC, column block = NACC-1-acc
+                    const uint32_t g_top = g0 + static_cast<uint32_t>(j + 1 - k0 - hb);           // row of tap k0 (largest row)
+                    const uint32_t acc_top = g_top % NACC;
+                    const uint32_t blk0 = (NACC - 1) - acc_top;                                     // block of tap k0
+                    const uint32_t ntap = static_cast<uint32_t>(k1 - k0 + 1);
+                    // taps k0.. occupy blocks blk0, blk0+1, ... until the ring wraps at NACC
+                    const uint32_t n0 = min(ntap, static_cast<uint32_t>(NACC) - blk0);
+                    const uint32_t n1 = ntap - n0;                                                  // wrapped part starts at block 0
+                    if (k0 == 0)                       // tap 0 opens a fresh accumulator (row j+1): it must have been drained
+                        PNPF_TIMED_WAIT(&tempty_bar[acc_top], ((g_top / NACC) & 1) ^ 1, c_tempty);
+                    if (j == 0)                        // top image row (hb == 0): row 0 is opened by its centre tap
+                        PNPF_TIMED_WAIT(&tempty_bar[g0 % NACC], ((g0 / NACC) & 1) ^ 1, c_tempty);
                     tc_fence_after();
-                    const uint32_t s_lo0 = (smem_u32(slots + slot * p.slot_bytes) >> 4) | lo_flags;
-#pragma unroll 1
-                    for (int dh = 1; dh >= -1; --dh) {
-                        const int r = j - dh;          // output row fed by input row j through vertical tap kh = dh + 1
-                        if (r < hb || r >= he) continue;
-                        const uint32_t g = g0 + static_cast<uint32_t>(r - hb);
-                        const uint32_t acc = g % NACC;
-                        const bool first = (j == max(r - 1, 0));
-                        if (first) {
-                            mbar_wait(&tempty_bar[acc], ((g / NACC) & 1) ^ 1);
-                            tc_fence_after();
-                        }
-                        const uint32_t d_tmem = tmem_base + acc * BN;
-                        uint32_t accum = first ? 0u : 1u;
-                        uint32_t w_lo = w_lo0 + static_cast<uint32_t>(dh + 1) * 3u * kch * WT16;
+                    PNPF_TIMED_WAIT(&full_bar[slot], phase, c_full);
+                    tc_fence_after();
+                    const uint32_t s_lo0 = s_base_lo + slot * slot16;
+                    const uint32_t d0 = tmem_base + blk0 * BN, d1 = tmem_base;
+                    const uint32_t i0 = n0 == 3 ? idesc3 : (n0 == 2 ? idesc2 : idesc1);
+                    const uint32_t i1 = n1 == 2 ? idesc2 : idesc1;
+                    const uint32_t wk0 = w_lo0 + static_cast<uint32_t>(k0) * KH16;
+                    const uint32_t wk1 = wk0 + n0 * KH16;
 #pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) {
-                            uint32_t a_lo = s_lo0 + kw * ROW16;
-                            for (uint32_t c = 0; c < kch; ++c) {
+                    for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-                                for (int kk = 0; kk < BK / 16; ++kk) {
-                                    umma_bf16_lo(d_tmem, a_lo + 2 * kk, w_lo + 2 * kk, desc_hi, idesc, accum);
-                                    accum = 1u;
-                                }
-                                a_lo += HALO16;
-                                w_lo += WT16;
+                        for (int c = 0; c < KCH; ++c) {
+#pragma unroll
+                            for (int kk = 0; kk < BK / 16; ++kk) {
+                                const uint32_t a_lo = s_lo0 + (kw * ROW16 + c * HALO16 + 2 * kk);
+                                const uint32_t w_off = (kw * KCH + c) * WS16 + 2 * kk;
+                                umma_acc_lo(d0, a_lo, wk0 + w_off, desc_hi, i0);
+                                if (n1) umma_acc_lo(d1, a_lo, wk1 + w_off, desc_hi, i1);
                             }
                         }
-                        if (dh == 0 && kch2) {
-                            uint32_t a_lo = s_lo0 + kch * HALO16;
-                            uint32_t w2 = w_lo0 + 9u * kch * WT16;
-                            for (uint32_t c = 0; c < kch2; ++c) {
+                    }
+                    if (kch2 && j >= hb && j < he) {   // fused 1x1 shortcut: centre row only -> accumulator of row j
+                        const uint32_t gc = g0 + static_cast<uint32_t>(j - hb);
+                        const uint32_t dc = tmem_base + ((NACC - 1) - (gc % NACC)) * BN;
+                        uint32_t a_lo = s_lo0 + KCH * HALO16;
+                        uint32_t w2 = w_lo0 + 3u * KCH * WS16;
+                        for (uint32_t c = 0; c < kch2; ++c) {
 #pragma unroll
-                                for (int kk = 0; kk < BK / 16; ++kk) umma_bf16_lo(d_tmem, a_lo + 2 * kk, w2 + 2 * kk, desc_hi, idesc, 1u);
-                                a_lo += X216;
-                                w2 += WT16;
-                            }
+                            for (int kk = 0; kk < BK / 16; ++kk) umma_acc_lo(dc, a_lo + 2 * kk, w2 + 2 * kk, desc_hi, idesc1);
+                            a_lo += X216;
+                            w2 += WT16;
                         }
                     }
                     umma_commit(&empty_bar[slot]);     // the row slot can be refilled once these MMAs retire
                     if (j - 1 >= hb && j - 1 < he) umma_commit(&tfull_bar[(g0 + static_cast<uint32_t>(j - 1 - hb)) % NACC]);
                     if (j == p.H - 1 && j >= hb && j < he) umma_commit(&tfull_bar[(g0 + static_cast<uint32_t>(j - hb)) % NACC]);
-                    if (++slot == p.nslot) { slot = 0; phase ^= 1; }
+                    if (++slot == static_cast<uint32_t>(p.nslot)) { slot = 0; phase ^= 1; }
                 }
                 g0 += static_cast<uint32_t>(he - hb);
             }
+            if (p.dbg && blockIdx.x == 0) { p.dbg[4] = clock64() - c_start; p.dbg[5] = c_full; p.dbg[6] = c_tempty; }
         }
         __syncwarp();
     } else {
@@ -230,6 +283,8 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* bsm = bias_sm + set * 64;
         const uint32_t set_bar = 1 + set;             // named barrier id of this warp set (128 threads)
         uint32_t g0 = 0;
+        long long c_tfull = 0, c_rows = 0;
+        const long long c_start = clock64();
         for (int it = blockIdx.x; it < items; it += gridDim.x) {
             int img, hb, he, w0;
             decode(it, img, hb, he, w0);
@@ -253,14 +308,22 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int r = hb + (Cfg::ROW_SPLIT ? set : 0); r < he; r += (Cfg::ROW_SPLIT ? 2 : 1)) {
                 const uint32_t g = g0 + static_cast<uint32_t>(r - hb);
                 const uint32_t acc = g % NACC;
-                mbar_wait(&tfull_bar[acc], (g / NACC) & 1);
+                {
+                    const long long _t0 = clock64();
+                    mbar_wait_warp(&tfull_bar[acc], (g / NACC) & 1, lane);
+                    c_tfull += clock64() - _t0;
+                }
+                ++c_rows;
                 tc_fence_after();
                 const long long pix = static_cast<long long>(r) * p.W + w0 + m;
-                const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + colbase;
+                const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ((NACC - 1) - acc) * BN + colbase;
                 uint32_t rr[CPT / 16][16];
 #pragma unroll
                 for (int q = 0; q < CPT / 16; ++q) tmem_ld_x16(t_addr + q * 16, rr[q]);
                 tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < CPT / 16; ++q) tmem_zero_x16(t_addr + q * 16);   // re-arm: every MMA accumulates
+                tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);          // accumulator is in registers: release it early
@@ -331,6 +394,8 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             g0 += static_cast<uint32_t>(he - hb);
         }
+        if (p.dbg && blockIdx.x == 0 && ethread == 0) { p.dbg[8] = clock64() - c_start; p.dbg[9] = c_tfull; p.dbg[10] = c_rows; }
+        if (p.dbg && blockIdx.x == 0 && ethread == 128) { p.dbg[12] = clock64() - c_start; p.dbg[13] = c_tfull; p.dbg[14] = c_rows; }
     }
     tc_fence_before();
     __syncthreads();
