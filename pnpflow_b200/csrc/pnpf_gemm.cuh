@@ -202,8 +202,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer (one lane) =====================
-        if (lane == 0) {
+        // ===================== TMA producer: converged warp, one ELECTED lane issues (see elect_one_sync) =====================
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -215,24 +215,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES_RAW);
-                    if (i < nk_main) {
-                        const int tap = i / p.kchunks;
-                        const int ch = i - tap * p.kchunks;
-                        tma_load_4d(sa, &tmA, &full_bar[stage], p.c_base + ch * BK, w0 * p.in_stride + p.dw[tap],
-                                    h0 * p.in_stride + p.dh[tap], ab);
-                    } else {
-                        tma_load_4d(sa, &tmA2, &full_bar[stage], (i - nk_main) * BK, w0, h0, ab);
+                    if (elect_one_sync()) {
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES_RAW);
+                        if (i < nk_main) {
+                            const int tap = i / p.kchunks;
+                            const int ch = i - tap * p.kchunks;
+                            tma_load_4d(sa, &tmA, &full_bar[stage], p.c_base + ch * BK, w0 * p.in_stride + p.dw[tap],
+                                        h0 * p.in_stride + p.dh[tap], ab);
+                        } else {
+                            tma_load_4d(sa, &tmA2, &full_bar[stage], (i - nk_main) * BK, w0, h0, ab);
+                        }
+                        tma_load_3d(sb, &tmB, &full_bar[stage], i * BK, nt * BN, bb);
                     }
-                    tma_load_3d(sb, &tmB, &full_bar[stage], i * BK, nt * BN, bb);
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer (one lane) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer: converged warp, one ELECTED lane issues =====================
+        {
             constexpr uint32_t idesc = make_idesc_bf16(128, BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -248,15 +251,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint64_t adesc = make_smem_desc<Cfg::kRowBytes>(sa);
                     const uint64_t bdesc = make_smem_desc<Cfg::kRowBytes>(sa + Cfg::A_BYTES);
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int kk = 0; kk < BK / 16; ++kk) {
-                        // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr>>4) field
-                        umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) ? 1u : 0u);
+                        for (int kk = 0; kk < BK / 16; ++kk) {
+                            // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr>>4) field
+                            umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) ? 1u : 0u);
+                        }
+                        umma_commit(&empty_bar[stage]);           // frees the smem slot when these MMAs retire
+                        if (i == nk - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
                     }
-                    umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);                     // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }

@@ -154,15 +154,21 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            mbar_arrive_expect_tx(wbar, (9 * KCH + p.kchunks2) * Cfg::W_TILE_RAW);
-            for (int kw = 0; kw < 3; ++kw)
-                for (int c = 0; c < KCH; ++c)
-                    for (int kh = 0; kh < 3; ++kh)      // packed K order is (kh, kw, cin): see pack_conv_weight
-                        tma_load_3d(wsm + (kw * KCH + c) * Cfg::W_STACK + kh * Cfg::KH_BYTES, &tmB, wbar,
-                                    ((kh * 3 + kw) * KCH + c) * BK, 0, 0);
-            for (int c = 0; c < p.kchunks2; ++c)
-                tma_load_3d(wsm + 3 * KCH * Cfg::W_STACK + c * Cfg::W_TILE, &tmB, wbar, (9 * KCH + c) * BK, 0, 0);
+        // The whole warp stays converged and computes warp-uniform values; only the async instructions are issued by
+        // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers — a divergent `lane == 0`
+        // branch forces R2UR moves and a uniformisation loop around every TMA / MMA instruction).
+        {
+            if (elect_one_sync()) {
+                mbar_arrive_expect_tx(wbar, (9 * KCH + p.kchunks2) * Cfg::W_TILE_RAW);
+                for (int kw = 0; kw < 3; ++kw)
+                    for (int c = 0; c < KCH; ++c)
+                        for (int kh = 0; kh < 3; ++kh)      // packed K order is (kh, kw, cin): see pack_conv_weight
+                            tma_load_3d(wsm + (kw * KCH + c) * Cfg::W_STACK + kh * Cfg::KH_BYTES, &tmB, wbar,
+                                        ((kh * 3 + kw) * KCH + c) * BK, 0, 0);
+                for (int c = 0; c < p.kchunks2; ++c)
+                    tma_load_3d(wsm + 3 * KCH * Cfg::W_STACK + c * Cfg::W_TILE, &tmB, wbar, (9 * KCH + c) * BK, 0, 0);
+            }
+            __syncwarp();
             int slot = 0;
             uint32_t phase = 0;
             long long c_wait = 0, c_rows = 0;
@@ -176,22 +182,25 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     ++c_rows;
                     uint8_t* sp = slots + slot * p.slot_bytes;
                     const bool centre = (j >= hb) && (j < he) && p.kchunks2;
-                    mbar_arrive_expect_tx(&full_bar[slot], KCH * Cfg::HALO_ROWS * Cfg::kRowBytes + (centre ? p.kchunks2 * Cfg::X2_TILE : 0));
+                    if (elect_one_sync()) {
+                        mbar_arrive_expect_tx(&full_bar[slot], KCH * Cfg::HALO_ROWS * Cfg::kRowBytes + (centre ? p.kchunks2 * Cfg::X2_TILE : 0));
 #pragma unroll
-                    for (int c = 0; c < KCH; ++c)
-                        tma_load_4d(sp + c * Cfg::HALO_TILE, &tmA, &full_bar[slot], c * BK, w0 - 1, j, img);
-                    if (centre)
-                        for (int c = 0; c < p.kchunks2; ++c)
-                            tma_load_4d(sp + KCH * Cfg::HALO_TILE + c * Cfg::X2_TILE, &tmA2, &full_bar[slot], c * BK, w0, j, img);
+                        for (int c = 0; c < KCH; ++c)
+                            tma_load_4d(sp + c * Cfg::HALO_TILE, &tmA, &full_bar[slot], c * BK, w0 - 1, j, img);
+                        if (centre)
+                            for (int c = 0; c < p.kchunks2; ++c)
+                                tma_load_4d(sp + KCH * Cfg::HALO_TILE + c * Cfg::X2_TILE, &tmA2, &full_bar[slot], c * BK, w0, j, img);
+                    }
+                    __syncwarp();
                     if (++slot == p.nslot) { slot = 0; phase ^= 1; }
                 }
             }
-            if (p.dbg && blockIdx.x == 0) { p.dbg[0] = clock64() - c_start; p.dbg[1] = c_wait; p.dbg[2] = c_rows; }
+            if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[0] = clock64() - c_start; p.dbg[1] = c_wait; p.dbg[2] = c_rows; }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (converged warp, elected lane issues) =====================
+        {
             // descriptor words: hi is shared by every operand tile; lo = (addr >> 4) | LBO bit
             const uint64_t proto = make_smem_desc<Cfg::kRowBytes>(0);
             const uint32_t desc_hi = static_cast<uint32_t>(proto >> 32);
@@ -238,39 +247,42 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t i1 = n1 == 2 ? idesc2 : idesc1;
                     const uint32_t wk0 = w_lo0 + static_cast<uint32_t>(k0) * KH16;
                     const uint32_t wk1 = wk0 + n0 * KH16;
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
+                        for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-                        for (int c = 0; c < KCH; ++c) {
+                            for (int c = 0; c < KCH; ++c) {
 #pragma unroll
-                            for (int kk = 0; kk < BK / 16; ++kk) {
-                                const uint32_t a_lo = s_lo0 + (kw * ROW16 + c * HALO16 + 2 * kk);
-                                const uint32_t w_off = (kw * KCH + c) * WS16 + 2 * kk;
-                                umma_acc_lo(d0, a_lo, wk0 + w_off, desc_hi, i0);
-                                if (n1) umma_acc_lo(d1, a_lo, wk1 + w_off, desc_hi, i1);
+                                for (int kk = 0; kk < BK / 16; ++kk) {
+                                    const uint32_t a_lo = s_lo0 + (kw * ROW16 + c * HALO16 + 2 * kk);
+                                    const uint32_t w_off = (kw * KCH + c) * WS16 + 2 * kk;
+                                    umma_acc_lo(d0, a_lo, wk0 + w_off, desc_hi, i0);
+                                    if (n1) umma_acc_lo(d1, a_lo, wk1 + w_off, desc_hi, i1);
+                                }
                             }
                         }
-                    }
-                    if (kch2 && j >= hb && j < he) {   // fused 1x1 shortcut: centre row only -> accumulator of row j
-                        const uint32_t gc = g0 + static_cast<uint32_t>(j - hb);
-                        const uint32_t dc = tmem_base + ((NACC - 1) - (gc % NACC)) * BN;
-                        uint32_t a_lo = s_lo0 + KCH * HALO16;
-                        uint32_t w2 = w_lo0 + 3u * KCH * WS16;
-                        for (uint32_t c = 0; c < kch2; ++c) {
+                        if (kch2 && j >= hb && j < he) {   // fused 1x1 shortcut: centre row only -> accumulator of row j
+                            const uint32_t gc = g0 + static_cast<uint32_t>(j - hb);
+                            const uint32_t dc = tmem_base + ((NACC - 1) - (gc % NACC)) * BN;
+                            uint32_t a_lo = s_lo0 + KCH * HALO16;
+                            uint32_t w2 = w_lo0 + 3u * KCH * WS16;
+                            for (uint32_t c = 0; c < kch2; ++c) {
 #pragma unroll
-                            for (int kk = 0; kk < BK / 16; ++kk) umma_acc_lo(dc, a_lo + 2 * kk, w2 + 2 * kk, desc_hi, idesc1);
-                            a_lo += X216;
-                            w2 += WT16;
+                                for (int kk = 0; kk < BK / 16; ++kk) umma_acc_lo(dc, a_lo + 2 * kk, w2 + 2 * kk, desc_hi, idesc1);
+                                a_lo += X216;
+                                w2 += WT16;
+                            }
                         }
+                        umma_commit(&empty_bar[slot]);     // the row slot can be refilled once these MMAs retire
+                        if (j - 1 >= hb && j - 1 < he) umma_commit(&tfull_bar[(g0 + static_cast<uint32_t>(j - 1 - hb)) % NACC]);
+                        if (j == p.H - 1 && j >= hb && j < he) umma_commit(&tfull_bar[(g0 + static_cast<uint32_t>(j - hb)) % NACC]);
                     }
-                    umma_commit(&empty_bar[slot]);     // the row slot can be refilled once these MMAs retire
-                    if (j - 1 >= hb && j - 1 < he) umma_commit(&tfull_bar[(g0 + static_cast<uint32_t>(j - 1 - hb)) % NACC]);
-                    if (j == p.H - 1 && j >= hb && j < he) umma_commit(&tfull_bar[(g0 + static_cast<uint32_t>(j - hb)) % NACC]);
+                    __syncwarp();
                     if (++slot == static_cast<uint32_t>(p.nslot)) { slot = 0; phase ^= 1; }
                 }
                 g0 += static_cast<uint32_t>(he - hb);
             }
-            if (p.dbg && blockIdx.x == 0) { p.dbg[4] = clock64() - c_start; p.dbg[5] = c_full; p.dbg[6] = c_tempty; }
+            if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[4] = clock64() - c_start; p.dbg[5] = c_full; p.dbg[6] = c_tempty; }
         }
         __syncwarp();
     } else {
