@@ -133,6 +133,12 @@ int pnpf_push_accum(const float* zt, const float* v, float t, int S, float* x_ne
 int pnpf_conv2d_nhwc(const void* x, int B, int Hin, int Win, int Cin, const float* host_w, const float* host_bias, int Cout,
                      int ksize, int stride, const void* x2, int C2, const float* host_w2, const void* residual, void* out,
                      int out_f32, void* stream);
+/* out = conv3x3(act(GroupNorm_32(cat[xa | xb]))) + bias with the GroupNorm(+SiLU) applied INSIDE the row-streaming conv kernel
+ * (shared-memory transform between TMA and MMA) and the concat read straight from its two sources (xb may be NULL).
+ * models.py:94-101 (norm1 -> act -> conv1 on torch.cat([h, skip])).  Needs W % 128 == 0 and Cout <= 64.  Synchronous. */
+int pnpf_gn_conv2d_nhwc(const void* xa, int Ca, const void* xb, int Cb, int B, int H, int W, const float* host_gamma,
+                        const float* host_beta, const float* host_w, const float* host_bias, int Cout, int silu, void* out,
+                        int out_f32, void* stream);
 /* out[b] = A[b] (M x K) * Bm[b]^T (N x K), bf16 row-major operands, fp32 (out_f32=1) or bf16 output. Synchronous. */
 int pnpf_gemm_nt(const void* A, const void* Bm, void* out, int batch, int M, int N, int K, int out_f32, void* stream);
 

@@ -56,6 +56,7 @@ SYMBOLS = {
     "pnpf_interp": (_I, [_VP, _VP, _F, _VP, _LL, _I, _VP]),
     "pnpf_push_accum": (_I, [_VP, _VP, _F, _I, _VP, _LL, _VP]),
     "pnpf_conv2d_nhwc": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _I, _VP]),
+    "pnpf_gn_conv2d_nhwc": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _I, _I, _VP, _I, _VP]),
     "pnpf_gemm_nt": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
 }
 

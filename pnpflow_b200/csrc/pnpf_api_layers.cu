@@ -89,3 +89,55 @@ extern "C" int pnpf_gemm_nt(const void* A, const void* Bm, void* out, int batch,
     PNPF_CHECK_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
+
+#include "pnpf_kernels.cuh"
+
+extern "C" int pnpf_gn_conv2d_nhwc(const void* xa, int Ca, const void* xb, int Cb, int B, int H, int W, const float* host_gamma,
+                                   const float* host_beta, const float* host_w, const float* host_bias, int Cout, int silu,
+                                   void* out, int out_f32, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PNPF_REQUIRE(xa && host_gamma && host_beta && host_w && out, "null pointer");
+    PNPF_REQUIRE(Cout % 16 == 0, "Cout %% 16");
+    const int Cin = Ca + Cb;
+    const int N_pad = round_up_n(Cout);
+    const long long Ktot = 9LL * Cin;
+    std::vector<bf16> wp((size_t)N_pad * Ktot);
+    pack_conv_weight(wp.data(), host_w, Cout, Cin, 3, N_pad, Cin, nullptr, 0, 1.0f);
+    std::vector<float> bp(N_pad, 0.f);
+    if (host_bias)
+        for (int i = 0; i < Cout; ++i) bp[i] = host_bias[i];
+    bf16* dw = nullptr;
+    float *db = nullptr, *dg = nullptr, *dbeta = nullptr;
+    double *sta = nullptr, *stb = nullptr;
+    PNPF_CHECK_CUDA(cudaMalloc(&dw, wp.size() * sizeof(bf16)));
+    PNPF_CHECK_CUDA(cudaMalloc(&db, bp.size() * sizeof(float)));
+    PNPF_CHECK_CUDA(cudaMalloc(&dg, Cin * sizeof(float)));
+    PNPF_CHECK_CUDA(cudaMalloc(&dbeta, Cin * sizeof(float)));
+    PNPF_CHECK_CUDA(cudaMalloc(&sta, (size_t)B * Ca * 2 * sizeof(double)));
+    PNPF_CHECK_CUDA(cudaMalloc(&stb, (size_t)B * (Cb ? Cb : 1) * 2 * sizeof(double)));
+    PNPF_CHECK_CUDA(cudaMemcpyAsync(dw, wp.data(), wp.size() * sizeof(bf16), cudaMemcpyHostToDevice, s));
+    PNPF_CHECK_CUDA(cudaMemcpyAsync(db, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    PNPF_CHECK_CUDA(cudaMemcpyAsync(dg, host_gamma, Cin * sizeof(float), cudaMemcpyHostToDevice, s));
+    PNPF_CHECK_CUDA(cudaMemcpyAsync(dbeta, host_beta, Cin * sizeof(float), cudaMemcpyHostToDevice, s));
+    PNPF_CHECK_CUDA(cudaMemsetAsync(sta, 0, (size_t)B * Ca * 2 * sizeof(double), s));
+    PNPF_CHECK_CUDA(cudaMemsetAsync(stb, 0, (size_t)B * (Cb ? Cb : 1) * 2 * sizeof(double), s));
+    int rc = launch_gn_stats(GnSrc{static_cast<const bf16*>(xa), Ca, Ca, nullptr, 0, 0, nullptr, nullptr}, B, H * W, sta, s);
+    if (!rc && Cb) rc = launch_gn_stats(GnSrc{static_cast<const bf16*>(xb), Cb, Cb, nullptr, 0, 0, nullptr, nullptr}, B, H * W, stb, s);
+    ConvDesc d;
+    d.x = static_cast<const bf16*>(xa); d.x_pitch = Ca; d.Cin = Cin;
+    d.xb = static_cast<const bf16*>(xb); d.Cb = Cb; d.xb_pitch = Cb;
+    d.B = B; d.Hin = d.Hout = H; d.Win = d.Wout = W;
+    d.w = dw; d.N_pad = N_pad; d.ksize = 3; d.stride = 1;
+    d.out = out; d.out_mode = out_f32 ? 1 : 0;
+    d.out_img_stride = (long long)H * W * Cout; d.out_row_stride = Cout; d.n_valid = Cout;
+    d.bias = db;
+    d.gn_gamma = dg; d.gn_beta = dbeta; d.gn_stats_a = sta; d.gn_stats_b = Cb ? stb : nullptr; d.gn_silu = silu;
+    TcOp op;
+    if (!rc) rc = prepare_conv(op, d);
+    if (!rc) rc = launch_tc(op, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(dw); cudaFree(db); cudaFree(dg); cudaFree(dbeta); cudaFree(sta); cudaFree(stb);
+    if (rc) return rc;
+    PNPF_CHECK_CUDA(e);
+    return 0;
+}

@@ -38,24 +38,41 @@ static void fill_epi(EpiParams& e, const ConvDesc& d) {
 constexpr int ROWCONV_SMEM_BUDGET = 200 * 1024;
 int rowconv_max_smem() { return ROWCONV_SMEM_BUDGET + 1024 + 512; }
 
-// Row-streaming kernel eligibility + preparation; returns -1 when the shape does not qualify (caller falls back).
-static int try_prepare_rowconv(TcOp& op, const ConvDesc& d) {
-    if (!d.allow_rowconv || d.ksize != 3 || d.stride != 1 || d.Wout % 128 != 0 || d.Wout != d.Win || d.Hout != d.Hin) return -1;
-    if (!(d.N_pad == 16 || d.N_pad == 32 || d.N_pad == 64) || d.c_base != 0) return -1;
-    if (d.Cin % 32 != 0 || d.C2 % 32 != 0) return -1;
-    const int BK = (d.Cin % 64 == 0 && d.C2 % 64 == 0) ? 64 : 32;
-    const int BN = d.N_pad;
-    const int rowb = BK * 2;
+// Row-streaming kernel: shape analysis shared by rowconv_eligible() and the preparation.
+struct RowShape { int BK, BN, kch, kch2, kch_a, kch2_a, w_bytes, slot_bytes, nslot; };
+static bool rowconv_shape(const ConvDesc& d, RowShape& r) {
+    if (!d.allow_rowconv || d.ksize != 3 || d.stride != 1 || d.Wout % 128 != 0 || d.Wout != d.Win || d.Hout != d.Hin) return false;
+    if (!(d.N_pad == 16 || d.N_pad == 32 || d.N_pad == 64) || d.c_base != 0) return false;
+    const int Ca = d.Cin - d.Cb, C2a = d.C2 - d.C2b;
+    if (d.Cin % 32 || d.C2 % 32 || Ca % 32 || d.Cb % 32 || C2a % 32 || d.C2b % 32 || Ca <= 0) return false;
+    r.BK = (Ca % 64 == 0 && d.Cb % 64 == 0 && C2a % 64 == 0 && d.C2b % 64 == 0) ? 64 : 32;
+    r.BN = d.N_pad;
+    const int rowb = r.BK * 2;
     const int halo_tile = (136 * rowb + 1023) / 1024 * 1024, x2_tile = 128 * rowb;
-    const int w_tile = (BN * BK * 2 + 1023) / 1024 * 1024;
-    const int kch = d.Cin / BK, kch2 = d.x2 ? d.C2 / BK : 0;
-    if (kch < 1 || kch > 3) return -1;
-    if ((BN * rowb) % 1024 != 0) return -1;       // stacked vertical-tap tiles must keep the swizzle phase
-    const int w_bytes = 3 * kch * (3 * BN * rowb) + kch2 * w_tile;
-    const int slot_bytes = kch * halo_tile + kch2 * x2_tile;
-    int nslot = (ROWCONV_SMEM_BUDGET - w_bytes) / slot_bytes;
-    if (nslot > 8) nslot = 8;
-    if (nslot < 4) return -1;
+    const int w_tile = (r.BN * r.BK * 2 + 1023) / 1024 * 1024;
+    r.kch = d.Cin / r.BK;
+    r.kch2 = d.C2 > 0 ? d.C2 / r.BK : 0;        // by channel count, not pointer: the size-query plan has no pointers
+    r.kch_a = Ca / r.BK;
+    r.kch2_a = d.C2 > 0 ? C2a / r.BK : 0;
+    if (r.kch < 1 || r.kch > 3) return false;
+    if ((r.BN * rowb) % 1024 != 0) return false;    // stacked vertical-tap tiles must keep the swizzle phase
+    if (d.gn_gamma && d.Cin > 128) return false;     // scale/shift table
+    r.w_bytes = 3 * r.kch * (3 * r.BN * rowb) + r.kch2 * w_tile;
+    r.slot_bytes = r.kch * halo_tile + r.kch2 * x2_tile;
+    r.nslot = (ROWCONV_SMEM_BUDGET - r.w_bytes) / r.slot_bytes;
+    if (r.nslot > 8) r.nslot = 8;
+    return r.nslot >= 4;
+}
+bool rowconv_eligible(const ConvDesc& d) {
+    RowShape r;
+    return rowconv_shape(d, r);
+}
+
+// returns -1 when the shape does not qualify (caller falls back to the per-tap kernel)
+static int try_prepare_rowconv(TcOp& op, const ConvDesc& d) {
+    RowShape sh;
+    if (!rowconv_shape(d, sh)) return -1;
+    const int BK = sh.BK, BN = sh.BN;
     RowConvParams& r = op.rp;
     memset(&r, 0, sizeof(r));
     r.H = d.Hout; r.W = d.Wout; r.n_img = d.B;
@@ -64,15 +81,26 @@ static int try_prepare_rowconv(TcOp& op, const ConvDesc& d) {
     while (seg > 8 && (long long)d.B * r.strips * ((d.Hout + seg - 1) / seg) < 3LL * num_sms()) seg >>= 1;
     r.seg_rows = seg;
     r.segs = (d.Hout + seg - 1) / seg;
-    r.kchunks = kch; r.kchunks2 = kch2; r.nslot = nslot; r.slot_bytes = slot_bytes;
+    r.kchunks = sh.kch; r.kchunks2 = sh.kch2; r.nslot = sh.nslot; r.slot_bytes = sh.slot_bytes;
+    r.kch_a = sh.kch_a; r.kch2_a = sh.kch2_a;
+    if (d.gn_gamma) {
+        PNPF_REQUIRE(d.gn_beta && d.gn_stats_a && (d.Cb == 0 || d.gn_stats_b), "fused GroupNorm needs beta and statistics");
+        PNPF_REQUIRE(d.Cin % d.gn_groups == 0, "GroupNorm: %d channels not divisible into %d groups", d.Cin, d.gn_groups);
+        r.gn = 1; r.gn_silu = d.gn_silu; r.gn_gs = d.Cin / d.gn_groups; r.gn_Ca = d.Cin - d.Cb; r.gn_Cb = d.Cb; r.gn_eps = d.gn_eps;
+        r.gn_gamma = d.gn_gamma; r.gn_beta = d.gn_beta; r.gn_st_a = d.gn_stats_a; r.gn_st_b = d.gn_stats_b;
+    }
     fill_epi(r.epi, d);
     op.kind = 1; op.BK = BK; op.BN = BN;
     const long long Ktot = 9LL * d.Cin + (d.x2 ? d.C2 : 0);
-    if (int e = make_act_tmap(&op.tmA, d.x, d.Cin, d.x_pitch, d.Win, d.Hin, d.B, BK, 130, 1, 1)) return e;
+    if (int e = make_act_tmap(&op.tmA, d.x, d.Cin - d.Cb, d.x_pitch, d.Win, d.Hin, d.B, BK, 130, 1, 1)) return e;
+    op.tmAb = op.tmA;
+    if (d.Cb) { if (int e = make_act_tmap(&op.tmAb, d.xb, d.Cb, d.xb_pitch, d.Win, d.Hin, d.B, BK, 130, 1, 1)) return e; }
+    op.tmA2 = op.tmA;
+    op.tmA2b = op.tmA;
     if (d.x2) {
-        if (int e = make_act_tmap(&op.tmA2, d.x2, d.C2, d.x2_pitch, d.Wout, d.Hout, d.B, BK, 128, 1, 1)) return e;
-    } else {
-        op.tmA2 = op.tmA;
+        if (int e = make_act_tmap(&op.tmA2, d.x2, d.C2 - d.C2b, d.x2_pitch, d.Wout, d.Hout, d.B, BK, 128, 1, 1)) return e;
+        op.tmA2b = op.tmA2;
+        if (d.C2b) { if (int e = make_act_tmap(&op.tmA2b, d.x2b, d.C2b, d.x2b_pitch, d.Wout, d.Hout, d.B, BK, 128, 1, 1)) return e; }
     }
     if (int e = make_b_tmap(&op.tmB, d.w, Ktot, Ktot, d.N_pad, 1, 0, BK, BN)) return e;
     op.flops = 2.0 * d.B * d.Hout * d.Wout * (double)d.n_valid * (double)Ktot;
@@ -85,6 +113,8 @@ int prepare_conv(TcOp& op, const ConvDesc& d) {
         const int rc = try_prepare_rowconv(op, d);
         if (rc >= 0) return rc;
     }
+    PNPF_REQUIRE(!d.xb && !d.x2b && !d.gn_gamma, "two-source / fused-GroupNorm convolution needs the row-streaming kernel "
+                 "(3x3 stride 1, W %% 128 == 0, C_out <= 64): check rowconv_eligible() first");
     op.kind = 0;
     PNPF_REQUIRE(d.stride == 1 || d.stride == 2, "conv stride %d unsupported (1 or 2)", d.stride);
     PNPF_REQUIRE(d.Cin % 32 == 0 && d.C2 % 32 == 0, "conv channels (%d,%d) must be multiples of 32", d.Cin, d.C2);
@@ -187,7 +217,7 @@ static int launch_row_t(const TcOp& op, cudaStream_t stream) {
     const long long items = (long long)r.n_img * r.segs * r.strips;
     const int grid = (int)(items < num_sms() ? items : num_sms());
     if (grid < 1) return 0;
-    rowconv_kernel<BK, BN, KCH><<<grid, Cfg::THREADS, smem, stream>>>(op.tmA, op.tmA2, op.tmB, r);
+    rowconv_kernel<BK, BN, KCH><<<grid, Cfg::THREADS, smem, stream>>>(op.tmA, op.tmAb, op.tmA2, op.tmA2b, op.tmB, r);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

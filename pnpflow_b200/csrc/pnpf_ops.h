@@ -9,7 +9,7 @@ typedef __nv_bfloat16 bf16;
 
 // ------------------------------------------------------------------ tensor-core ops
 struct TcOp {               // a prepared conv_gemm launch
-    CUtensorMap tmA, tmA2, tmB;
+    CUtensorMap tmA, tmAb, tmA2, tmA2b, tmB;   // *b: second source of a channel concat (row conv only)
     GemmParams p;
     RowConvParams rp;       // kind == 1: row-streaming conv (pnpf_rowconv.cuh)
     int kind = 0;           // 0: conv_gemm_kernel, 1: rowconv_kernel
@@ -44,8 +44,24 @@ struct ConvDesc {
     long long res_img_stride = 0, res_row_stride = 0;
     double* stats_out = nullptr;    // optional [B][n_valid][2] GroupNorm statistics of the output (must be zeroed)
     int allow_rowconv = 1;          // use the row-streaming kernel when the shape qualifies
+    // ---- row-streaming kernel only (rowconv_eligible(d) must hold, else prepare_conv fails loudly) ----
+    // channel concat [x | xb] as main input, [x2 | x2b] as fused 1x1 input: Cin / C2 are the TOTAL channel counts
+    const bf16* xb = nullptr;
+    int Cb = 0;
+    long long xb_pitch = 0;
+    const bf16* x2b = nullptr;
+    int C2b = 0;
+    long long x2b_pitch = 0;
+    // fused GroupNorm(+SiLU) of the main input with statistics from the producers' epilogues
+    const float* gn_gamma = nullptr;
+    const float* gn_beta = nullptr;
+    const double* gn_stats_a = nullptr;
+    const double* gn_stats_b = nullptr;
+    int gn_groups = 32, gn_silu = 1;
+    float gn_eps = 1e-6f;
 };
 int prepare_conv(TcOp& op, const ConvDesc& d);
+bool rowconv_eligible(const ConvDesc& d);     // would prepare_conv pick the row-streaming kernel?
 int rowconv_max_smem();
 
 struct GemmDesc {           // out[b][m][n] = sum_k A[b|0][m][k] * Bm[b|0][n][k]  (+bias[n]) (+residual)

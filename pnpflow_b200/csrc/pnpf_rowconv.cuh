@@ -32,6 +32,18 @@ struct RowConvParams {
     int kchunks2;          // C2 / BK of the fused 1x1 source (0 = none)
     int nslot;             // depth of the input-row ring
     int slot_bytes;
+    // The main input (and the fused 1x1 input) may be a channel concat [a | b] of two tensors (skip connections):
+    // the first kch_a (kch2_a) chunks are fetched through the "a" tensor map, the rest through the "b" map.
+    int kch_a, kch2_a;
+    // Fused GroupNorm(+SiLU) of the main input: the halo tile is normalised IN PLACE in shared memory by two transform
+    // warps between the TMA and the MMAs (per-channel statistics come from the producing conv's epilogue).
+    int gn;                // 0 = input is used as is
+    int gn_silu, gn_gs, gn_Ca, gn_Cb;    // activation flag, channels per group, channels of source a / b
+    float gn_eps;
+    const float* gn_gamma; // [Ca+Cb]
+    const float* gn_beta;
+    const double* gn_st_a; // [img][Ca][2]
+    const double* gn_st_b; // [img][Cb][2]
     long long* dbg;        // optional [16] cycle counters of CTA 0 (profiling experiments), else nullptr
     EpiParams epi;
 };
@@ -50,10 +62,10 @@ struct RowCfg {
     static constexpr int NACC = (512 / BN) > 16 ? 16 : (512 / BN);
     static constexpr int TMEM_COLS = NACC * BN;              // 256 (BN=16) or 512
     static constexpr int MAX_SLOTS = 8;
-    static constexpr int THREADS = 64 + 256;                 // producer, MMA issuer, 8 epilogue warps
+    static constexpr int THREADS = 64 + 256 + 64;            // producer, MMA issuer, 8 epilogue warps, 2 GroupNorm transform warps
     static constexpr int CPT = BN > 32 ? 32 : BN;            // columns per epilogue thread
     static constexpr bool ROW_SPLIT = BN <= 32;              // the two epilogue warp sets alternate rows (else: split columns)
-    static constexpr int BAR_BYTES = 1024;                   // barriers + tmem slot + bias staging (2 x 64 floats)
+    static constexpr int BAR_BYTES = 2048;                   // barriers + tmem slot | bias staging (2 x 64 floats) | GN scale/shift (2 x 128)
     static_assert(BN == 16 || BN == 32 || BN == 64, "row conv is for thin outputs");
 };
 
@@ -90,7 +102,8 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
 
 template <int BK, int BN, int KCH>
 __global__ void __launch_bounds__(RowCfg<BK, BN>::THREADS, 1)
-rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAb,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA2b,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ RowConvParams p) {
     using Cfg = RowCfg<BK, BN>;
     constexpr int NACC = Cfg::NACC;
@@ -107,7 +120,9 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull_bar = empty_bar + Cfg::MAX_SLOTS;
     uint64_t* tempty_bar = tfull_bar + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 16);
+    uint64_t* ready_bar = tempty_bar + 17;                          // [MAX_SLOTS] transform -> MMA (GroupNorm fusion)
     float* bias_sm = reinterpret_cast<float*>(bars) + 128;          // [2 sets][64] floats at byte offset 512
+    float* gn_tab = reinterpret_cast<float*>(bars) + 256;           // scale[128] | shift[128] at byte offset 1024
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -117,10 +132,13 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (p.kchunks2) tma_prefetch_desc(&tmA2);
+        if (p.kch_a < KCH) tma_prefetch_desc(&tmAb);
+        if (p.kch2_a < p.kchunks2) tma_prefetch_desc(&tmA2b);
         mbar_init(wbar, 1);
         for (int s = 0; s < Cfg::MAX_SLOTS; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+            mbar_init(&ready_bar[s], 2);
         }
         for (int a = 0; a < 16; ++a) {
             mbar_init(&tfull_bar[a], 1);
@@ -186,10 +204,12 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         mbar_arrive_expect_tx(&full_bar[slot], KCH * Cfg::HALO_ROWS * Cfg::kRowBytes + (centre ? p.kchunks2 * Cfg::X2_TILE : 0));
 #pragma unroll
                         for (int c = 0; c < KCH; ++c)
-                            tma_load_4d(sp + c * Cfg::HALO_TILE, &tmA, &full_bar[slot], c * BK, w0 - 1, j, img);
+                            tma_load_4d(sp + c * Cfg::HALO_TILE, c < p.kch_a ? &tmA : &tmAb, &full_bar[slot],
+                                        (c < p.kch_a ? c : c - p.kch_a) * BK, w0 - 1, j, img);
                         if (centre)
                             for (int c = 0; c < p.kchunks2; ++c)
-                                tma_load_4d(sp + KCH * Cfg::HALO_TILE + c * Cfg::X2_TILE, &tmA2, &full_bar[slot], c * BK, w0, j, img);
+                                tma_load_4d(sp + KCH * Cfg::HALO_TILE + c * Cfg::X2_TILE, c < p.kch2_a ? &tmA2 : &tmA2b, &full_bar[slot],
+                                            (c < p.kch2_a ? c : c - p.kch2_a) * BK, w0, j, img);
                     }
                     __syncwarp();
                     if (++slot == p.nslot) { slot = 0; phase ^= 1; }
@@ -239,7 +259,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (j == 0)                        // top image row (hb == 0): row 0 is opened by its centre tap
                         PNPF_TIMED_WAIT(&tempty_bar[g0 % NACC], ((g0 / NACC) & 1) ^ 1, c_tempty);
                     tc_fence_after();
-                    PNPF_TIMED_WAIT(&full_bar[slot], phase, c_full);
+                    PNPF_TIMED_WAIT(p.gn ? &ready_bar[slot] : &full_bar[slot], phase, c_full);
                     tc_fence_after();
                     const uint32_t s_lo0 = s_base_lo + slot * slot16;
                     const uint32_t d0 = tmem_base + blk0 * BN, d1 = tmem_base;
@@ -285,6 +305,83 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[4] = clock64() - c_start; p.dbg[5] = c_full; p.dbg[6] = c_tempty; }
         }
         __syncwarp();
+    } else if (warp >= 10) {
+        // ===================== GroupNorm(+SiLU) transform: warps 10, 11 normalise each halo tile in place =====================
+        if (p.gn) {
+            const int tt = threadIdx.x - 320;             // 0..63
+            const int Ctot = p.gn_Ca + p.gn_Cb;
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int it = blockIdx.x; it < items; it += gridDim.x) {
+                int img, hb, he, w0;
+                decode(it, img, hb, he, w0);
+                // per-image scale / shift of every input channel (a group may straddle the two concatenated sources)
+                asm volatile("bar.sync 3, 64;");
+                for (int c = tt; c < Ctot; c += 64) {
+                    const int g0c = (c / p.gn_gs) * p.gn_gs;
+                    double S = 0, Q = 0;
+                    for (int k = 0; k < p.gn_gs; ++k) {
+                        const int cc = g0c + k;
+                        const double* sp2 = (cc < p.gn_Ca) ? p.gn_st_a + (static_cast<long long>(img) * p.gn_Ca + cc) * 2
+                                                           : p.gn_st_b + (static_cast<long long>(img) * p.gn_Cb + (cc - p.gn_Ca)) * 2;
+                        S += sp2[0];
+                        Q += sp2[1];
+                    }
+                    const double n = static_cast<double>(p.gn_gs) * p.H * p.W;
+                    const double mean = S / n;
+                    double var = Q / n - mean * mean;
+                    if (var < 0) var = 0;
+                    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.gn_eps)));
+                    const float sc = rstd * __ldg(p.gn_gamma + c);
+                    gn_tab[c] = sc;
+                    gn_tab[128 + c] = __ldg(p.gn_beta + c) - static_cast<float>(mean) * sc;
+                }
+                asm volatile("bar.sync 3, 64;");
+                const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
+                for (int j = j0; j <= j1; ++j) {
+                    mbar_wait_warp(&full_bar[slot], phase, lane);
+                    uint8_t* sp = slots + slot * p.slot_bytes;
+#pragma unroll 1
+                    for (int r = tt; r < Cfg::HALO_ROWS; r += 64) {
+                        const int wpix = w0 - 1 + r;
+                        if (wpix < 0 || wpix >= p.W) continue;          // conv zero padding stays zero
+                        // 128B swizzle: 16B chunk index ^= (row & 7); 64B swizzle: ^= ((row >> 1) & 3)
+                        const int sw = (Cfg::kRowBytes == 128) ? (r & 7) : ((r >> 1) & 3);
+#pragma unroll
+                        for (int c = 0; c < KCH; ++c) {
+                            uint4* rowp = reinterpret_cast<uint4*>(sp + c * Cfg::HALO_TILE + r * Cfg::kRowBytes);
+#pragma unroll
+                            for (int q = 0; q < Cfg::kRowBytes / 16; ++q) {
+                                const int ch0 = c * BK + ((q ^ sw) << 3);      // first of the 8 channels held by physical chunk q
+                                uint4 u = rowp[q];
+                                uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                                for (int e2 = 0; e2 < 4; ++e2) {
+                                    const float2 sc2 = *reinterpret_cast<const float2*>(gn_tab + ch0 + 2 * e2);
+                                    const float2 sh2 = *reinterpret_cast<const float2*>(gn_tab + 128 + ch0 + 2 * e2);
+                                    float y0 = fmaf(__uint_as_float(wds[e2] << 16), sc2.x, sh2.x);
+                                    float y1 = fmaf(__uint_as_float(wds[e2] & 0xFFFF0000u), sc2.y, sh2.y);
+                                    if (p.gn_silu) {
+                                        float t0, t1;                              // silu(y) = 0.5 y (1 + tanh(0.5 y))
+                                        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.5f * y0));
+                                        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.5f * y1));
+                                        y0 = 0.5f * y0 * (1.f + t0);
+                                        y1 = 0.5f * y1 * (1.f + t1);
+                                    }
+                                    __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
+                                    wds[e2] = *reinterpret_cast<uint32_t*>(&b2);
+                                }
+                                rowp[q] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                            }
+                        }
+                    }
+                    fence_proxy_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ready_bar[slot]);
+                    if (++slot == p.nslot) { slot = 0; phase ^= 1; }
+                }
+            }
+        }
     } else {
         // ===================== epilogue: warps 2..5 = set 0, warps 6..9 = set 1 =====================
         const int set = (warp - 2) >> 2;

@@ -541,7 +541,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
         d.B = Bm;
         if (real) { if (int rc = prepare_conv(o.tc, d)) return rc; }
         o.flops = 2.0 * d.Hout * d.Wout * (double)d.n_valid * ((double)d.ksize * d.ksize * d.Cin + (d.x2 ? d.C2 : 0));
-        o.bytes = 2.0 * d.Hin * d.Win * d.Cin + (d.x2 ? 2.0 * d.Hout * d.Wout * d.C2 : 0.0) +
+        o.bytes = 2.0 * d.Hin * d.Win * d.Cin + (d.x2 ? 2.0 * d.Hout * d.Wout * d.C2 : 0.0) +   // Cin / C2 are concat totals
                   (d.residual ? 2.0 * d.Hout * d.Wout * d.n_valid : 0.0) +
                   (d.out_mode == 0 ? 2.0 : 4.0) * d.Hout * d.Wout * d.n_valid;
         flops += o.flops;
@@ -597,30 +597,61 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                     src = GnSrc{h.p, h.C, h.C, nullptr, 0, 0, h.stats, nullptr};
                 }
                 const bool sc = L.in_ch != L.out_ch;
-                add_gn(p + ".norm1", src, side, p + ".norm1", 1, t_a1, (L.skip_ch && sc) ? t_xcat : nullptr);
-                ConvDesc d1;
-                d1.x = t_a1; d1.Hin = d1.Win = d1.Hout = d1.Wout = side; d1.Cin = L.in_ch; d1.x_pitch = L.in_ch;
-                d1.N_pad = round_n(L.out_ch); d1.ksize = 3; d1.stride = 1;
-                if (real) { d1.w = wptr<bf16>(e, p + ".conv1.w"); d1.bias = wptr<float>(e, p + ".conv1.b"); }
-                d1.bias_img = real ? tproj + e->proj_off.at(p) : nullptr; d1.bias_img_stride = e->total_proj;
                 double* h1_stats = new_stats(L.out_ch);
+                Act y = new_h(L.out_ch, side, L.push);
+                // ---- conv1 (+ temb) and conv2 (+ shortcut / residual) descriptors in their FUSED form: GroupNorm+SiLU applied
+                //      inside the row-streaming kernel, concat inputs read straight from the two source tensors
+                ConvDesc d1;
+                d1.x = h.p; d1.x_pitch = h.C; d1.Cin = L.in_ch;
+                if (L.skip_ch) { d1.xb = skip.p; d1.Cb = skip.C; d1.xb_pitch = skip.C; }
+                d1.Hin = d1.Win = d1.Hout = d1.Wout = side;
+                d1.N_pad = round_n(L.out_ch); d1.ksize = 3; d1.stride = 1;
+                if (real) {
+                    d1.w = wptr<bf16>(e, p + ".conv1.w"); d1.bias = wptr<float>(e, p + ".conv1.b");
+                    d1.gn_gamma = wptr<float>(e, p + ".norm1.gamma"); d1.gn_beta = wptr<float>(e, p + ".norm1.beta");
+                } else {
+                    d1.gn_gamma = reinterpret_cast<const float*>(0x10); d1.gn_beta = d1.gn_gamma;   // shape analysis only
+                }
+                d1.gn_stats_a = h.stats; d1.gn_stats_b = L.skip_ch ? skip.stats : nullptr;
+                if (!real) { d1.gn_stats_a = reinterpret_cast<const double*>(0x10); d1.gn_stats_b = d1.gn_stats_a; }
+                d1.bias_img = real ? tproj + e->proj_off.at(p) : nullptr; d1.bias_img_stride = e->total_proj;
                 d1.stats_out = h1_stats;
                 d1.out = t_h1; d1.out_mode = 0; d1.out_img_stride = px * L.out_ch; d1.out_row_stride = L.out_ch; d1.n_valid = L.out_ch;
-                if (int rc = add_conv(p + ".conv1", d1, t_h1, L.out_ch, side)) return rc;
-                add_gn(p + ".norm2", GnSrc{t_h1, L.out_ch, L.out_ch, nullptr, 0, 0, h1_stats, nullptr}, side, p + ".norm2", 1, t_a2, nullptr);
-                Act y = new_h(L.out_ch, side, L.push);
                 ConvDesc d2;
-                d2.x = t_a2; d2.Hin = d2.Win = d2.Hout = d2.Wout = side; d2.Cin = L.out_ch; d2.x_pitch = L.out_ch;
+                d2.x = t_h1; d2.x_pitch = L.out_ch; d2.Cin = L.out_ch;
+                d2.Hin = d2.Win = d2.Hout = d2.Wout = side;
                 d2.N_pad = round_n(L.out_ch); d2.ksize = 3; d2.stride = 1;
-                if (real) { d2.w = wptr<bf16>(e, p + ".conv2.w"); d2.bias = wptr<float>(e, p + ".conv2.b"); }
+                if (real) {
+                    d2.w = wptr<bf16>(e, p + ".conv2.w"); d2.bias = wptr<float>(e, p + ".conv2.b");
+                    d2.gn_gamma = wptr<float>(e, p + ".norm2.gamma"); d2.gn_beta = wptr<float>(e, p + ".norm2.beta");
+                } else {
+                    d2.gn_gamma = reinterpret_cast<const float*>(0x10); d2.gn_beta = d2.gn_gamma;
+                }
+                d2.gn_stats_a = real ? h1_stats : reinterpret_cast<const double*>(0x10);
                 if (sc) {
-                    d2.x2 = L.skip_ch ? t_xcat : h.p; d2.C2 = L.in_ch; d2.x2_pitch = L.in_ch;
+                    d2.x2 = h.p; d2.x2_pitch = h.C; d2.C2 = L.in_ch;
+                    if (L.skip_ch) { d2.x2b = skip.p; d2.C2b = skip.C; d2.x2b_pitch = skip.C; }
                 } else {
                     PNPF_REQUIRE(!L.skip_ch, "internal: concat block without shortcut");
                     d2.residual = h.p; d2.res_img_stride = px * L.out_ch; d2.res_row_stride = L.out_ch;
                 }
                 d2.stats_out = y.stats;
                 d2.out = y.p; d2.out_mode = 0; d2.out_img_stride = px * L.out_ch; d2.out_row_stride = L.out_ch; d2.n_valid = L.out_ch;
+                bool fuse2 = rowconv_eligible(d2);
+                bool fuse1 = rowconv_eligible(d1);
+                if (!fuse2 && L.skip_ch && sc) fuse1 = false;       // the unfused conv2 needs the raw concat copy made by norm1
+                if (!fuse1) {                                        // separate GroupNorm pass -> normalised (concatenated) operand
+                    add_gn(p + ".norm1", src, side, p + ".norm1", 1, t_a1, (L.skip_ch && sc) ? t_xcat : nullptr);
+                    d1.x = t_a1; d1.x_pitch = L.in_ch; d1.xb = nullptr; d1.Cb = 0;
+                    d1.gn_gamma = d1.gn_beta = nullptr; d1.gn_stats_a = d1.gn_stats_b = nullptr;
+                }
+                if (int rc = add_conv(p + ".conv1", d1, t_h1, L.out_ch, side)) return rc;
+                if (!fuse2) {
+                    add_gn(p + ".norm2", GnSrc{t_h1, L.out_ch, L.out_ch, nullptr, 0, 0, h1_stats, nullptr}, side, p + ".norm2", 1, t_a2, nullptr);
+                    d2.x = t_a2;
+                    d2.gn_gamma = d2.gn_beta = nullptr; d2.gn_stats_a = nullptr;
+                    if (sc && L.skip_ch) { d2.x2 = t_xcat; d2.x2_pitch = L.in_ch; d2.x2b = nullptr; d2.C2b = 0; }
+                }
                 if (int rc = add_conv(p, d2, y.p, y.C, side)) return rc;
                 h = y;
                 break;
@@ -708,13 +739,24 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 break;
             }
             case LayerSpec::END: {
-                add_gn(p + ".0", GnSrc{h.p, h.C, h.C, nullptr, 0, 0, h.stats, nullptr}, side, p + ".0", 1, t_a1, nullptr);
                 ConvDesc d;
-                d.x = t_a1; d.Hin = d.Win = d.Hout = d.Wout = side; d.Cin = L.in_ch; d.x_pitch = L.in_ch;
+                d.x = h.p; d.x_pitch = h.C; d.Hin = d.Win = d.Hout = d.Wout = side; d.Cin = L.in_ch;
                 d.N_pad = round_n(L.out_ch); d.ksize = 3; d.stride = 1;
-                if (real) { d.w = wptr<bf16>(e, p + ".2.w"); d.bias = wptr<float>(e, p + ".2.b"); }
+                if (real) {
+                    d.w = wptr<bf16>(e, p + ".2.w"); d.bias = wptr<float>(e, p + ".2.b");
+                    d.gn_gamma = wptr<float>(e, p + ".0.gamma"); d.gn_beta = wptr<float>(e, p + ".0.beta");
+                    d.gn_stats_a = h.stats;
+                } else {
+                    d.gn_gamma = reinterpret_cast<const float*>(0x10); d.gn_beta = d.gn_gamma;
+                    d.gn_stats_a = reinterpret_cast<const double*>(0x10);
+                }
                 d.out = reinterpret_cast<void*>(0x10);         // patched per call with the caller's v pointer
                 d.out_mode = 2; d.out_img_stride = px * L.out_ch; d.out_row_stride = 1; d.out_col_stride = px; d.n_valid = L.out_ch;
+                if (!rowconv_eligible(d)) {
+                    add_gn(p + ".0", GnSrc{h.p, h.C, h.C, nullptr, 0, 0, h.stats, nullptr}, side, p + ".0", 1, t_a1, nullptr);
+                    d.x = t_a1; d.x_pitch = L.in_ch;
+                    d.gn_gamma = d.gn_beta = nullptr; d.gn_stats_a = nullptr;
+                }
                 if (int rc = add_conv(p + ".2", d, nullptr, 0, 0)) return rc;
                 break;
             }

@@ -71,6 +71,41 @@ def test_rowconv_wide_maps(B, H, W, Cin, Cout, C2, res):
     _conv_case(B, H, W, Cin, Cout, 3, 1, C2=C2, res=res, seed=H + W + Cin)
 
 
+@pytest.mark.parametrize("B,H,W,Ca,Cb,Cout,silu", [
+    (2, 64, 128, 32, 0, 32, 1), (1, 256, 256, 32, 0, 32, 1), (2, 40, 128, 64, 0, 32, 1), (2, 64, 128, 64, 32, 32, 1),
+    (1, 128, 256, 32, 32, 32, 1), (2, 64, 128, 64, 0, 64, 1), (2, 33, 128, 32, 0, 16, 1), (1, 64, 128, 64, 64, 64, 0),
+])
+def test_rowconv_fused_groupnorm_two_sources(B, H, W, Ca, Cb, Cout, silu):
+    """conv3x3(act(GroupNorm(cat[xa|xb]))) with the normalisation done in shared memory inside the conv kernel."""
+    lib, L = _lib()
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(B + H + Ca + Cb)
+    dev = "cuda"
+    C = Ca + Cb
+    xa = (torch.randn(B, Ca, H, W, generator=g) * 1.5 + 0.3).to(dev).bfloat16()
+    xb = (torch.randn(B, Cb, H, W, generator=g) * 0.7 - 0.2).to(dev).bfloat16() if Cb else None
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).contiguous()
+    beta = (0.1 * torch.randn(C, generator=g)).contiguous()
+    w = (torch.randn(Cout, C, 3, 3, generator=g) / (C * 9) ** 0.5).bfloat16().float().contiguous()
+    b = torch.randn(Cout, generator=g).contiguous()
+    x = torch.cat([xa, xb], 1).float() if Cb else xa.float()
+    a = F.group_norm(x, 32, gamma.to(dev), beta.to(dev), eps=1e-6)
+    if silu:
+        a = torch.sigmoid(a) * a
+    ref = F.conv2d(a.bfloat16().float(), w.to(dev), b.to(dev), padding=1)
+    xan = xa.permute(0, 2, 3, 1).contiguous()
+    xbn = xb.permute(0, 2, 3, 1).contiguous() if Cb else None
+    out = torch.full((B, H, W, Cout), float("nan"), device=dev)
+    L.check(lib.pnpf_gn_conv2d_nhwc(xan.data_ptr(), Ca, xbn.data_ptr() if Cb else None, Cb, B, H, W, gamma.data_ptr(), beta.data_ptr(),
+                                    w.data_ptr(), b.data_ptr(), Cout, silu, out.data_ptr(), 1, None))
+    got = out.permute(0, 3, 1, 2)
+    # the engine rounds the normalised activation to bf16 like the reference above; tanh.approx / rounding-boundary
+    # flips give rare 1-ulp(bf16) operand differences -> compare in relative L2 and with a loose max
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel < 3e-3, rel
+    assert (got - ref).abs().max().item() < 5e-2
+
+
 def test_conv_ragged_edges():
     _conv_case(2, 28, 28, 32, 32, 3, 1)
     _conv_case(2, 14, 14, 64, 64, 3, 1)

@@ -1,0 +1,57 @@
+"""Turn gpurun_out/ captures into the tracked summaries under profiles/ (run in the build container; needs `ncu` for .ncu-rep)."""
+import csv, json, os, re, subprocess, sys, collections
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+os.makedirs(P, exist_ok=True)
+
+def short(name):
+    name = re.sub(r"\(.*", "", name)
+    return name.replace("pnpf::", "").replace("void ", "").strip()
+
+# ---- launch list (ncu --metrics gpu__time_duration.sum): share of time per kernel
+lp = os.path.join(G, f"{tag}_launches.csv")
+if os.path.exists(lp):
+    rows = [r for r in csv.reader(l for l in open(lp) if l.startswith('"'))]
+    hdr = rows[0]; ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[1:]:
+        k = short(r[ki]); agg[k][0] += 1; agg[k][1] += float(r[vi].replace(",", "")) / 1e3
+    tot = sum(v[1] for v in agg.values())
+    out = dict(command="ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline",
+               note="cold-cache, serialised per-launch times: compare SHARES, not absolutes", total_us=tot, launches=len(rows) - 1,
+               kernels=[dict(kernel=k, launches=v[0], us=round(v[1], 1), share=round(v[1] / tot, 4)) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])])
+    json.dump(out, open(os.path.join(P, f"{tag}_launch_summary.json"), "w"), indent=1)
+    import gzip, shutil
+    with open(lp, "rb") as fi, gzip.open(os.path.join(P, f"{tag}_launches.csv.gz"), "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    print("launch summary:", [(d["kernel"][:40], d["share"]) for d in out["kernels"][:8]])
+
+# ---- full captures
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+        "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg", "sm__cycles_active.avg"]
+for f in sorted(os.listdir(G)):
+    if not f.endswith(".ncu-rep"): continue
+    raw = subprocess.run(["ncu", "-i", os.path.join(G, f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    if len(rows) < 3: continue
+    hdr, units = rows[0], rows[1]
+    res = []
+    for vals in rows[2:]:
+        d = {"kernel": short(vals[hdr.index("Kernel Name")]) if "Kernel Name" in hdr else "?"}
+        for h, u, v in zip(hdr, units, vals):
+            if h in KEYS or any(h.endswith(k) for k in KEYS):
+                d[h.split(".TriageCompute.")[-1] + (f" [{u}]" if u else "")] = v
+        res.append(d)
+    name = f if f.startswith(tag) else f"{tag}_{f}"
+    json.dump(dict(source=f, command="ncu --set full --clock-control none --import-source on (see tools/, DESIGN.md §5)", launches=res),
+              open(os.path.join(P, name.replace(".ncu-rep", "_ncu.json")), "w"), indent=1)
+    print(f, [(d["kernel"][:30], d.get("gpu__time_duration.sum [us]")) for d in res])
+for src, dst in (("unet_profile_afhq256_b80.json", f"{tag}_unet_ops_afhq256_b80.json"), ("parity_report.json", f"{tag}_parity_report.json"),
+                 ("rate_probe3.json", f"{tag}_umma_rate_probe.json"), ("offset_probe.json", f"{tag}_umma_row_offset_probe.json")):
+    if os.path.exists(os.path.join(G, src)):
+        json.dump(json.load(open(os.path.join(G, src))), open(os.path.join(P, dst), "w"), indent=0)
