@@ -62,7 +62,7 @@ struct RowCfg {
     static constexpr int NACC = (512 / BN) > 16 ? 16 : (512 / BN);
     static constexpr int TMEM_COLS = NACC * BN;              // 256 (BN=16) or 512
     static constexpr int MAX_SLOTS = 8;
-    static constexpr int THREADS = 64 + 256 + 64;            // producer, MMA issuer, 8 epilogue warps, 2 GroupNorm transform warps
+    static constexpr int THREADS = 64 + 256 + 128;           // producer, MMA issuer, 8 epilogue warps, 4 GroupNorm transform warps
     static constexpr int CPT = BN > 32 ? 32 : BN;            // columns per epilogue thread
     static constexpr bool ROW_SPLIT = BN <= 32;              // the two epilogue warp sets alternate rows (else: split columns)
     static constexpr int BAR_BYTES = 2048;                   // barriers + tmem slot | bias staging (2 x 64 floats) | GN scale/shift (2 x 128)
@@ -138,7 +138,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < Cfg::MAX_SLOTS; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
-            mbar_init(&ready_bar[s], 2);
+            mbar_init(&ready_bar[s], 4);
         }
         for (int a = 0; a < 16; ++a) {
             mbar_init(&tfull_bar[a], 1);
@@ -306,9 +306,9 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
     } else if (warp >= 10) {
-        // ===================== GroupNorm(+SiLU) transform: warps 10, 11 normalise each halo tile in place =====================
+        // ===================== GroupNorm(+SiLU) transform: warps 10..13 normalise each halo tile in place =====================
         if (p.gn) {
-            const int tt = threadIdx.x - 320;             // 0..63
+            const int tt = threadIdx.x - 320;             // 0..127
             const int Ctot = p.gn_Ca + p.gn_Cb;
             int slot = 0;
             uint32_t phase = 0;
@@ -316,8 +316,8 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int img, hb, he, w0;
                 decode(it, img, hb, he, w0);
                 // per-image scale / shift of every input channel (a group may straddle the two concatenated sources)
-                asm volatile("bar.sync 3, 64;");
-                for (int c = tt; c < Ctot; c += 64) {
+                asm volatile("bar.sync 3, 128;");
+                for (int c = tt; c < Ctot; c += 128) {
                     const int g0c = (c / p.gn_gs) * p.gn_gs;
                     double S = 0, Q = 0;
                     for (int k = 0; k < p.gn_gs; ++k) {
@@ -336,43 +336,52 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     gn_tab[c] = sc;
                     gn_tab[128 + c] = __ldg(p.gn_beta + c) - static_cast<float>(mean) * sc;
                 }
-                asm volatile("bar.sync 3, 64;");
+                asm volatile("bar.sync 3, 128;");
+                // Thread -> 16-byte chunk mapping: consecutive lanes take consecutive chunks (conflict-free LDS/STS.128); the
+                // 128 threads cover RPI = 2048 / rowbytes pixel rows per iteration, a multiple of 8, so a thread's swizzle
+                // phase — hence the 8 channels its chunk holds — never changes: scale/shift stay in registers per item.
+                constexpr int CPR = Cfg::kRowBytes / 16;           // chunks per pixel row (4 or 8)
+                constexpr int RPI = 128 / CPR;                     // rows per iteration (32 or 16)
+                const int q = tt % CPR, row0 = tt / CPR;
+                const int sw = (Cfg::kRowBytes == 128) ? (row0 & 7) : ((row0 >> 1) & 3);
+                float tsc[KCH][8], tsh[KCH][8];
+#pragma unroll
+                for (int c = 0; c < KCH; ++c)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int ch = c * BK + ((q ^ sw) << 3) + e;
+                        tsc[c][e] = gn_tab[ch];
+                        tsh[c][e] = gn_tab[128 + ch];
+                    }
                 const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
                 for (int j = j0; j <= j1; ++j) {
                     mbar_wait_warp(&full_bar[slot], phase, lane);
                     uint8_t* sp = slots + slot * p.slot_bytes;
 #pragma unroll 1
-                    for (int r = tt; r < Cfg::HALO_ROWS; r += 64) {
+                    for (int r = row0; r < Cfg::HALO_ROWS; r += RPI) {
                         const int wpix = w0 - 1 + r;
                         if (wpix < 0 || wpix >= p.W) continue;          // conv zero padding stays zero
-                        // 128B swizzle: 16B chunk index ^= (row & 7); 64B swizzle: ^= ((row >> 1) & 3)
-                        const int sw = (Cfg::kRowBytes == 128) ? (r & 7) : ((r >> 1) & 3);
 #pragma unroll
                         for (int c = 0; c < KCH; ++c) {
-                            uint4* rowp = reinterpret_cast<uint4*>(sp + c * Cfg::HALO_TILE + r * Cfg::kRowBytes);
+                            uint4* cp = reinterpret_cast<uint4*>(sp + c * Cfg::HALO_TILE + r * Cfg::kRowBytes) + q;
+                            const uint4 u = *cp;
+                            uint32_t wds[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                            for (int q = 0; q < Cfg::kRowBytes / 16; ++q) {
-                                const int ch0 = c * BK + ((q ^ sw) << 3);      // first of the 8 channels held by physical chunk q
-                                uint4 u = rowp[q];
-                                uint32_t wds[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                                for (int e2 = 0; e2 < 4; ++e2) {
-                                    const float2 sc2 = *reinterpret_cast<const float2*>(gn_tab + ch0 + 2 * e2);
-                                    const float2 sh2 = *reinterpret_cast<const float2*>(gn_tab + 128 + ch0 + 2 * e2);
-                                    float y0 = fmaf(__uint_as_float(wds[e2] << 16), sc2.x, sh2.x);
-                                    float y1 = fmaf(__uint_as_float(wds[e2] & 0xFFFF0000u), sc2.y, sh2.y);
-                                    if (p.gn_silu) {
-                                        float t0, t1;                              // silu(y) = 0.5 y (1 + tanh(0.5 y))
-                                        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.5f * y0));
-                                        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.5f * y1));
-                                        y0 = 0.5f * y0 * (1.f + t0);
-                                        y1 = 0.5f * y1 * (1.f + t1);
-                                    }
-                                    __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
-                                    wds[e2] = *reinterpret_cast<uint32_t*>(&b2);
+                            for (int e2 = 0; e2 < 4; ++e2) {
+                                float y0 = fmaf(__uint_as_float(wds[e2] << 16), tsc[c][2 * e2], tsh[c][2 * e2]);
+                                float y1 = fmaf(__uint_as_float(wds[e2] & 0xFFFF0000u), tsc[c][2 * e2 + 1], tsh[c][2 * e2 + 1]);
+                                if (p.gn_silu) {                       // silu(y) = h + h * tanh(h), h = y / 2
+                                    const float h0 = 0.5f * y0, h1 = 0.5f * y1;
+                                    float t0, t1;
+                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+                                    y0 = fmaf(h0, t0, h0);
+                                    y1 = fmaf(h1, t1, h1);
                                 }
-                                rowp[q] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
+                                wds[e2] = *reinterpret_cast<uint32_t*>(&b2);
                             }
+                            *cp = make_uint4(wds[0], wds[1], wds[2], wds[3]);
                         }
                     }
                     fence_proxy_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
