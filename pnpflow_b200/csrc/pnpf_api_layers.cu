@@ -134,8 +134,22 @@ extern "C" int pnpf_gn_conv2d_nhwc(const void* xa, int Ca, const void* xb, int C
     d.gn_gamma = dg; d.gn_beta = dbeta; d.gn_stats_a = sta; d.gn_stats_b = Cb ? stb : nullptr; d.gn_silu = silu;
     TcOp op;
     if (!rc) rc = prepare_conv(op, d);
+    long long* dbg = nullptr;
+    if (!rc && op.kind == 1 && getenv("PNPF_ROWCONV_DBG")) {
+        cudaMalloc(&dbg, 16 * sizeof(long long));
+        cudaMemset(dbg, 0, 16 * sizeof(long long));
+        op.rp.dbg = dbg;
+    }
     if (!rc) rc = launch_tc(op, s);
     cudaError_t e = cudaStreamSynchronize(s);
+    if (dbg) {
+        long long h[16];
+        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("ROWCONV_GN_DBG producer: total %lld wait_empty %lld rows %lld | transform: total %lld wait_full %lld table %lld | mma: total %lld "
+               "wait_ready %lld wait_tempty %lld | epi0: total %lld wait_tfull %lld\n", h[0], h[1], h[2], h[3], h[7], h[11], h[4], h[5], h[6], h[8], h[9]);
+        fflush(stdout);
+        cudaFree(dbg);
+    }
     cudaFree(dw); cudaFree(db); cudaFree(dg); cudaFree(dbeta); cudaFree(sta); cudaFree(stb);
     if (rc) return rc;
     PNPF_CHECK_CUDA(e);

@@ -21,6 +21,7 @@
 //     warp shuffles + one fp64 atomic per lane per item.
 #pragma once
 #include "pnpf_gemm.cuh"
+#include <cuda_fp16.h>
 
 namespace pnpf {
 
@@ -62,9 +63,12 @@ struct RowCfg {
     static constexpr int NACC = (512 / BN) > 16 ? 16 : (512 / BN);
     static constexpr int TMEM_COLS = NACC * BN;              // 256 (BN=16) or 512
     static constexpr int MAX_SLOTS = 8;
-    static constexpr int THREADS = 64 + 256 + 128;           // producer, MMA issuer, 8 epilogue warps, 4 GroupNorm transform warps
+    // 12 worker warps besides the producer and the MMA issuer: thin outputs (C_out <= 32) need little epilogue work, so
+    // they get 4 epilogue + 8 GroupNorm-transform warps; C_out = 64 uses 8 epilogue warps (two sets split the columns) + 4.
+    static constexpr int NEW = BN > 32 ? 8 : 4;              // epilogue warps
+    static constexpr int NTW = 12 - NEW;                     // transform warps
+    static constexpr int THREADS = 64 + 12 * 32;
     static constexpr int CPT = BN > 32 ? 32 : BN;            // columns per epilogue thread
-    static constexpr bool ROW_SPLIT = BN <= 32;              // the two epilogue warp sets alternate rows (else: split columns)
     static constexpr int BAR_BYTES = 2048;                   // barriers + tmem slot | bias staging (2 x 64 floats) | GN scale/shift (2 x 128)
     static_assert(BN == 16 || BN == 32 || BN == 64, "row conv is for thin outputs");
 };
@@ -94,6 +98,14 @@ __device__ __forceinline__ void tmem_zero_x16(uint32_t taddr) {
                  : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 // one lane polls, the warp follows
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
     if (lane == 0) mbar_wait(bar, parity);
@@ -138,11 +150,11 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < Cfg::MAX_SLOTS; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
-            mbar_init(&ready_bar[s], 4);
+            mbar_init(&ready_bar[s], Cfg::NTW);
         }
         for (int a = 0; a < 16; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], Cfg::ROW_SPLIT ? 4 : 8);
+            mbar_init(&tempty_bar[a], Cfg::NEW);
         }
         fence_barrier_init();
     }
@@ -305,19 +317,23 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[4] = clock64() - c_start; p.dbg[5] = c_full; p.dbg[6] = c_tempty; }
         }
         __syncwarp();
-    } else if (warp >= 10) {
+    } else if (warp >= 2 + Cfg::NEW) {
         // ===================== GroupNorm(+SiLU) transform: warps 10..13 normalise each halo tile in place =====================
         if (p.gn) {
-            const int tt = threadIdx.x - 320;             // 0..127
+            constexpr int NTT = Cfg::NTW * 32;            // transform threads
+            const int tt = threadIdx.x - (64 + Cfg::NEW * 32);
             const int Ctot = p.gn_Ca + p.gn_Cb;
             int slot = 0;
             uint32_t phase = 0;
+            long long c_twait = 0, c_tab = 0;
+            const long long c_tstart = clock64();
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 int img, hb, he, w0;
                 decode(it, img, hb, he, w0);
+                const long long c_t0 = clock64();
                 // per-image scale / shift of every input channel (a group may straddle the two concatenated sources)
-                asm volatile("bar.sync 3, 128;");
-                for (int c = tt; c < Ctot; c += 128) {
+                asm volatile("bar.sync 3, %0;" ::"n"(NTT));
+                for (int c = tt; c < Ctot; c += NTT) {
                     const int g0c = (c / p.gn_gs) * p.gn_gs;
                     double S = 0, Q = 0;
                     for (int k = 0; k < p.gn_gs; ++k) {
@@ -336,12 +352,12 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     gn_tab[c] = sc;
                     gn_tab[128 + c] = __ldg(p.gn_beta + c) - static_cast<float>(mean) * sc;
                 }
-                asm volatile("bar.sync 3, 128;");
+                asm volatile("bar.sync 3, %0;" ::"n"(NTT));
                 // Thread -> 16-byte chunk mapping: consecutive lanes take consecutive chunks (conflict-free LDS/STS.128); the
                 // 128 threads cover RPI = 2048 / rowbytes pixel rows per iteration, a multiple of 8, so a thread's swizzle
                 // phase — hence the 8 channels its chunk holds — never changes: scale/shift stay in registers per item.
                 constexpr int CPR = Cfg::kRowBytes / 16;           // chunks per pixel row (4 or 8)
-                constexpr int RPI = 128 / CPR;                     // rows per iteration (32 or 16)
+                constexpr int RPI = NTT / CPR;                     // rows per iteration (16..64, always a multiple of 8)
                 const int q = tt % CPR, row0 = tt / CPR;
                 const int sw = (Cfg::kRowBytes == 128) ? (row0 & 7) : ((row0 >> 1) & 3);
                 float tsc[KCH][8], tsh[KCH][8];
@@ -354,34 +370,51 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tsh[c][e] = gn_tab[128 + ch];
                     }
                 const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
+                c_tab += clock64() - c_t0;
                 for (int j = j0; j <= j1; ++j) {
-                    mbar_wait_warp(&full_bar[slot], phase, lane);
-                    uint8_t* sp = slots + slot * p.slot_bytes;
-#pragma unroll 1
-                    for (int r = row0; r < Cfg::HALO_ROWS; r += RPI) {
-                        const int wpix = w0 - 1 + r;
-                        if (wpix < 0 || wpix >= p.W) continue;          // conv zero padding stays zero
+                    {
+                        const long long _t0 = clock64();
+                        mbar_wait_warp(&full_bar[slot], phase, lane);
+                        c_twait += clock64() - _t0;
+                    }
+                    // all of a thread's rows of one tile are loaded first (explicit ld.shared: independent 16-byte loads in
+                    // flight), then transformed, then stored — the per-warp latency chain is paid once per tile, not per row
+                    constexpr int NIT = (Cfg::HALO_ROWS + RPI - 1) / RPI;            // 5 (64-byte rows) or 9 (128-byte rows)
+                    const uint32_t sbase = smem_u32(slots) + slot * p.slot_bytes + row0 * Cfg::kRowBytes + q * 16;
 #pragma unroll
-                        for (int c = 0; c < KCH; ++c) {
-                            uint4* cp = reinterpret_cast<uint4*>(sp + c * Cfg::HALO_TILE + r * Cfg::kRowBytes) + q;
-                            const uint4 u = *cp;
-                            uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+                    for (int c = 0; c < KCH; ++c) {
+                        uint4 u[NIT];
+                        bool ok[NIT];
+#pragma unroll
+                        for (int k = 0; k < NIT; ++k) {
+                            const int r = row0 + k * RPI;
+                            const int wpix = w0 - 1 + r;
+                            ok[k] = (r < Cfg::HALO_ROWS) && (wpix >= 0) && (wpix < p.W);   // conv zero padding stays zero
+                            if (ok[k]) u[k] = lds128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes);
+                        }
+#pragma unroll
+                        for (int k = 0; k < NIT; ++k) {
+                            if (!ok[k]) continue;
+                            uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
 #pragma unroll
                             for (int e2 = 0; e2 < 4; ++e2) {
                                 float y0 = fmaf(__uint_as_float(wds[e2] << 16), tsc[c][2 * e2], tsh[c][2 * e2]);
                                 float y1 = fmaf(__uint_as_float(wds[e2] & 0xFFFF0000u), tsc[c][2 * e2 + 1], tsh[c][2 * e2 + 1]);
                                 if (p.gn_silu) {                       // silu(y) = h + h * tanh(h), h = y / 2
-                                    const float h0 = 0.5f * y0, h1 = 0.5f * y1;
-                                    float t0, t1;
-                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
-                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
-                                    y0 = fmaf(h0, t0, h0);
-                                    y1 = fmaf(h1, t1, h1);
+                                    // packed fp16 tanh: ONE MUFU op per two elements (the SFU is this stage's bottleneck); fp16 keeps
+                                    // 3 more mantissa bits than the bf16 result, so the rounding of the output dominates the error
+                                    const __half2 hh = __floats2half2_rn(0.5f * y0, 0.5f * y1);
+                                    uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh), tb;
+                                    asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(hb));
+                                    const __half2 th = *reinterpret_cast<const __half2*>(&tb);
+                                    const float2 o = __half22float2(__hfma2(hh, th, hh));
+                                    y0 = o.x;
+                                    y1 = o.y;
                                 }
                                 __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
                                 wds[e2] = *reinterpret_cast<uint32_t*>(&b2);
                             }
-                            *cp = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                            sts128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes, make_uint4(wds[0], wds[1], wds[2], wds[3]));
                         }
                     }
                     fence_proxy_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -390,14 +423,15 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (++slot == p.nslot) { slot = 0; phase ^= 1; }
                 }
             }
+            if (p.dbg && blockIdx.x == 0 && tt == 0) { p.dbg[3] = clock64() - c_tstart; p.dbg[7] = c_twait; p.dbg[11] = c_tab; }
         }
     } else {
-        // ===================== epilogue: warps 2..5 = set 0, warps 6..9 = set 1 =====================
+        // ===================== epilogue: warps 2..5 = set 0 (and warps 6..9 = set 1 for C_out = 64) =====================
         const int set = (warp - 2) >> 2;
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int m = quarter * 32 + lane;            // pixel within the strip
         const int ethread = threadIdx.x - 64;         // 0..255
-        const int colbase = Cfg::ROW_SPLIT ? 0 : set * 32;
+        const int colbase = set * 32;                 // set 1 exists only for C_out = 64 (column split)
         float* bsm = bias_sm + set * 64;
         const uint32_t set_bar = 1 + set;             // named barrier id of this warp set (128 threads)
         uint32_t g0 = 0;
@@ -423,7 +457,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float ssum[CPT], ssq[CPT];
 #pragma unroll
             for (int q = 0; q < CPT; ++q) ssum[q] = ssq[q] = 0.f;
-            for (int r = hb + (Cfg::ROW_SPLIT ? set : 0); r < he; r += (Cfg::ROW_SPLIT ? 2 : 1)) {
+            for (int r = hb; r < he; ++r) {
                 const uint32_t g = g0 + static_cast<uint32_t>(r - hb);
                 const uint32_t acc = g % NACC;
                 {
@@ -513,7 +547,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             g0 += static_cast<uint32_t>(he - hb);
         }
         if (p.dbg && blockIdx.x == 0 && ethread == 0) { p.dbg[8] = clock64() - c_start; p.dbg[9] = c_tfull; p.dbg[10] = c_rows; }
-        if (p.dbg && blockIdx.x == 0 && ethread == 128) { p.dbg[12] = clock64() - c_start; p.dbg[13] = c_tfull; p.dbg[14] = c_rows; }
+        if (p.dbg && blockIdx.x == 0 && ethread == 128 && Cfg::NEW == 8) { p.dbg[12] = clock64() - c_start; p.dbg[13] = c_tfull; p.dbg[14] = c_rows; }
     }
     tc_fence_before();
     __syncthreads();
