@@ -281,6 +281,17 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---------------- the U-Net evaluation alone (CUDA-graph replay), to split the step time ----------------
+    _, _, _, replay = eng.graphed(S * B)
+    replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        replay()
+    e1.record()
+    torch.cuda.synchronize()
+    unet_replay_ms = e0.elapsed_time(e1) / 5
+
     # ---------------- roofline of the dominant kernel class (tcgen05 implicit-GEMM), per-op CUDA events ----------------
     prof = eng.profile(S * B)
     tc = [o for o in prof if o["kind"] == "tc"]
@@ -296,7 +307,7 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch_mean")
         except Exception:
             traffic = None
-    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<BK,BN> (all tensor-core launches of one U-Net evaluation)",
+    roofline = {"bound": "tensor", "kernel": "rowconv_kernel<BK,BN,KCH> + conv_gemm_kernel<BK,BN> (all tensor-core launches of one U-Net evaluation)",
                 "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"] if pk["tflops"] else None,
                 "traffic": traffic, "peak_source": pk["src"], "launches": len(tc),
                 "flops_per_eval_batch": tc_fl, "tc_ms_per_eval": tc_ms, "tc_share_of_eval": tc_ms / (tc_ms + simt_ms) if tc_ms + simt_ms > 0 else None,
@@ -316,7 +327,7 @@ def main():
                     "ms_per_step": ms_e / K},
             "gpu_launches": K * sess.launches_per_step, "roofline": roofline, "cpu_baseline": cpu,
             "finite": finite, "unet_flops_per_image": eng.flops_per_image, "unet_launches_per_eval": eng.num_launches,
-            "scatter_ms": scatter_ms, "gather_ms": gather_ms, "workspace_gb": eng.workspace_bytes / 2 ** 30}
+            "unet_graph_replay_ms": unet_replay_ms, "scatter_ms": scatter_ms, "gather_ms": gather_ms, "workspace_gb": eng.workspace_bytes / 2 ** 30}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
