@@ -212,7 +212,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int ab = p.a_batched ? img : 0;
                 const int bb = p.b_batched ? img : 0;
                 for (int i = 0; i < nk; ++i) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (lane == 0) mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+                    __syncwarp();
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     if (elect_one_sync()) {
@@ -280,7 +281,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int h = h0 + th, w = w0 + tw;
             const bool valid = (h < p.H) && (w < p.W);
             const long long pix = static_cast<long long>(h) * p.W + w;
-            if (lane == 0) mbar_wait(&tfull_bar[acc], acc_phase);   // one lane polls, the warp follows
+            if (lane == 0) mbar_wait_relaxed(&tfull_bar[acc], acc_phase);   // one lane polls (with back-off), the warp follows
             __syncwarp();
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;

@@ -108,7 +108,7 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
 }
 // one lane polls, the warp follows
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
-    if (lane == 0) mbar_wait(bar, parity);
+    if (lane == 0) mbar_wait_relaxed(bar, parity);
     __syncwarp();
 }
 
@@ -208,7 +208,11 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 decode(it, img, hb, he, w0);
                 const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
                 for (int j = j0; j <= j1; ++j) {
-                    PNPF_TIMED_WAIT(&empty_bar[slot], phase ^ 1, c_wait);
+                    {
+                        const long long _t0 = clock64();
+                        mbar_wait_warp(&empty_bar[slot], phase ^ 1, lane);
+                        c_wait += clock64() - _t0;
+                    }
                     ++c_rows;
                     uint8_t* sp = slots + slot * p.slot_bytes;
                     const bool centre = (j >= hb) && (j < he) && p.kchunks2;
