@@ -316,7 +316,7 @@ def main():
                 "whole_step_conv_gemm_frac": (value * T * S * eng.flops_per_image / world) / (pk["tflops"] * 1e12) if pk["tflops"] else None}
 
     cpu = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:          # reported baseline: rank 0 at N=1 only
         r = cpu_reference(a.config, a.cpu_steps, 1)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 

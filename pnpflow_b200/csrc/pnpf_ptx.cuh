@@ -57,7 +57,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // burns issue slots of the SM sub-partition it shares with working warps (ncu: ~50 % issue-active from polling alone).
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+    while (!mbar_try_wait(bar, parity)) {
+    }   // (a __nanosleep back-off here was measured SLOWER: wake-up latency outweighs the freed issue slots)
 }
 
 // ------------------------------------------------------------------ TMA
