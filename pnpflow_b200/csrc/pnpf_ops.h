@@ -58,6 +58,7 @@ struct ConvDesc {
     const double* gn_stats_a = nullptr;
     const double* gn_stats_b = nullptr;
     int gn_groups = 32, gn_silu = 1;
+    int gn_packed = 1;              // packed bf16x2 transform arithmetic (PNPF_GN_PRECISE=1 in the environment forces fp32)
     float gn_eps = 1e-6f;
 };
 int prepare_conv(TcOp& op, const ConvDesc& d);

@@ -22,6 +22,7 @@
 #pragma once
 #include "pnpf_gemm.cuh"
 #include <cuda_fp16.h>
+#include <cuda/std/type_traits>
 
 namespace pnpf {
 
@@ -40,6 +41,7 @@ struct RowConvParams {
     // warps between the TMA and the MMAs (per-channel statistics come from the producing conv's epilogue).
     int gn;                // 0 = input is used as is
     int gn_silu, gn_gs, gn_Ca, gn_Cb;    // activation flag, channels per group, channels of source a / b
+    int gn_packed;         // 1: packed bf16x2 arithmetic (3 instructions per 2 elements), 0: fp32 FMA + fp16x2 tanh
     float gn_eps;
     const float* gn_gamma; // [Ca+Cb]
     const float* gn_beta;
@@ -358,74 +360,102 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 asm volatile("bar.sync 3, %0;" ::"n"(NTT));
                 // Thread -> 16-byte chunk mapping: consecutive lanes take consecutive chunks (conflict-free LDS/STS.128); the
-                // 128 threads cover RPI = 2048 / rowbytes pixel rows per iteration, a multiple of 8, so a thread's swizzle
+                // NTT threads cover RPI = NTT / CPR pixel rows per iteration, a multiple of 8, so a thread's swizzle
                 // phase — hence the 8 channels its chunk holds — never changes: scale/shift stay in registers per item.
                 constexpr int CPR = Cfg::kRowBytes / 16;           // chunks per pixel row (4 or 8)
                 constexpr int RPI = NTT / CPR;                     // rows per iteration (16..64, always a multiple of 8)
+                constexpr int NIT = (Cfg::HALO_ROWS + RPI - 1) / RPI;
                 const int q = tt % CPR, row0 = tt / CPR;
                 const int sw = (Cfg::kRowBytes == 128) ? (row0 & 7) : ((row0 >> 1) & 3);
-                float tsc[KCH][8], tsh[KCH][8];
-#pragma unroll
-                for (int c = 0; c < KCH; ++c)
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int ch = c * BK + ((q ^ sw) << 3) + e;
-                        tsc[c][e] = gn_tab[ch];
-                        tsh[c][e] = gn_tab[128 + ch];
-                    }
                 const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
-                c_tab += clock64() - c_t0;
-                for (int j = j0; j <= j1; ++j) {
-                    {
-                        const long long _t0 = clock64();
-                        mbar_wait_warp(&full_bar[slot], phase, lane);
-                        c_twait += clock64() - _t0;
-                    }
-                    // all of a thread's rows of one tile are loaded first (explicit ld.shared: independent 16-byte loads in
-                    // flight), then transformed, then stored — the per-warp latency chain is paid once per tile, not per row
-                    constexpr int NIT = (Cfg::HALO_ROWS + RPI - 1) / RPI;            // 5 (64-byte rows) or 9 (128-byte rows)
-                    const uint32_t sbase = smem_u32(slots) + slot * p.slot_bytes + row0 * Cfg::kRowBytes + q * 16;
+                // Two arithmetic variants, each with its own register-resident table (generic lambda = separate scopes):
+                //   packed : bf16x2 FMA -> tanh.approx.bf16x2 -> bf16x2 FMA   (3 instructions per 2 elements)
+                //   precise: fp32 FMA, packed fp16 tanh, fp32 result rounded once to bf16
+                auto run_rows = [&](auto packed_tag) {
+                    constexpr bool PACKED = decltype(packed_tag)::value;
+                    float tsc[PACKED ? 1 : KCH][8], tsh[PACKED ? 1 : KCH][8];
+                    uint32_t psc[PACKED ? KCH : 1][4], psh[PACKED ? KCH : 1][4];
+                    const float pre = p.gn_silu ? 0.5f : 1.0f;     // SiLU works on h = y/2: silu(y) = h + h*tanh(h)
 #pragma unroll
-                    for (int c = 0; c < KCH; ++c) {
-                        uint4 u[NIT];
-                        bool ok[NIT];
+                    for (int c = 0; c < KCH; ++c)
 #pragma unroll
-                        for (int k = 0; k < NIT; ++k) {
-                            const int r = row0 + k * RPI;
-                            const int wpix = w0 - 1 + r;
-                            ok[k] = (r < Cfg::HALO_ROWS) && (wpix >= 0) && (wpix < p.W);   // conv zero padding stays zero
-                            if (ok[k]) u[k] = lds128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes);
-                        }
-#pragma unroll
-                        for (int k = 0; k < NIT; ++k) {
-                            if (!ok[k]) continue;
-                            uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-#pragma unroll
-                            for (int e2 = 0; e2 < 4; ++e2) {
-                                float y0 = fmaf(__uint_as_float(wds[e2] << 16), tsc[c][2 * e2], tsh[c][2 * e2]);
-                                float y1 = fmaf(__uint_as_float(wds[e2] & 0xFFFF0000u), tsc[c][2 * e2 + 1], tsh[c][2 * e2 + 1]);
-                                if (p.gn_silu) {                       // silu(y) = h + h * tanh(h), h = y / 2
-                                    // packed fp16 tanh: ONE MUFU op per two elements (the SFU is this stage's bottleneck); fp16 keeps
-                                    // 3 more mantissa bits than the bf16 result, so the rounding of the output dominates the error
-                                    const __half2 hh = __floats2half2_rn(0.5f * y0, 0.5f * y1);
-                                    uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh), tb;
-                                    asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(hb));
-                                    const __half2 th = *reinterpret_cast<const __half2*>(&tb);
-                                    const float2 o = __half22float2(__hfma2(hh, th, hh));
-                                    y0 = o.x;
-                                    y1 = o.y;
-                                }
-                                __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
-                                wds[e2] = *reinterpret_cast<uint32_t*>(&b2);
+                        for (int e2 = 0; e2 < 4; ++e2) {
+                            const int ch = c * BK + ((q ^ sw) << 3) + 2 * e2;
+                            const float s0 = gn_tab[ch], s1 = gn_tab[ch + 1], b0 = gn_tab[128 + ch], b1 = gn_tab[128 + ch + 1];
+                            if constexpr (PACKED) {
+                                __nv_bfloat162 a2 = __floats2bfloat162_rn(pre * s0, pre * s1);
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(pre * b0, pre * b1);
+                                psc[c][e2] = *reinterpret_cast<uint32_t*>(&a2);
+                                psh[c][e2] = *reinterpret_cast<uint32_t*>(&b2);
+                            } else {
+                                tsc[c][2 * e2] = s0; tsc[c][2 * e2 + 1] = s1;
+                                tsh[c][2 * e2] = b0; tsh[c][2 * e2 + 1] = b1;
                             }
-                            sts128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes, make_uint4(wds[0], wds[1], wds[2], wds[3]));
                         }
+                    c_tab += clock64() - c_t0;
+                    for (int j = j0; j <= j1; ++j) {
+                        {
+                            const long long _t0 = clock64();
+                            mbar_wait_warp(&full_bar[slot], phase, lane);
+                            c_twait += clock64() - _t0;
+                        }
+                        // all of a thread's rows of one tile are loaded first (explicit ld.shared: independent 16-byte loads in
+                        // flight), then transformed, then stored — the per-warp latency chain is paid once per tile, not per row
+                        const uint32_t sbase = smem_u32(slots) + slot * p.slot_bytes + row0 * Cfg::kRowBytes + q * 16;
+#pragma unroll
+                        for (int c = 0; c < KCH; ++c) {
+                            uint4 u[NIT];
+                            bool ok[NIT];
+#pragma unroll
+                            for (int k = 0; k < NIT; ++k) {
+                                const int r = row0 + k * RPI;
+                                const int wpix = w0 - 1 + r;
+                                ok[k] = (r < Cfg::HALO_ROWS) && (wpix >= 0) && (wpix < p.W);   // conv zero padding stays zero
+                                if (ok[k]) u[k] = lds128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes);
+                            }
+#pragma unroll
+                            for (int k = 0; k < NIT; ++k) {
+                                if (!ok[k]) continue;
+                                uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+                                for (int e2 = 0; e2 < 4; ++e2) {
+                                    if constexpr (PACKED) {
+                                        uint32_t h2, t2;
+                                        asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(h2) : "r"(wds[e2]), "r"(psc[c][e2]), "r"(psh[c][e2]));
+                                        if (p.gn_silu) {
+                                            asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t2) : "r"(h2));
+                                            asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(wds[e2]) : "r"(h2), "r"(t2));
+                                        } else {
+                                            wds[e2] = h2;
+                                        }
+                                    } else {
+                                        float y0 = fmaf(__uint_as_float(wds[e2] << 16), tsc[c][2 * e2], tsh[c][2 * e2]);
+                                        float y1 = fmaf(__uint_as_float(wds[e2] & 0xFFFF0000u), tsc[c][2 * e2 + 1], tsh[c][2 * e2 + 1]);
+                                        if (p.gn_silu) {
+                                            // packed fp16 tanh: one SFU op per two elements; fp16 keeps 3 more mantissa bits than the bf16 result
+                                            const __half2 hh = __floats2half2_rn(0.5f * y0, 0.5f * y1);
+                                            uint32_t hb2 = *reinterpret_cast<const uint32_t*>(&hh), tb;
+                                            asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(hb2));
+                                            const __half2 th = *reinterpret_cast<const __half2*>(&tb);
+                                            const float2 o = __half22float2(__hfma2(hh, th, hh));
+                                            y0 = o.x;
+                                            y1 = o.y;
+                                        }
+                                        __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
+                                        wds[e2] = *reinterpret_cast<uint32_t*>(&b2);
+                                    }
+                                }
+                                sts128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes, make_uint4(wds[0], wds[1], wds[2], wds[3]));
+                            }
+                        }
+                        fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&ready_bar[slot]);
+                        if (++slot == p.nslot) { slot = 0; phase ^= 1; }
                     }
-                    fence_proxy_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&ready_bar[slot]);
-                    if (++slot == p.nslot) { slot = 0; phase ^= 1; }
-                }
+                };
+                if (p.gn_packed) run_rows(cuda::std::true_type{});
+                else run_rows(cuda::std::false_type{});
             }
             if (p.dbg && blockIdx.x == 0 && tt == 0) { p.dbg[3] = clock64() - c_tstart; p.dbg[7] = c_twait; p.dbg[11] = c_tab; }
         }
