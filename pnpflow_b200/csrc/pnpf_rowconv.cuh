@@ -494,6 +494,16 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int r = hb; r < he; ++r) {
                 const uint32_t g = g0 + static_cast<uint32_t>(r - hb);
                 const uint32_t acc = g % NACC;
+                const long long pix = static_cast<long long>(r) * p.W + w0 + m;
+                // the residual does not depend on the accumulator: issue its (latency-bound, strided) global loads BEFORE
+                // waiting for the MMAs so that the wait hides them
+                uint4 resv[CPT / 8];
+                if (p.epi.residual) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.epi.residual + img * p.epi.res_img_stride + pix * p.epi.res_row_stride + colbase);
+#pragma unroll
+                    for (int q = 0; q < CPT / 8; ++q)
+                        if (colbase + q * 8 < p.epi.n_valid) resv[q] = __ldg(rp + q);
+                }
                 {
                     const long long _t0 = clock64();
                     mbar_wait_warp(&tfull_bar[acc], (g / NACC) & 1, lane);
@@ -501,7 +511,6 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 ++c_rows;
                 tc_fence_after();
-                const long long pix = static_cast<long long>(r) * p.W + w0 + m;
                 const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ((NACC - 1) - acc) * BN + colbase;
                 uint32_t rr[CPT / 16][16];
 #pragma unroll
@@ -527,10 +536,9 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         v[jj + 3] = __uint_as_float(rr[q][jj + 3]) + b4.w;
                     }
                     if (p.epi.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.epi.residual + img * p.epi.res_img_stride + pix * p.epi.res_row_stride + col0);
 #pragma unroll
                         for (int h2 = 0; h2 < 2; ++h2) {
-                            const uint4 u = __ldg(rp + h2);
+                            const uint4 u = resv[q * 2 + h2];
                             const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj) {
