@@ -65,10 +65,12 @@ struct RowCfg {
     static constexpr int NACC = (512 / BN) > 16 ? 16 : (512 / BN);
     static constexpr int TMEM_COLS = NACC * BN;              // 256 (BN=16) or 512
     static constexpr int MAX_SLOTS = 8;
-    // 12 worker warps besides the producer and the MMA issuer: thin outputs (C_out <= 32) need little epilogue work, so
-    // they get 4 epilogue + 8 GroupNorm-transform warps; C_out = 64 uses 8 epilogue warps (two sets split the columns) + 4.
-    static constexpr int NEW = BN > 32 ? 8 : 4;              // epilogue warps
+    // 12 worker warps besides the producer and the MMA issuer: 8 epilogue + 4 GroupNorm-transform warps.
+    // (measured: the epilogue is a per-warp LATENCY chain — wait, tcgen05.ld, tcgen05.st, arrive — so two warp sets
+    //  working on alternate rows beat one set even for thin outputs; 8 transform warps did not beat 4)
+    static constexpr int NEW = 8;                            // epilogue warps: two sets of 4
     static constexpr int NTW = 12 - NEW;                     // transform warps
+    static constexpr bool ROW_SPLIT = BN <= 32;              // the two sets alternate rows (C_out <= 32) or split the columns (64)
     static constexpr int THREADS = 64 + 12 * 32;
     static constexpr int CPT = BN > 32 ? 32 : BN;            // columns per epilogue thread
     static constexpr int BAR_BYTES = 2048;                   // barriers + tmem slot | bias staging (2 x 64 floats) | GN scale/shift (2 x 128)
@@ -156,7 +158,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 16; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], Cfg::NEW);
+            mbar_init(&tempty_bar[a], Cfg::ROW_SPLIT ? 4 : 8);
         }
         fence_barrier_init();
     }
@@ -465,7 +467,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int m = quarter * 32 + lane;            // pixel within the strip
         const int ethread = threadIdx.x - 64;         // 0..255
-        const int colbase = set * 32;                 // set 1 exists only for C_out = 64 (column split)
+        const int colbase = Cfg::ROW_SPLIT ? 0 : set * 32;
         float* bsm = bias_sm + set * 64;
         const uint32_t set_bar = 1 + set;             // named barrier id of this warp set (128 threads)
         uint32_t g0 = 0;
@@ -491,7 +493,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float ssum[CPT], ssq[CPT];
 #pragma unroll
             for (int q = 0; q < CPT; ++q) ssum[q] = ssq[q] = 0.f;
-            for (int r = hb; r < he; ++r) {
+            for (int r = hb + (Cfg::ROW_SPLIT ? set : 0); r < he; r += (Cfg::ROW_SPLIT ? 2 : 1)) {
                 const uint32_t g = g0 + static_cast<uint32_t>(r - hb);
                 const uint32_t acc = g % NACC;
                 const long long pix = static_cast<long long>(r) * p.W + w0 + m;
