@@ -115,6 +115,10 @@ int pnpf_apply_H_adj(const pnpf_operator* op, const float* y, float* x, int B, i
 /* z = x - gamma * A^T(A x - y)   pnp_flow.py:39-41 + :111-112 with gamma = lr_t (sigma^2 cancels, :60-62) */
 int pnpf_datafit_step(const pnpf_operator* op, const float* x, const float* y, float* z, float gamma, int B, int C, int H,
                       int W, void* stream);
+/* Laplace noise model: z = x - gamma * A^T(2*heaviside(Ax - y, 0) - 1)   pnp_flow.py:42-43 + :111-112, gamma = lr_t / sigma
+ * (lr = sigma * lr_pnp, :64-66, so sigma cancels like sigma^2 does in the gaussian case). */
+int pnpf_datafit_step_laplace(const pnpf_operator* op, const float* x, const float* y, float* z, float gamma, int B, int C, int H,
+                              int W, void* stream);
 /* zt[s] = t*z + (1-t)*eps[s], s < S      pnp_flow.py:47-48 (interpolation_step) for the S Monte-Carlo draws of one
  * step (:115-117); n = B*C*H*W, eps and zt are [S][n] (draw-major), z is [n]. */
 int pnpf_interp(const float* z, const float* eps, float t, float* zt, long long n, int S, void* stream);

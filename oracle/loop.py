@@ -35,11 +35,18 @@ def grad_datafit(x, y, H, H_adj, sigma_noise: float, noise_type: str = 'gaussian
     raise ValueError('Noise type not supported')
 
 
-def synthesize_measurement(clean: torch.Tensor, H, sigma_noise: float, batch_idx: int) -> torch.Tensor:
-    """pnp_flow.py:77-80 (gaussian): y = H(clean); torch.manual_seed(batch); y += sigma * randn_like(y)."""
+def synthesize_measurement(clean: torch.Tensor, H, sigma_noise: float, batch_idx: int,
+                           noise_type: str = 'gaussian') -> torch.Tensor:
+    """pnp_flow.py:77-80 (gaussian): y = H(clean); torch.manual_seed(batch); y += sigma * randn_like(y).
+    pnp_flow.py:81-85 (laplace): y = H(clean) + Laplace(0, sigma).sample() from the global generator (not re-seeded)."""
     y = H(clean.clone())
-    torch.manual_seed(batch_idx)
-    y = y + torch.randn_like(y) * sigma_noise
+    if noise_type == 'gaussian':
+        torch.manual_seed(batch_idx)
+        y = y + torch.randn_like(y) * sigma_noise
+    elif noise_type == 'laplace':
+        y = y + torch.distributions.laplace.Laplace(torch.zeros_like(y), sigma_noise * torch.ones_like(y)).sample()
+    else:
+        raise ValueError('Noise type not supported')
     return y
 
 

@@ -53,6 +53,7 @@ SYMBOLS = {
     "pnpf_apply_H": (_I, [C.POINTER(OperatorC), _VP, _VP, _I, _I, _I, _I, _VP]),
     "pnpf_apply_H_adj": (_I, [C.POINTER(OperatorC), _VP, _VP, _I, _I, _I, _I, _VP]),
     "pnpf_datafit_step": (_I, [C.POINTER(OperatorC), _VP, _VP, _VP, _F, _I, _I, _I, _I, _VP]),
+    "pnpf_datafit_step_laplace": (_I, [C.POINTER(OperatorC), _VP, _VP, _VP, _F, _I, _I, _I, _I, _VP]),
     "pnpf_interp": (_I, [_VP, _VP, _F, _VP, _LL, _I, _VP]),
     "pnpf_push_accum": (_I, [_VP, _VP, _F, _I, _VP, _LL, _VP]),
     "pnpf_conv2d_nhwc": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _I, _VP]),

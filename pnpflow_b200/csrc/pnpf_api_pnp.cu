@@ -34,7 +34,14 @@ extern "C" int pnpf_datafit_step(const pnpf_operator* op, const float* x, const 
     OpDesc d;
     if (int rc = to_desc(op, d)) return rc;
     PNPF_REQUIRE(x && y && z, "null pointer");
-    return launch_datafit(d, x, y, z, gamma, B, C, H, W, static_cast<cudaStream_t>(stream));
+    return launch_datafit(d, x, y, z, gamma, 0, B, C, H, W, static_cast<cudaStream_t>(stream));
+}
+extern "C" int pnpf_datafit_step_laplace(const pnpf_operator* op, const float* x, const float* y, float* z, float gamma, int B,
+                                         int C, int H, int W, void* stream) {
+    OpDesc d;
+    if (int rc = to_desc(op, d)) return rc;
+    PNPF_REQUIRE(x && y && z, "null pointer");
+    return launch_datafit(d, x, y, z, gamma, 1, B, C, H, W, static_cast<cudaStream_t>(stream));
 }
 extern "C" int pnpf_interp(const float* z, const float* eps, float t, float* zt, long long n, int S, void* stream) {
     PNPF_REQUIRE(z && eps && zt && n >= 0 && S >= 1, "bad argument");

@@ -32,8 +32,7 @@ struct EpiParams {
 };
 
 // One thread = one output pixel; v[16] = accumulator columns [col0, col0+16).  Adds bias / temb / residual and stores.
-// `res`: the 16 residual values of this chunk, already loaded by the caller (software-pipelined), used iff p.residual.
-__device__ __forceinline__ void epilogue_apply16(const EpiParams& p, int img, long long pix, int col0, float (&v)[16], const uint4 (&res)[2]) {
+__device__ __forceinline__ void epilogue_apply16(const EpiParams& p, int img, long long pix, int col0, float (&v)[16]) {
     if (p.bias) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -50,9 +49,10 @@ __device__ __forceinline__ void epilogue_apply16(const EpiParams& p, int img, lo
         }
     }
     if (p.residual) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + img * p.res_img_stride + pix * p.res_row_stride + col0);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            const uint4 u = res[q];
+            const uint4 u = __ldg(rp + q);
             const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -212,8 +212,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int ab = p.a_batched ? img : 0;
                 const int bb = p.b_batched ? img : 0;
                 for (int i = 0; i < nk; ++i) {
-                    if (lane == 0) mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
-                    __syncwarp();
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     if (elect_one_sync()) {
@@ -281,18 +280,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int h = h0 + th, w = w0 + tw;
             const bool valid = (h < p.H) && (w < p.W);
             const long long pix = static_cast<long long>(h) * p.W + w;
-            // residual: independent of the accumulator and latency-bound (strided 16-byte global loads) -> software-pipelined
-            // one 16-column chunk ahead, the first chunk is issued before waiting for the MMAs
-            uint4 rq[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            auto ld_res = [&](int c0, uint4(&dst)[2]) {
-                if (p.epi.residual && valid && nt * BN + c0 < p.epi.n_valid) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.epi.residual + img * p.epi.res_img_stride + pix * p.epi.res_row_stride + nt * BN + c0);
-                    dst[0] = __ldg(rp);
-                    dst[1] = __ldg(rp + 1);
-                }
-            };
-            ld_res(0, rq);
-            if (lane == 0) mbar_wait_relaxed(&tfull_bar[acc], acc_phase);   // one lane polls, the warp follows
+            if (lane == 0) mbar_wait(&tfull_bar[acc], acc_phase);   // one lane polls, the warp follows
             __syncwarp();
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
@@ -300,17 +288,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 uint32_t r[16];
                 tmem_ld_x16(t_addr + c0, r);
-                uint4 rn[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-                if (c0 + 16 < BN) ld_res(c0 + 16, rn);
                 tmem_ld_wait();
                 const int col0 = nt * BN + c0;
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
                 const bool act = valid && col0 < p.epi.n_valid;
-                if (act) epilogue_apply16(p.epi, img, pix, col0, v, rq);
-                rq[0] = rn[0];
-                rq[1] = rn[1];
+                if (act) epilogue_apply16(p.epi, img, pix, col0, v);
                 if (p.epi.stats && col0 < p.epi.n_valid) {       // warp-uniform branch
                     const float tot = warp_colsum16(v, act, lane);
                     const int c = col0 + colsum16_col(lane);

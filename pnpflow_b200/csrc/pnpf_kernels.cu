@@ -400,6 +400,7 @@ __global__ void blur_kernel(const float* __restrict__ in, const float* __restric
         const long long o = plane * H * W + (long long)h * W + w;
         if (mode == 1) acc = acc - aux[o];
         else if (mode == 2) acc = aux[o] - gamma * acc;
+        else if (mode == 3) acc = (acc - aux[o] > 0.f) ? 1.f : -1.f;      // laplace: 2*heaviside(Gx - y, 0) - 1 (pnp_flow.py:43)
         out[o] = acc;
     }
 }
@@ -441,8 +442,14 @@ int launch_apply_H(const OpDesc& op, const float* x, float* y, int B, int C, int
 }
 
 // z = x - gamma * A^T(Ax - y) for the diagonal operators and SR, one pass (12 N bytes)
+// residual of the data term: gaussian  r = Ax - y ;  laplace  r = 2*heaviside(Ax - y, 0) - 1  (pnp_flow.py:41,43)
+__device__ __forceinline__ float datafit_residual(float ax, float yv, int laplace) {
+    const float d = __fsub_rn(ax, yv);
+    return laplace ? ((d > 0.f) ? 1.f : -1.f) : d;
+}
+
 __global__ void datafit_diag_kernel(OpDesc op, const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ z,
-                                    float gamma, int C, int H, int W, long long total) {
+                                    float gamma, int laplace, int C, int H, int W, long long total) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int w = (int)(i % W);
@@ -454,27 +461,27 @@ __global__ void datafit_diag_kernel(OpDesc op, const float* __restrict__ x, cons
     if (op.kind == 3) {
         if ((h % op.sf) == 0 && (w % op.sf) == 0) {
             const float yv = y[(r * (H / op.sf) + h / op.sf) * (W / op.sf) + w / op.sf];
-            out = __fsub_rn(xv, __fmul_rn(gamma, __fsub_rn(xv, yv)));
+            out = __fsub_rn(xv, __fmul_rn(gamma, datafit_residual(xv, yv, laplace)));
         }
     } else {
         const int b = (int)(r / C);
-        if (keep_pixel(op, b, h, w, H, W)) out = __fsub_rn(xv, __fmul_rn(gamma, __fsub_rn(xv, y[i])));
+        if (keep_pixel(op, b, h, w, H, W)) out = __fsub_rn(xv, __fmul_rn(gamma, datafit_residual(xv, y[i], laplace)));
     }
     z[i] = out;
 }
 
-int launch_datafit(const OpDesc& op, const float* x, const float* y, float* z, float gamma, int B, int C, int H, int W,
+int launch_datafit(const OpDesc& op, const float* x, const float* y, float* z, float gamma, int laplace, int B, int C, int H, int W,
                    cudaStream_t st) {
     const long long n = (long long)B * C * H * W;
     if (op.kind == 4) {
         PNPF_REQUIRE(op.scratch, "blur data-fidelity step needs pnpf_operator.scratch");
-        if (int e = launch_blur(op, x, y, op.scratch, B * C, H, W, 1, 0.f, st)) return e;   // r = Gx - y
+        if (int e = launch_blur(op, x, y, op.scratch, B * C, H, W, laplace ? 3 : 1, 0.f, st)) return e;   // r = Gx - y (or its sign)
         return launch_blur(op, op.scratch, x, z, B * C, H, W, 2, gamma, st);                 // z = x - gamma G r
     }
     PNPF_REQUIRE(op.kind >= 0 && op.kind <= 3, "unknown operator kind %d", op.kind);
     PNPF_REQUIRE(op.kind != 2 || op.mask, "mask operator without a device mask");
     PNPF_REQUIRE(op.kind != 3 || (op.sf >= 1 && H % op.sf == 0 && W % op.sf == 0), "SR factor %d vs %dx%d", op.sf, H, W);
-    datafit_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, x, y, z, gamma, C, H, W, n);
+    datafit_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, x, y, z, gamma, laplace, C, H, W, n);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -48,7 +48,7 @@ struct OpDesc {                        // device-side view of pnpf_operator
     float* scratch;
 };
 int launch_apply_H(const OpDesc& op, const float* x, float* y, int B, int C, int H, int W, bool adjoint, cudaStream_t st);
-int launch_datafit(const OpDesc& op, const float* x, const float* y, float* z, float gamma, int B, int C, int H, int W,
+int launch_datafit(const OpDesc& op, const float* x, const float* y, float* z, float gamma, int laplace, int B, int C, int H, int W,
                    cudaStream_t st);
 // zt[s][i] = t*z[i] + (1-t)*eps[s][i]
 int launch_interp(const float* z, const float* eps, float t, float* zt, long long n, int S, cudaStream_t st);

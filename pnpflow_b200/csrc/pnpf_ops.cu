@@ -1,7 +1,6 @@
 // Preparation (tensor maps + GemmParams) of the tensor-core ops.
 #include "pnpf_ops.h"
 
-#include <cstdlib>
 #include <cstring>
 
 namespace pnpf {
@@ -87,8 +86,6 @@ static int try_prepare_rowconv(TcOp& op, const ConvDesc& d) {
     if (d.gn_gamma) {
         PNPF_REQUIRE(d.gn_beta && d.gn_stats_a && (d.Cb == 0 || d.gn_stats_b), "fused GroupNorm needs beta and statistics");
         PNPF_REQUIRE(d.Cin % d.gn_groups == 0, "GroupNorm: %d channels not divisible into %d groups", d.Cin, d.gn_groups);
-        static const bool packed_env = getenv("PNPF_GN_PACKED") != nullptr;
-        r.gn_packed = (d.gn_packed || packed_env) ? 1 : 0;
         r.gn = 1; r.gn_silu = d.gn_silu; r.gn_gs = d.Cin / d.gn_groups; r.gn_Ca = d.Cin - d.Cb; r.gn_Cb = d.Cb; r.gn_eps = d.gn_eps;
         r.gn_gamma = d.gn_gamma; r.gn_beta = d.gn_beta; r.gn_st_a = d.gn_stats_a; r.gn_st_b = d.gn_stats_b;
     }

@@ -58,7 +58,6 @@ struct ConvDesc {
     const double* gn_stats_a = nullptr;
     const double* gn_stats_b = nullptr;
     int gn_groups = 32, gn_silu = 1;
-    int gn_packed = 0;              // 1 = packed bf16x2 transform arithmetic (2 % faster, 13 % more error; PNPF_GN_PACKED=1 forces it)
     float gn_eps = 1e-6f;
 };
 int prepare_conv(TcOp& op, const ConvDesc& d);

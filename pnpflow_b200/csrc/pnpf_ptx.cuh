@@ -53,13 +53,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
-// Waiting with back-off for warps that are NOT on the critical path (producer, epilogue, transform): a tight try_wait loop
-// burns issue slots of the SM sub-partition it shares with working warps (ncu: ~50 % issue-active from polling alone).
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    while (!mbar_try_wait(bar, parity)) {
-    }   // (a __nanosleep back-off here was measured SLOWER: wake-up latency outweighs the freed issue slots)
-}
 
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

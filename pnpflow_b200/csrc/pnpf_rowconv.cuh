@@ -22,7 +22,6 @@
 #pragma once
 #include "pnpf_gemm.cuh"
 #include <cuda_fp16.h>
-#include <cuda/std/type_traits>
 
 namespace pnpf {
 
@@ -41,7 +40,6 @@ struct RowConvParams {
     // warps between the TMA and the MMAs (per-channel statistics come from the producing conv's epilogue).
     int gn;                // 0 = input is used as is
     int gn_silu, gn_gs, gn_Ca, gn_Cb;    // activation flag, channels per group, channels of source a / b
-    int gn_packed;         // 1: packed bf16x2 arithmetic (3 instructions per 2 elements), 0: fp32 FMA + fp16x2 tanh
     float gn_eps;
     const float* gn_gamma; // [Ca+Cb]
     const float* gn_beta;
@@ -65,23 +63,29 @@ struct RowCfg {
     static constexpr int NACC = (512 / BN) > 16 ? 16 : (512 / BN);
     static constexpr int TMEM_COLS = NACC * BN;              // 256 (BN=16) or 512
     static constexpr int MAX_SLOTS = 8;
-    // 12 worker warps besides the producer and the MMA issuer: 8 epilogue + 4 GroupNorm-transform warps.
-    // (measured: the epilogue is a per-warp LATENCY chain — wait, tcgen05.ld, tcgen05.st, arrive — so two warp sets
-    //  working on alternate rows beat one set even for thin outputs; 8 transform warps did not beat 4)
+    // 12 worker warps besides the producer and the MMA issuer: 8 epilogue + 4 GroupNorm-transform warps.  The epilogue is
+    // a per-warp latency chain (wait, tcgen05.ld, tcgen05.st, arrive), so two warp sets on alternate rows beat one set
+    // even for thin outputs (same-box A/B in profiles/r01_ab_experiments.md).
     static constexpr int NEW = 8;                            // epilogue warps: two sets of 4
-    static constexpr int NTW = 12 - NEW;                     // transform warps
     static constexpr bool ROW_SPLIT = BN <= 32;              // the two sets alternate rows (C_out <= 32) or split the columns (64)
+    static constexpr int NTW = 12 - NEW;                     // transform warps
     static constexpr int THREADS = 64 + 12 * 32;
     static constexpr int CPT = BN > 32 ? 32 : BN;            // columns per epilogue thread
     static constexpr int BAR_BYTES = 2048;                   // barriers + tmem slot | bias staging (2 x 64 floats) | GN scale/shift (2 x 128)
     static_assert(BN == 16 || BN == 32 || BN == 64, "row conv is for thin outputs");
 };
 
+// cycle counters of CTA 0 (tools/rowconv_dbg.py): compiled in only with -DPNPF_ROWCONV_CLOCKS
+#ifdef PNPF_ROWCONV_CLOCKS
+#define PNPF_CLK() clock64()
+#else
+#define PNPF_CLK() 0ll
+#endif
 #define PNPF_TIMED_WAIT(bar, par, ctr)        \
     do {                                      \
-        const long long _t0 = clock64();      \
+        const long long _t0 = PNPF_CLK();      \
         mbar_wait(bar, par);                  \
-        ctr += clock64() - _t0;               \
+        ctr += PNPF_CLK() - _t0;               \
     } while (0)
 
 // tcgen05.mma, always accumulating, descriptors given as (low word, shared high word)
@@ -112,7 +116,7 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
 }
 // one lane polls, the warp follows
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
-    if (lane == 0) mbar_wait_relaxed(bar, parity);
+    if (lane == 0) mbar_wait(bar, parity);
     __syncwarp();
 }
 
@@ -158,7 +162,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 16; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], Cfg::ROW_SPLIT ? 4 : 8);
+            mbar_init(&tempty_bar[a], Cfg::ROW_SPLIT ? 4 : Cfg::NEW);
         }
         fence_barrier_init();
     }
@@ -206,17 +210,13 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int slot = 0;
             uint32_t phase = 0;
             long long c_wait = 0, c_rows = 0;
-            const long long c_start = clock64();
+            const long long c_start = PNPF_CLK();
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 int img, hb, he, w0;
                 decode(it, img, hb, he, w0);
                 const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
                 for (int j = j0; j <= j1; ++j) {
-                    {
-                        const long long _t0 = clock64();
-                        mbar_wait_warp(&empty_bar[slot], phase ^ 1, lane);
-                        c_wait += clock64() - _t0;
-                    }
+                    PNPF_TIMED_WAIT(&empty_bar[slot], phase ^ 1, c_wait);
                     ++c_rows;
                     uint8_t* sp = slots + slot * p.slot_bytes;
                     const bool centre = (j >= hb) && (j < he) && p.kchunks2;
@@ -235,7 +235,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (++slot == p.nslot) { slot = 0; phase ^= 1; }
                 }
             }
-            if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[0] = clock64() - c_start; p.dbg[1] = c_wait; p.dbg[2] = c_rows; }
+            if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[0] = PNPF_CLK() - c_start; p.dbg[1] = c_wait; p.dbg[2] = c_rows; }
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -257,7 +257,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t slot = 0, phase = 0;
             uint32_t g0 = 0;                           // running output-row counter (selects the accumulator)
             long long c_full = 0, c_tempty = 0;
-            const long long c_start = clock64();
+            const long long c_start = PNPF_CLK();
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 int img, hb, he, w0;
                 decode(it, img, hb, he, w0);
@@ -322,7 +322,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 g0 += static_cast<uint32_t>(he - hb);
             }
-            if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[4] = clock64() - c_start; p.dbg[5] = c_full; p.dbg[6] = c_tempty; }
+            if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[4] = PNPF_CLK() - c_start; p.dbg[5] = c_full; p.dbg[6] = c_tempty; }
         }
         __syncwarp();
     } else if (warp >= 2 + Cfg::NEW) {
@@ -334,11 +334,11 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int slot = 0;
             uint32_t phase = 0;
             long long c_twait = 0, c_tab = 0;
-            const long long c_tstart = clock64();
+            const long long c_tstart = PNPF_CLK();
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 int img, hb, he, w0;
                 decode(it, img, hb, he, w0);
-                const long long c_t0 = clock64();
+                const long long c_t0 = PNPF_CLK();
                 // per-image scale / shift of every input channel (a group may straddle the two concatenated sources)
                 asm volatile("bar.sync 3, %0;" ::"n"(NTT));
                 for (int c = tt; c < Ctot; c += NTT) {
@@ -362,104 +362,76 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 asm volatile("bar.sync 3, %0;" ::"n"(NTT));
                 // Thread -> 16-byte chunk mapping: consecutive lanes take consecutive chunks (conflict-free LDS/STS.128); the
-                // NTT threads cover RPI = NTT / CPR pixel rows per iteration, a multiple of 8, so a thread's swizzle
+                // 128 threads cover RPI = 2048 / rowbytes pixel rows per iteration, a multiple of 8, so a thread's swizzle
                 // phase — hence the 8 channels its chunk holds — never changes: scale/shift stay in registers per item.
                 constexpr int CPR = Cfg::kRowBytes / 16;           // chunks per pixel row (4 or 8)
                 constexpr int RPI = NTT / CPR;                     // rows per iteration (16..64, always a multiple of 8)
-                constexpr int NIT = (Cfg::HALO_ROWS + RPI - 1) / RPI;
                 const int q = tt % CPR, row0 = tt / CPR;
                 const int sw = (Cfg::kRowBytes == 128) ? (row0 & 7) : ((row0 >> 1) & 3);
-                const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
-                // Two arithmetic variants, each with its own register-resident table (generic lambda = separate scopes):
-                //   packed : bf16x2 FMA -> tanh.approx.bf16x2 -> bf16x2 FMA   (3 instructions per 2 elements)
-                //   precise: fp32 FMA, packed fp16 tanh, fp32 result rounded once to bf16
-                auto run_rows = [&](auto packed_tag) {
-                    constexpr bool PACKED = decltype(packed_tag)::value;
-                    float tsc[PACKED ? 1 : KCH][8], tsh[PACKED ? 1 : KCH][8];
-                    uint32_t psc[PACKED ? KCH : 1][4], psh[PACKED ? KCH : 1][4];
-                    const float pre = p.gn_silu ? 0.5f : 1.0f;     // SiLU works on h = y/2: silu(y) = h + h*tanh(h)
+                float tsc[KCH][8], tsh[KCH][8];
 #pragma unroll
-                    for (int c = 0; c < KCH; ++c)
+                for (int c = 0; c < KCH; ++c)
 #pragma unroll
-                        for (int e2 = 0; e2 < 4; ++e2) {
-                            const int ch = c * BK + ((q ^ sw) << 3) + 2 * e2;
-                            const float s0 = gn_tab[ch], s1 = gn_tab[ch + 1], b0 = gn_tab[128 + ch], b1 = gn_tab[128 + ch + 1];
-                            if constexpr (PACKED) {
-                                __nv_bfloat162 a2 = __floats2bfloat162_rn(pre * s0, pre * s1);
-                                __nv_bfloat162 b2 = __floats2bfloat162_rn(pre * b0, pre * b1);
-                                psc[c][e2] = *reinterpret_cast<uint32_t*>(&a2);
-                                psh[c][e2] = *reinterpret_cast<uint32_t*>(&b2);
-                            } else {
-                                tsc[c][2 * e2] = s0; tsc[c][2 * e2 + 1] = s1;
-                                tsh[c][2 * e2] = b0; tsh[c][2 * e2 + 1] = b1;
-                            }
-                        }
-                    c_tab += clock64() - c_t0;
-                    for (int j = j0; j <= j1; ++j) {
-                        {
-                            const long long _t0 = clock64();
-                            mbar_wait_warp(&full_bar[slot], phase, lane);
-                            c_twait += clock64() - _t0;
-                        }
-                        // all of a thread's rows of one tile are loaded first (explicit ld.shared: independent 16-byte loads in
-                        // flight), then transformed, then stored — the per-warp latency chain is paid once per tile, not per row
-                        const uint32_t sbase = smem_u32(slots) + slot * p.slot_bytes + row0 * Cfg::kRowBytes + q * 16;
-#pragma unroll
-                        for (int c = 0; c < KCH; ++c) {
-                            uint4 u[NIT];
-                            bool ok[NIT];
-#pragma unroll
-                            for (int k = 0; k < NIT; ++k) {
-                                const int r = row0 + k * RPI;
-                                const int wpix = w0 - 1 + r;
-                                ok[k] = (r < Cfg::HALO_ROWS) && (wpix >= 0) && (wpix < p.W);   // conv zero padding stays zero
-                                if (ok[k]) u[k] = lds128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes);
-                            }
-#pragma unroll
-                            for (int k = 0; k < NIT; ++k) {
-                                if (!ok[k]) continue;
-                                uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-#pragma unroll
-                                for (int e2 = 0; e2 < 4; ++e2) {
-                                    if constexpr (PACKED) {
-                                        uint32_t h2, t2;
-                                        asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(h2) : "r"(wds[e2]), "r"(psc[c][e2]), "r"(psh[c][e2]));
-                                        if (p.gn_silu) {
-                                            asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t2) : "r"(h2));
-                                            asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(wds[e2]) : "r"(h2), "r"(t2));
-                                        } else {
-                                            wds[e2] = h2;
-                                        }
-                                    } else {
-                                        float y0 = fmaf(__uint_as_float(wds[e2] << 16), tsc[c][2 * e2], tsh[c][2 * e2]);
-                                        float y1 = fmaf(__uint_as_float(wds[e2] & 0xFFFF0000u), tsc[c][2 * e2 + 1], tsh[c][2 * e2 + 1]);
-                                        if (p.gn_silu) {
-                                            // packed fp16 tanh: one SFU op per two elements; fp16 keeps 3 more mantissa bits than the bf16 result
-                                            const __half2 hh = __floats2half2_rn(0.5f * y0, 0.5f * y1);
-                                            uint32_t hb2 = *reinterpret_cast<const uint32_t*>(&hh), tb;
-                                            asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(hb2));
-                                            const __half2 th = *reinterpret_cast<const __half2*>(&tb);
-                                            const float2 o = __half22float2(__hfma2(hh, th, hh));
-                                            y0 = o.x;
-                                            y1 = o.y;
-                                        }
-                                        __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
-                                        wds[e2] = *reinterpret_cast<uint32_t*>(&b2);
-                                    }
-                                }
-                                sts128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes, make_uint4(wds[0], wds[1], wds[2], wds[3]));
-                            }
-                        }
-                        fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&ready_bar[slot]);
-                        if (++slot == p.nslot) { slot = 0; phase ^= 1; }
+                    for (int e = 0; e < 8; ++e) {
+                        const int ch = c * BK + ((q ^ sw) << 3) + e;
+                        tsc[c][e] = gn_tab[ch];
+                        tsh[c][e] = gn_tab[128 + ch];
                     }
-                };
-                if (p.gn_packed) run_rows(cuda::std::true_type{});
-                else run_rows(cuda::std::false_type{});
+                const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
+                c_tab += PNPF_CLK() - c_t0;
+                for (int j = j0; j <= j1; ++j) {
+                    {
+                        const long long _t0 = PNPF_CLK();
+                        mbar_wait_warp(&full_bar[slot], phase, lane);
+                        c_twait += PNPF_CLK() - _t0;
+                    }
+                    // all of a thread's rows of one tile are loaded first (explicit ld.shared: independent 16-byte loads in
+                    // flight), then transformed, then stored — the per-warp latency chain is paid once per tile, not per row
+                    constexpr int NIT = (Cfg::HALO_ROWS + RPI - 1) / RPI;            // 5 (64-byte rows) or 9 (128-byte rows)
+                    const uint32_t sbase = smem_u32(slots) + slot * p.slot_bytes + row0 * Cfg::kRowBytes + q * 16;
+#pragma unroll
+                    for (int c = 0; c < KCH; ++c) {
+                        uint4 u[NIT];
+                        bool ok[NIT];
+#pragma unroll
+                        for (int k = 0; k < NIT; ++k) {
+                            const int r = row0 + k * RPI;
+                            const int wpix = w0 - 1 + r;
+                            ok[k] = (r < Cfg::HALO_ROWS) && (wpix >= 0) && (wpix < p.W);   // conv zero padding stays zero
+                            if (ok[k]) u[k] = lds128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes);
+                        }
+#pragma unroll
+                        for (int k = 0; k < NIT; ++k) {
+                            if (!ok[k]) continue;
+                            uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+                            for (int e2 = 0; e2 < 4; ++e2) {
+                                float y0 = fmaf(__uint_as_float(wds[e2] << 16), tsc[c][2 * e2], tsh[c][2 * e2]);
+                                float y1 = fmaf(__uint_as_float(wds[e2] & 0xFFFF0000u), tsc[c][2 * e2 + 1], tsh[c][2 * e2 + 1]);
+                                if (p.gn_silu) {                       // silu(y) = h + h * tanh(h), h = y / 2
+                                    // packed fp16 tanh: ONE MUFU op per two elements (the SFU is this stage's bottleneck); fp16 keeps
+                                    // 3 more mantissa bits than the bf16 result, so the rounding of the output dominates the error
+                                    const __half2 hh = __floats2half2_rn(0.5f * y0, 0.5f * y1);
+                                    uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh), tb;
+                                    asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(hb));
+                                    const __half2 th = *reinterpret_cast<const __half2*>(&tb);
+                                    const float2 o = __half22float2(__hfma2(hh, th, hh));
+                                    y0 = o.x;
+                                    y1 = o.y;
+                                }
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
+                                wds[e2] = *reinterpret_cast<uint32_t*>(&b2);
+                            }
+                            sts128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes, make_uint4(wds[0], wds[1], wds[2], wds[3]));
+                        }
+                    }
+                    fence_proxy_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ready_bar[slot]);
+                    if (++slot == p.nslot) { slot = 0; phase ^= 1; }
+                }
             }
-            if (p.dbg && blockIdx.x == 0 && tt == 0) { p.dbg[3] = clock64() - c_tstart; p.dbg[7] = c_twait; p.dbg[11] = c_tab; }
+            if (p.dbg && blockIdx.x == 0 && tt == 0) { p.dbg[3] = PNPF_CLK() - c_tstart; p.dbg[7] = c_twait; p.dbg[11] = c_tab; }
         }
     } else {
         // ===================== epilogue: warps 2..5 = set 0 (and warps 6..9 = set 1 for C_out = 64) =====================
@@ -467,12 +439,12 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int m = quarter * 32 + lane;            // pixel within the strip
         const int ethread = threadIdx.x - 64;         // 0..255
-        const int colbase = Cfg::ROW_SPLIT ? 0 : set * 32;
+        const int colbase = Cfg::ROW_SPLIT ? 0 : set * 32;   // column split: set 1 takes columns 32..63 of C_out = 64
         float* bsm = bias_sm + set * 64;
         const uint32_t set_bar = 1 + set;             // named barrier id of this warp set (128 threads)
         uint32_t g0 = 0;
         long long c_tfull = 0, c_rows = 0;
-        const long long c_start = clock64();
+        const long long c_start = PNPF_CLK();
         for (int it = blockIdx.x; it < items; it += gridDim.x) {
             int img, hb, he, w0;
             decode(it, img, hb, he, w0);
@@ -497,19 +469,10 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t g = g0 + static_cast<uint32_t>(r - hb);
                 const uint32_t acc = g % NACC;
                 const long long pix = static_cast<long long>(r) * p.W + w0 + m;
-                // the residual does not depend on the accumulator: issue its (latency-bound, strided) global loads BEFORE
-                // waiting for the MMAs so that the wait hides them
-                uint4 resv[CPT / 8];
-                if (p.epi.residual) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.epi.residual + img * p.epi.res_img_stride + pix * p.epi.res_row_stride + colbase);
-#pragma unroll
-                    for (int q = 0; q < CPT / 8; ++q)
-                        if (colbase + q * 8 < p.epi.n_valid) resv[q] = __ldg(rp + q);
-                }
                 {
-                    const long long _t0 = clock64();
+                    const long long _t0 = PNPF_CLK();
                     mbar_wait_warp(&tfull_bar[acc], (g / NACC) & 1, lane);
-                    c_tfull += clock64() - _t0;
+                    c_tfull += PNPF_CLK() - _t0;
                 }
                 ++c_rows;
                 tc_fence_after();
@@ -538,9 +501,11 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         v[jj + 3] = __uint_as_float(rr[q][jj + 3]) + b4.w;
                     }
                     if (p.epi.residual) {
+                        // (prefetching these loads ahead of the accumulator wait was measured 4 % SLOWER: profiles/r01_ab_experiments.md)
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.epi.residual + img * p.epi.res_img_stride + pix * p.epi.res_row_stride + col0);
 #pragma unroll
                         for (int h2 = 0; h2 < 2; ++h2) {
-                            const uint4 u = resv[q * 2 + h2];
+                            const uint4 u = __ldg(rp + h2);
                             const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj) {
@@ -590,8 +555,8 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             g0 += static_cast<uint32_t>(he - hb);
         }
-        if (p.dbg && blockIdx.x == 0 && ethread == 0) { p.dbg[8] = clock64() - c_start; p.dbg[9] = c_tfull; p.dbg[10] = c_rows; }
-        if (p.dbg && blockIdx.x == 0 && ethread == 128 && Cfg::NEW == 8) { p.dbg[12] = clock64() - c_start; p.dbg[13] = c_tfull; p.dbg[14] = c_rows; }
+        if (p.dbg && blockIdx.x == 0 && ethread == 0) { p.dbg[8] = PNPF_CLK() - c_start; p.dbg[9] = c_tfull; p.dbg[10] = c_rows; }
+        if (p.dbg && blockIdx.x == 0 && ethread == 128 && Cfg::NEW == 8) { p.dbg[12] = PNPF_CLK() - c_start; p.dbg[13] = c_tfull; p.dbg[14] = c_rows; }
     }
     tc_fence_before();
     __syncthreads();

@@ -65,14 +65,19 @@ class Degradation:
         return (B, C, Hy, Wy)
 
     # -- fused data-fidelity step  z = x - gamma * A^T(Ax - y)   (pnp_flow.py:39-41,111-112)
-    def datafit_step(self, x, y, gamma: float, out=None):
+    def datafit_step(self, x, y, gamma: float, out=None, noise_type: str = 'gaussian'):
+        """z = x - gamma * A^T r,  r = Ax - y (gaussian, pnp_flow.py:41) or 2*heaviside(Ax - y, 0) - 1 (laplace, :43)."""
         _check_cuda(x)
+        if noise_type not in ('gaussian', 'laplace'):
+            raise ValueError('Noise type not supported')                     # pnp_flow.py:45
         B, Cc, Hh, Ww = x.shape
         op, _keep = self.descriptor(B, Cc, Hh, Ww, x.device)
         z = out if out is not None else torch.empty_like(x)
+        lib = _lib.load()
+        fn = lib.pnpf_datafit_step if noise_type == 'gaussian' else lib.pnpf_datafit_step_laplace
         with torch.cuda.device(x.device):
-            _lib.check(_lib.load().pnpf_datafit_step(C.byref(op), x.data_ptr(), y.data_ptr(), z.data_ptr(), float(gamma),
-                                                     B, Cc, Hh, Ww, _lib.stream_ptr()))
+            _lib.check(fn(C.byref(op), x.data_ptr(), y.data_ptr(), z.data_ptr(), float(gamma), B, Cc, Hh, Ww,
+                          _lib.stream_ptr()))
         return z
 
 
@@ -207,8 +212,13 @@ class _PythonOperator(Degradation):
     def H_adj(self, y):
         return self.inner.H_adj(y)
 
-    def datafit_step(self, x, y, gamma, out=None):
-        z = x - gamma * self.inner.H_adj(self.inner.H(x) - y)
+    def datafit_step(self, x, y, gamma, out=None, noise_type='gaussian'):
+        r = self.inner.H(x) - y
+        if noise_type == 'laplace':
+            r = 2 * torch.heaviside(r, torch.zeros_like(r)) - 1
+        elif noise_type != 'gaussian':
+            raise ValueError('Noise type not supported')
+        z = x - gamma * self.inner.H_adj(r)
         if out is not None:
             out.copy_(z)
             return out

@@ -6,6 +6,7 @@ state_dict is repacked into the engine), an ``oracle``-style ``(cfg, state_dict)
 
 Per outer step (pnp_flow.py:102-121) the engine runs
     1. one fused data-fidelity kernel          z = x - gamma_t * A^T(Ax - y)            (:29-45,111-112)
+       (noise_type='laplace': A^T(2*heaviside(Ax - y, 0) - 1), :42-43)
     2. one interpolation kernel for all S draws  z~_s = t z + (1-t) eps_s               (:47-48)
     3. ONE U-Net evaluation on the S*B batch    v_s = v_theta(z~_s, t)                  (:19-21)  [CUDA-graph replay]
     4. one push+average kernel                 x = (1/S) sum_s (z~_s + (1-t) v_s)       (:50-52,114-121)
@@ -78,10 +79,9 @@ class PnPFlowSession:
 
     def __init__(self, engine: UNetEngine, degradation, y_shape, *, steps_pnp=100, lr_pnp=1.0, alpha=1.0,
                  gamma_style='alpha_1_minus_t', num_samples=5, noise_type='gaussian', use_cuda_graph=True, device="cuda"):
-        if noise_type != 'gaussian':
-            if noise_type == 'laplace':
-                raise NotImplementedError("laplace data term (pnp_flow.py:42-43) is not implemented on the engine yet")
+        if noise_type not in ('gaussian', 'laplace'):
             raise ValueError('Noise type not supported')                     # pnp_flow.py:45,68,87
+        self.noise_type = noise_type
         self.lib = _lib.load()
         self.engine = engine
         self.op = as_engine_operator(degradation)
@@ -119,7 +119,7 @@ class PnPFlowSession:
         t = float(np.float32(self.delta * it))                               # :107-108 (python double -> fp32 tensor)
         gamma = gamma_schedule(self.lr_pnp, t, self.gamma_style, self.alpha)
         with torch.no_grad(), torch.cuda.device(self.dev):
-            self.op.datafit_step(x, y, gamma, out=self.z)
+            self.op.datafit_step(x, y, gamma, out=self.z, noise_type=self.noise_type)
             for s in range(S):
                 if noise_it is not None:
                     self.eps[s].copy_(next(noise_it))
@@ -211,7 +211,8 @@ class PNP_FLOW(object):
             lr_eff = a.lr_pnp                       # gamma_t = lr_pnp (1-t)^alpha: sigma^2 cancels (:41 vs :61)
             a.lr_pnp = sigma_noise ** 2 * a.lr_pnp  # keep the reference's observable side effect on args (:61)
         elif a.noise_type == 'laplace':
-            raise NotImplementedError("laplace data term (pnp_flow.py:42-43,64-66) is not implemented on the engine yet")
+            lr_eff = a.lr_pnp                       # lr_t * grad = sigma lr_pnp g(t) * A^T(sign)/sigma: sigma cancels (:43 vs :65)
+            a.lr_pnp = sigma_noise * a.lr_pnp       # observable side effect on args (:65)
         else:
             raise ValueError('Noise type not supported')
         op = as_engine_operator(degradation)
@@ -222,8 +223,12 @@ class PNP_FLOW(object):
             a.batch = batch
             clean_dev = clean_img.clone().to(self.device).float()
             noisy_img = op.H(clean_dev)
-            torch.manual_seed(batch)                                         # :79
-            noisy_img = noisy_img + torch.randn_like(noisy_img) * sigma_noise
+            if a.noise_type == 'gaussian':
+                torch.manual_seed(batch)                                     # :79
+                noisy_img = noisy_img + torch.randn_like(noisy_img) * sigma_noise
+            else:                                                            # :81-85 (unseeded in the reference too)
+                noisy_img = noisy_img + torch.distributions.laplace.Laplace(
+                    torch.zeros_like(noisy_img), sigma_noise * torch.ones_like(noisy_img)).sample()
             if getattr(a, 'compute_time', False):
                 torch.cuda.synchronize()
                 t0 = perf_counter()

@@ -58,3 +58,25 @@ def test_loop_bit_exact_vs_reference_solve_ip(problem, alpha):
                                 steps_pnp=10, num_samples=2, alpha=alpha)
     assert torch.equal(y, y_ref)
     assert torch.equal(x, x_ref), (x - x_ref).abs().max()
+
+
+@pytest.mark.parametrize("problem", ["box", "sr2", "blur"])
+def test_laplace_loop_bit_exact_vs_reference_solve_ip(problem):
+    """noise_type='laplace' (pnp_flow.py:42-43,64-66,81-85): measurement synthesis + 10 steps x 2 draws."""
+    _, D, _, _ = ref_shim.load()
+    cfg = oracle.UNetConfig(3, 64, 32, (1, 2), 1, (16,))
+    sd = oracle.init_state_dict(cfg, seed=2)
+    net = ref_shim.build_reference_unet(cfg, sd)
+    case = {n: (r, o) for n, r, o in mg.operator_cases()}[problem]
+    g = torch.Generator().manual_seed(78)
+    clean = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    args = ref_shim.RefArgs(steps_pnp=10, num_samples=2, alpha=0.5, dim_image=64, noise_type='laplace', lr_pnp=0.05)
+    torch.manual_seed(4321)
+    (y_ref, x_ref), = ref_shim.run_reference_solve_ip(net, [clean], case[0](D), 0.05, args)
+    deg = case[1]()
+    torch.manual_seed(4321)
+    y = loop.synthesize_measurement(clean, deg.H, 0.05, 0, 'laplace')
+    x = oracle.pnp_flow_restore(lambda a, b: oracle.unet_forward(sd, cfg, a, b), y, deg, 0.05, steps_pnp=10,
+                                num_samples=2, alpha=0.5, lr_pnp=0.05, noise_type='laplace')
+    assert torch.equal(y, y_ref)
+    assert torch.equal(x, x_ref), (x - x_ref).abs().max()

@@ -1,3 +1,4 @@
+"""Cycle counters of CTA 0 of the row kernel.  Needs a library built with `make -C pnpflow_b200/csrc clean all EXTRA=-DPNPF_ROWCONV_CLOCKS`."""
 import ctypes as C, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 os.environ["PNPF_ROWCONV_DBG"] = "1"
