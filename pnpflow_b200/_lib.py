@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpnpflow_sm100a.so")
+# PNPF_LIB selects another BUILD of the same library (profiling / A-B builds under ab/); there is no other implementation
+LIB_PATH = os.environ.get("PNPF_LIB") or os.path.join(_HERE, "libpnpflow_sm100a.so")
 
 _lib = None
 

@@ -53,19 +53,22 @@ extern "C" int pnpf_conv2d_nhwc(const void* x, int B, int Hin, int Win, int Cin,
     TcOp op;
     int rc = prepare_conv(op, d);
     long long* dbg = nullptr;
-    if (!rc && op.kind == 1 && getenv("PNPF_ROWCONV_DBG")) {          // profiling experiment: cycle counters of CTA 0
-        cudaMalloc(&dbg, 16 * sizeof(long long));
-        cudaMemset(dbg, 0, 16 * sizeof(long long));
+    if (!rc && getenv("PNPF_ROWCONV_DBG")) {          // profiling experiment: cycle counters of CTA 0
+        cudaMalloc(&dbg, 32 * sizeof(long long));
+        cudaMemset(dbg, 0, 32 * sizeof(long long));
         op.rp.dbg = dbg;
+        op.p.dbg = dbg;
     }
     if (!rc) rc = launch_tc(op, s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (dbg) {
-        long long h[16];
+        long long h[32];
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        printf("ROWCONV_DBG producer: total %lld wait_empty %lld rows %lld | mma: total %lld wait_full %lld wait_tempty %lld | "
-               "epi0: total %lld wait_tfull %lld rows %lld | epi1: total %lld wait_tfull %lld rows %lld\n",
+        printf("%s producer: total %lld wait_empty %lld rows/tiles %lld | mma: total %lld wait_full %lld wait_tempty %lld | "
+               "epi0: total %lld wait_tfull %lld rows %lld | epi1: total %lld wait_tfull %lld rows %lld\n", op.kind == 1 ? "ROWCONV_DBG" : "GEMM_DBG",
                h[0], h[1], h[2], h[4], h[5], h[6], h[8], h[9], h[10], h[12], h[13], h[14]);
+        if (op.kind == 1)
+            printf("   mma: issue %lld commit %lld | epi0: tmem_ld %lld tmem_st+arrive %lld stats_flush %lld\n", h[16], h[17], h[18], h[19], h[20]);
         fflush(stdout);
         cudaFree(dbg);
     }
@@ -136,17 +139,19 @@ extern "C" int pnpf_gn_conv2d_nhwc(const void* xa, int Ca, const void* xb, int C
     if (!rc) rc = prepare_conv(op, d);
     long long* dbg = nullptr;
     if (!rc && op.kind == 1 && getenv("PNPF_ROWCONV_DBG")) {
-        cudaMalloc(&dbg, 16 * sizeof(long long));
-        cudaMemset(dbg, 0, 16 * sizeof(long long));
+        cudaMalloc(&dbg, 32 * sizeof(long long));
+        cudaMemset(dbg, 0, 32 * sizeof(long long));
         op.rp.dbg = dbg;
     }
     if (!rc) rc = launch_tc(op, s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (dbg) {
-        long long h[16];
+        long long h[32];
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
         printf("ROWCONV_GN_DBG producer: total %lld wait_empty %lld rows %lld | transform: total %lld wait_full %lld table %lld | mma: total %lld "
                "wait_ready %lld wait_tempty %lld | epi0: total %lld wait_tfull %lld\n", h[0], h[1], h[2], h[3], h[7], h[11], h[4], h[5], h[6], h[8], h[9]);
+        printf("   mma: issue %lld commit %lld | epi0: tmem_ld %lld tmem_st+arrive %lld stats_flush %lld | transform: fence+arrive %lld\n", h[16], h[17], h[18],
+               h[19], h[20], h[21]);
         fflush(stdout);
         cudaFree(dbg);
     }

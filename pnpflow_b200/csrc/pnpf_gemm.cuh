@@ -131,8 +131,22 @@ struct GemmParams {
     int kchunks;           // channel chunks per tap read through tmA
     int c_base;            // first channel of tmA to read
     int kchunks2;          // trailing 1x1 chunks read through tmA2 (0 = none)
+    long long* dbg;        // optional [16] cycle counters of CTA 0 (-DPNPF_ROWCONV_CLOCKS builds), else nullptr
     EpiParams epi;
 };
+
+// cycle counters of CTA 0 (tools/rowconv_dbg.py): compiled in only with -DPNPF_ROWCONV_CLOCKS
+#ifdef PNPF_ROWCONV_CLOCKS
+#define PNPF_CLK() clock64()
+#else
+#define PNPF_CLK() 0ll
+#endif
+#define PNPF_TIMED_WAIT(bar, par, ctr)        \
+    do {                                      \
+        const long long _t0 = PNPF_CLK();      \
+        mbar_wait(bar, par);                  \
+        ctr += PNPF_CLK() - _t0;               \
+    } while (0)
 
 template <int BK, int BN>
 struct GemmCfg {
@@ -206,13 +220,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         {
             int stage = 0;
             uint32_t phase = 0;
+            long long c_wait = 0, c_tiles = 0;
+            const long long c_start = PNPF_CLK();
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 int img, h0, w0, nt;
                 decode_tile(p, t, img, h0, w0, nt);
                 const int ab = p.a_batched ? img : 0;
                 const int bb = p.b_batched ? img : 0;
+                ++c_tiles;
                 for (int i = 0; i < nk; ++i) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    PNPF_TIMED_WAIT(&empty_bar[stage], phase ^ 1, c_wait);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     if (elect_one_sync()) {
@@ -231,6 +248,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[0] = PNPF_CLK() - c_start; p.dbg[1] = c_wait; p.dbg[2] = c_tiles; }
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -241,12 +259,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            long long c_full = 0, c_tempty = 0;
+            const long long c_start = PNPF_CLK();
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
+                PNPF_TIMED_WAIT(&tempty_bar[acc], acc_phase ^ 1, c_tempty);      // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int i = 0; i < nk; ++i) {
-                    mbar_wait(&full_bar[stage], phase);
+                    PNPF_TIMED_WAIT(&full_bar[stage], phase, c_full);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint64_t adesc = make_smem_desc<Cfg::kRowBytes>(sa);
@@ -265,6 +285,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[4] = PNPF_CLK() - c_start; p.dbg[5] = c_full; p.dbg[6] = c_tempty; }
         }
         __syncwarp();
     } else {
@@ -274,14 +295,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int th = m / p.TW, tw = m - th * p.TW;
         int acc = 0;
         uint32_t acc_phase = 0;
+        long long c_tfull = 0;
+        const long long c_start = PNPF_CLK();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             int img, h0, w0, nt;
             decode_tile(p, t, img, h0, w0, nt);
             const int h = h0 + th, w = w0 + tw;
             const bool valid = (h < p.H) && (w < p.W);
             const long long pix = static_cast<long long>(h) * p.W + w;
-            if (lane == 0) mbar_wait(&tfull_bar[acc], acc_phase);   // one lane polls, the warp follows
-            __syncwarp();
+            {
+                const long long _t0 = PNPF_CLK();
+                if (lane == 0) mbar_wait(&tfull_bar[acc], acc_phase);   // one lane polls, the warp follows
+                __syncwarp();
+                c_tfull += PNPF_CLK() - _t0;
+            }
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
@@ -307,6 +334,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { p.dbg[8] = PNPF_CLK() - c_start; p.dbg[9] = c_tfull; }
     }
     tc_fence_before();
     __syncthreads();

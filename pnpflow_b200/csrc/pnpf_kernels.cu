@@ -102,17 +102,29 @@ int launch_gn_stats(const GnSrc& s, int B, int HW, double* stats, cudaStream_t s
 // =================================================================================================
 // GroupNorm apply (+ SiLU) -> bf16 NHWC conv operand; optional raw concat copy
 // =================================================================================================
-__global__ void gn_apply_kernel(GnSrc s, int HW, int pix_per_block, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, float eps, int gs, int silu, bf16* __restrict__ dst,
-                                bf16* __restrict__ raw_dst) {
-    extern __shared__ float ss[];                     // scale[C], shift[C]
+// Prologue: one thread per GROUP reduces the fp64 channel statistics (a group may straddle the two concatenated
+// sources) to mean / rstd, then one thread per channel derives scale / shift in fp32.  Main loop: a thread owns one
+// 16-byte channel vector and walks the block's pixels four at a time (four independent loads in flight);
+// SiLU(y) = h + h*tanh(h) with h = y/2 folded into scale/shift -> one MUFU op per element.
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(GnSrc s, int HW, int pix_per_block, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, int gs, int silu, bf16* __restrict__ dst,
+                bf16* __restrict__ raw_dst) {
+    extern __shared__ float ss[];                     // scale[C] | shift[C] | mean[G] | rstd[G]
     const int C = s.C1 + s.C2;
+    const int G = C / gs;
     const int img = blockIdx.y;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g0 = (c / gs) * gs;
+    float* gmean = ss + 2 * C;
+    float* grstd = gmean + G;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
         double S = 0, Q = 0;
-        for (int j = 0; j < gs; ++j) {                 // a group may straddle the two concatenated sources
-            const int cc = g0 + j;
+        for (int j = 0; j < gs; ++j) {
+            const int cc = g * gs + j;
             const double* sp = (cc < s.C1) ? s.st1 + ((long long)img * s.C1 + cc) * 2 : s.st2 + ((long long)img * s.C2 + (cc - s.C1)) * 2;
             S += sp[0];
             Q += sp[1];
@@ -121,10 +133,16 @@ __global__ void gn_apply_kernel(GnSrc s, int HW, int pix_per_block, const float*
         const double mean = S / n;
         double var = Q / n - mean * mean;
         if (var < 0) var = 0;
-        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-        const float sc = rstd * gamma[c];
-        ss[c] = sc;
-        ss[C + c] = beta[c] - (float)mean * sc;
+        gmean[g] = (float)mean;
+        grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const float half = silu ? 0.5f : 1.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / gs;
+        const float sc = grstd[g] * gamma[c];
+        ss[c] = half * sc;
+        ss[C + c] = half * (beta[c] - gmean[g] * sc);
     }
     __syncthreads();
     const int nvec = C >> 3;
@@ -138,19 +156,26 @@ __global__ void gn_apply_kernel(GnSrc s, int HW, int pix_per_block, const float*
         sc[j] = ss[v * 8 + j];
         sh[j] = ss[C + v * 8 + j];
     }
-    for (int p = p0 + pl; p < p1; p += ppb) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src_ptr(s, img, p, HW, v * 8)));
-        const long long o = ((long long)img * HW + p) * C + v * 8;
-        if (raw_dst) *reinterpret_cast<uint4*>(raw_dst + o) = u;
-        float f[8];
-        unpack8(u, f);
+    constexpr int U = 4;
+    for (int p = p0 + pl; p < p1; p += U * ppb) {
+        uint4 u[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float y = fmaf(f[j], sc[j], sh[j]);
-            if (silu) y = y / (1.f + __expf(-y));
-            f[j] = y;
+        for (int k = 0; k < U; ++k)
+            if (p + k * ppb < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(src_ptr(s, img, p + k * ppb, HW, v * 8)));
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (p + k * ppb >= p1) break;
+            const long long o = ((long long)img * HW + p + k * ppb) * C + v * 8;
+            if (raw_dst) *reinterpret_cast<uint4*>(raw_dst + o) = u[k];
+            float f[8];
+            unpack8(u[k], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float h = fmaf(f[j], sc[j], sh[j]);
+                f[j] = silu ? fmaf(h, tanh_approx(h), h) : h;
+            }
+            *reinterpret_cast<uint4*>(dst + o) = pack8(f);
         }
-        *reinterpret_cast<uint4*>(dst + o) = pack8(f);
     }
 }
 
@@ -162,7 +187,7 @@ int launch_gn_apply(const GnSrc& s, int B, int HW, const float* gamma, const flo
     const int ppb_blk = gn_pix_per_block(HW, B);
     dim3 grid((HW + ppb_blk - 1) / ppb_blk, B);
     PNPF_REQUIRE(s.st1 && (s.C2 == 0 || s.st2), "GroupNorm apply without statistics");
-    gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), st>>>(s, HW, ppb_blk, gamma, beta, eps, C / groups, silu, dst, raw_dst);
+    gn_apply_kernel<<<grid, threads, (2 * C + 2 * groups) * sizeof(float), st>>>(s, HW, ppb_blk, gamma, beta, eps, C / groups, silu, dst, raw_dst);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

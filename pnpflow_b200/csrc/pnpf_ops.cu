@@ -1,6 +1,7 @@
 // Preparation (tensor maps + GemmParams) of the tensor-core ops.
 #include "pnpf_ops.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace pnpf {
@@ -35,37 +36,59 @@ static void fill_epi(EpiParams& e, const ConvDesc& d) {
     e.stats = d.stats_out;
 }
 
-constexpr int ROWCONV_SMEM_BUDGET = 200 * 1024;
-int rowconv_max_smem() { return ROWCONV_SMEM_BUDGET + 1024 + 512; }
+// Shared memory of the row kernel: 227 KB per CTA on sm_100 minus barriers/tables (RowCfg::BAR_BYTES) and alignment slack.
+constexpr int ROWCONV_SMEM_MAX = 227 * 1024;
+constexpr int ROWCONV_SMEM_BUDGET = ROWCONV_SMEM_MAX - 2048 - 1024;
+int rowconv_max_smem() { return ROWCONV_SMEM_MAX; }
 
 // Row-streaming kernel: shape analysis shared by rowconv_eligible() and the preparation.
-struct RowShape { int BK, BN, kch, kch2, kch_a, kch2_a, w_bytes, slot_bytes, nslot; };
+struct RowShape { int BK, BN, nsplit, kch, kch2, kch_a, kch2_a, w_bytes, slot_bytes, nslot, stage_bytes; };
 static bool rowconv_shape(const ConvDesc& d, RowShape& r) {
     if (!d.allow_rowconv || d.ksize != 3 || d.stride != 1 || d.Wout % 128 != 0 || d.Wout != d.Win || d.Hout != d.Hin) return false;
     if (!(d.N_pad == 16 || d.N_pad == 32 || d.N_pad == 64) || d.c_base != 0) return false;
     const int Ca = d.Cin - d.Cb, C2a = d.C2 - d.C2b;
     if (d.Cin % 32 || d.C2 % 32 || Ca % 32 || d.Cb % 32 || C2a % 32 || d.C2b % 32 || Ca <= 0) return false;
     r.BK = (Ca % 64 == 0 && d.Cb % 64 == 0 && C2a % 64 == 0 && d.C2b % 64 == 0) ? 64 : 32;
-    r.BN = d.N_pad;
     const int rowb = r.BK * 2;
     const int halo_tile = (136 * rowb + 1023) / 1024 * 1024, x2_tile = 128 * rowb;
-    const int w_tile = (r.BN * r.BK * 2 + 1023) / 1024 * 1024;
     r.kch = d.Cin / r.BK;
     r.kch2 = d.C2 > 0 ? d.C2 / r.BK : 0;        // by channel count, not pointer: the size-query plan has no pointers
     r.kch_a = Ca / r.BK;
     r.kch2_a = d.C2 > 0 ? C2a / r.BK : 0;
     if (r.kch < 1 || r.kch > 3) return false;
-    if ((r.BN * rowb) % 1024 != 0) return false;    // stacked vertical-tap tiles must keep the swizzle phase
     if (d.gn_gamma && d.Cin > 128) return false;     // scale/shift table
-    r.w_bytes = 3 * r.kch * (3 * r.BN * rowb) + r.kch2 * w_tile;
     r.slot_bytes = r.kch * halo_tile + r.kch2 * x2_tile;
-    r.nslot = (ROWCONV_SMEM_BUDGET - r.w_bytes) / r.slot_bytes;
-    if (r.nslot > 8) r.nslot = 8;
-    return r.nslot >= 4;
+    // All nine taps of the weights stay resident next to a ring of input-row slots.  When the full C_out does not leave
+    // four slots, the output channels are split over two CTAs (nsplit = 2: each keeps half of the weights and both stream
+    // the same rows; the second read of a row hits L2) as long as three slots remain.
+    static const int max_split = getenv("PNPF_NO_NSPLIT") ? 1 : 2;     // A/B switch (tools/ab_env.py)
+    for (int nsplit = 1; nsplit <= max_split; ++nsplit) {
+        const int BN = d.N_pad / nsplit;
+        if (BN < 16 || (BN * rowb) % 1024 != 0) continue;        // stacked vertical-tap tiles must keep the swizzle phase
+        const int w_tile = (BN * r.BK * 2 + 1023) / 1024 * 1024;
+        const int w_bytes = 3 * r.kch * (3 * BN * rowb) + r.kch2 * w_tile;
+        // bf16 NHWC outputs with full 32-channel blocks leave through staging tiles + TMA store (RowCfg::STAGE_BYTES)
+        const int stage = (d.out_mode == 0 && BN >= 32 && d.n_valid == d.N_pad && d.out_col_stride == 1) ? (BN <= 32 ? 1 : 2) * 2 * 128 * 64 : 0;
+        int nslot = (ROWCONV_SMEM_BUDGET - w_bytes - stage) / r.slot_bytes;
+        if (nslot > 8) nslot = 8;
+        if (nslot >= (nsplit == 1 ? 4 : 3)) {
+            r.BN = BN; r.nsplit = nsplit; r.w_bytes = w_bytes; r.nslot = nslot; r.stage_bytes = stage;
+            return true;
+        }
+    }
+    return false;
 }
 bool rowconv_eligible(const ConvDesc& d) {
     RowShape r;
     return rowconv_shape(d, r);
+}
+void describe_conv_impl(const ConvDesc& d, char* buf, size_t n) {
+    RowShape r;
+    if (rowconv_shape(d, r))
+        snprintf(buf, n, "rowconv<%d,%d,%d> nsplit=%d nslot=%d kch2=%d w=%dKB slot=%dKB stage=%dKB gn=%d", r.BK, r.BN, r.kch, r.nsplit, r.nslot,
+                 r.kch2, r.w_bytes / 1024, r.slot_bytes / 1024, r.stage_bytes / 1024, d.gn_gamma ? 1 : 0);
+    else
+        snprintf(buf, n, "conv_gemm<%d,%d> k=%d s=%d", (d.Cin % 64 == 0 && d.C2 % 64 == 0) ? 64 : 32, d.N_pad > 256 ? 256 : d.N_pad, d.ksize, d.stride);
 }
 
 // returns -1 when the shape does not qualify (caller falls back to the per-tap kernel)
@@ -77,10 +100,9 @@ static int try_prepare_rowconv(TcOp& op, const ConvDesc& d) {
     memset(&r, 0, sizeof(r));
     r.H = d.Hout; r.W = d.Wout; r.n_img = d.B;
     r.strips = d.Wout / 128;
-    int seg = 32;
-    while (seg > 8 && (long long)d.B * r.strips * ((d.Hout + seg - 1) / seg) < 3LL * num_sms()) seg >>= 1;
-    r.seg_rows = seg;
-    r.segs = (d.Hout + seg - 1) / seg;
+    r.nsplit = sh.nsplit;
+    r.tma_store = sh.stage_bytes > 0;
+    PNPF_REQUIRE((long long)d.B * r.strips * d.Hout < (1LL << 31) / 256, "row conv: batch * rows too large for 32-bit row indices");
     r.kchunks = sh.kch; r.kchunks2 = sh.kch2; r.nslot = sh.nslot; r.slot_bytes = sh.slot_bytes;
     r.kch_a = sh.kch_a; r.kch2_a = sh.kch2_a;
     if (d.gn_gamma) {
@@ -103,7 +125,12 @@ static int try_prepare_rowconv(TcOp& op, const ConvDesc& d) {
         if (d.C2b) { if (int e = make_act_tmap(&op.tmA2b, d.x2b, d.C2b, d.x2b_pitch, d.Wout, d.Hout, d.B, BK, 128, 1, 1)) return e; }
     }
     if (int e = make_b_tmap(&op.tmB, d.w, Ktot, Ktot, d.N_pad, 1, 0, BK, BN)) return e;
-    op.flops = 2.0 * d.B * d.Hout * d.Wout * (double)d.n_valid * (double)Ktot;
+    op.tmO = op.tmA;
+    if (r.tma_store) {
+        PNPF_REQUIRE(d.out_img_stride == (long long)d.Hout * d.Wout * d.out_row_stride, "row conv: TMA store needs a dense NHWC output");
+        if (int e = make_act_tmap(&op.tmO, d.out, d.n_valid, d.out_row_stride, d.Wout, d.Hout, d.B, 32, 128, 1, 1)) return e;
+    }
+    op.flops = 2.0 * d.B * d.Hout * d.Wout * (double)d.n_valid * (double)(Ktot - (d.x2_identity ? d.C2 : 0));
     return 0;
 }
 
@@ -207,17 +234,21 @@ template <int BK, int BN, int KCH>
 static int launch_row_t(const TcOp& op, cudaStream_t stream) {
     using Cfg = RowCfg<BK, BN>;
     const RowConvParams& r = op.rp;
-    const int smem = 3 * r.kchunks * Cfg::W_STACK + r.kchunks2 * Cfg::W_TILE + r.nslot * r.slot_bytes + Cfg::BAR_BYTES + 1024;
+    const int smem = 3 * r.kchunks * Cfg::W_STACK + r.kchunks2 * Cfg::W_TILE + r.nslot * r.slot_bytes + (r.tma_store ? Cfg::STAGE_BYTES : 0) +
+                     Cfg::BAR_BYTES + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         PNPF_CHECK_CUDA(cudaFuncSetAttribute(rowconv_kernel<BK, BN, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowconv_max_smem()));
         attr_set = true;
     }
     PNPF_REQUIRE(smem <= rowconv_max_smem(), "row conv shared memory %d exceeds the budget", smem);
-    const long long items = (long long)r.n_img * r.segs * r.strips;
-    const int grid = (int)(items < num_sms() ? items : num_sms());
+    // one CTA group (nsplit CTAs) per contiguous range of the flattened row space; at least 8 rows per range
+    const long long rows = (long long)r.n_img * r.strips * r.H;
+    long long groups = num_sms() / r.nsplit;
+    if (groups > (rows + 7) / 8) groups = (rows + 7) / 8;
+    const int grid = (int)groups * r.nsplit;
     if (grid < 1) return 0;
-    rowconv_kernel<BK, BN, KCH><<<grid, Cfg::THREADS, smem, stream>>>(op.tmA, op.tmAb, op.tmA2, op.tmA2b, op.tmB, r);
+    rowconv_kernel<BK, BN, KCH><<<grid, Cfg::THREADS, smem, stream>>>(op.tmA, op.tmAb, op.tmA2, op.tmA2b, op.tmB, op.tmO, r);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

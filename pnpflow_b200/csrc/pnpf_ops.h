@@ -10,6 +10,7 @@ typedef __nv_bfloat16 bf16;
 // ------------------------------------------------------------------ tensor-core ops
 struct TcOp {               // a prepared conv_gemm launch
     CUtensorMap tmA, tmAb, tmA2, tmA2b, tmB;   // *b: second source of a channel concat (row conv only)
+    CUtensorMap tmO;                            // output map of the row conv's TMA-store epilogue
     GemmParams p;
     RowConvParams rp;       // kind == 1: row-streaming conv (pnpf_rowconv.cuh)
     int kind = 0;           // 0: conv_gemm_kernel, 1: rowconv_kernel
@@ -27,6 +28,7 @@ struct ConvDesc {
     const bf16* x2 = nullptr;
     int C2 = 0;
     long long x2_pitch = 0;
+    int x2_identity = 0;            // the fused 1x1 is the identity (residual add done by the tensor core): not counted as FLOPs
     // weights: packed bf16 [N_pad][Ktot], Ktot = ksize*ksize*Cin + C2 (pack_conv_weight)
     const bf16* w = nullptr;
     int N_pad = 0;
@@ -63,6 +65,7 @@ struct ConvDesc {
 int prepare_conv(TcOp& op, const ConvDesc& d);
 bool rowconv_eligible(const ConvDesc& d);     // would prepare_conv pick the row-streaming kernel?
 int rowconv_max_smem();
+void describe_conv_impl(const ConvDesc& d, char* buf, size_t n);   // which kernel prepare_conv would pick (PNPF_PLAN_DUMP)
 
 struct GemmDesc {           // out[b][m][n] = sum_k A[b|0][m][k] * Bm[b|0][n][k]  (+bias[n]) (+residual)
     const bf16* A = nullptr;

@@ -15,20 +15,21 @@
 //   * every MMA accumulates (the epilogue re-zeroes an accumulator block with tcgen05.st after draining it), which
 //     removes all per-instruction special cases; descriptor words live in registers, the tap loops are fully unrolled
 //     (template KCH = channel chunks) and only add immediates;
-//   * waits are issued by one lane per warp; 8 epilogue warps (alternate rows for C_out <= 32, split columns for 64);
+//   * waits are issued by one lane per warp; one epilogue warp set per 32 output columns, the other worker warps transform;
 //   * bias (+ the per-image time-embedding row) is staged in shared memory once per work item;
 //   * GroupNorm statistics of the OUTPUT tensor are accumulated per thread across the rows of an item and reduced with
 //     warp shuffles + one fp64 atomic per lane per item.
 #pragma once
 #include "pnpf_gemm.cuh"
 #include <cuda_fp16.h>
+#include <type_traits>
 
 namespace pnpf {
 
 struct RowConvParams {
     int H, W, n_img;
     int strips;            // W / 128
-    int seg_rows, segs;    // rows per work item, ceil(H / seg_rows)
+    int nsplit;            // 1, or 2: CTAs 2g / 2g+1 compute output channels [0,BN) / [BN,2BN) of the same rows (C_out = 2*BN)
     int kchunks;           // Cin / BK (== template KCH)
     int kchunks2;          // C2 / BK of the fused 1x1 source (0 = none)
     int nslot;             // depth of the input-row ring
@@ -45,7 +46,8 @@ struct RowConvParams {
     const float* gn_beta;
     const double* gn_st_a; // [img][Ca][2]
     const double* gn_st_b; // [img][Cb][2]
-    long long* dbg;        // optional [16] cycle counters of CTA 0 (profiling experiments), else nullptr
+    int tma_store;         // bf16 NHWC output through the staging tiles + TMA store (tmO); else per-thread global stores
+    long long* dbg;        // optional [32] cycle counters of CTA 0 (profiling experiments), else nullptr
     EpiParams epi;
 };
 
@@ -63,30 +65,22 @@ struct RowCfg {
     static constexpr int NACC = (512 / BN) > 16 ? 16 : (512 / BN);
     static constexpr int TMEM_COLS = NACC * BN;              // 256 (BN=16) or 512
     static constexpr int MAX_SLOTS = 8;
-    // 12 worker warps besides the producer and the MMA issuer: 8 epilogue + 4 GroupNorm-transform warps.  The epilogue is
-    // a per-warp latency chain (wait, tcgen05.ld, tcgen05.st, arrive), so two warp sets on alternate rows beat one set
-    // even for thin outputs (same-box A/B in profiles/r01_ab_experiments.md).
-    static constexpr int NEW = 8;                            // epilogue warps: two sets of 4
-    static constexpr bool ROW_SPLIT = BN <= 32;              // the two sets alternate rows (C_out <= 32) or split the columns (64)
+    // 12 worker warps besides the producer and the MMA issuer.  The GroupNorm transform (one MUFU + ~7 issue slots per
+    // element, 130 * C_in elements per row) is the heaviest stage, so thin outputs (BN <= 32: one epilogue warp set drains a
+    // whole row) give it eight warps; C_out = 64 keeps two epilogue sets that split the columns.
+    static constexpr int NEW = BN <= 32 ? 4 : 8;             // epilogue warps (sets of 4: one per TMEM lane quarter)
+    static constexpr int NSETS = NEW / 4;
     static constexpr int NTW = 12 - NEW;                     // transform warps
+    // bf16 NHWC outputs leave through shared memory: each epilogue set packs its 128 pixels x 32 channels into a 64B-swizzled
+    // staging tile and one thread issues a TMA store (coalesced 64-byte pixel rows instead of 16-byte stores at a 64/128-byte
+    // stride, which cost one L1 wavefront per lane).  Two tiles per set: the store of row r overlaps the packing of row r+1.
+    static constexpr int STAGE_TILE = 128 * 64;
+    static constexpr int STAGE_BYTES = BN >= 32 ? NSETS * 2 * STAGE_TILE : 0;
     static constexpr int THREADS = 64 + 12 * 32;
     static constexpr int CPT = BN > 32 ? 32 : BN;            // columns per epilogue thread
     static constexpr int BAR_BYTES = 2048;                   // barriers + tmem slot | bias staging (2 x 64 floats) | GN scale/shift (2 x 128)
     static_assert(BN == 16 || BN == 32 || BN == 64, "row conv is for thin outputs");
 };
-
-// cycle counters of CTA 0 (tools/rowconv_dbg.py): compiled in only with -DPNPF_ROWCONV_CLOCKS
-#ifdef PNPF_ROWCONV_CLOCKS
-#define PNPF_CLK() clock64()
-#else
-#define PNPF_CLK() 0ll
-#endif
-#define PNPF_TIMED_WAIT(bar, par, ctr)        \
-    do {                                      \
-        const long long _t0 = PNPF_CLK();      \
-        mbar_wait(bar, par);                  \
-        ctr += PNPF_CLK() - _t0;               \
-    } while (0)
 
 // tcgen05.mma, always accumulating, descriptors given as (low word, shared high word)
 __device__ __forceinline__ void umma_acc_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
@@ -114,6 +108,14 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // one lane polls, the warp follows
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
     if (lane == 0) mbar_wait(bar, parity);
@@ -124,7 +126,8 @@ template <int BK, int BN, int KCH>
 __global__ void __launch_bounds__(RowCfg<BK, BN>::THREADS, 1)
 rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAb,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA2b,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ RowConvParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+               const __grid_constant__ RowConvParams p) {
     using Cfg = RowCfg<BK, BN>;
     constexpr int NACC = Cfg::NACC;
     constexpr int CPT = Cfg::CPT;
@@ -133,7 +136,8 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* wsm = smem;                                  // [kw][chunk] stacked tiles, then the shortcut tiles
     const int w_bytes = 3 * KCH * Cfg::W_STACK + p.kchunks2 * Cfg::W_TILE;
     uint8_t* slots = smem + w_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(slots + p.nslot * p.slot_bytes);
+    uint8_t* stage = slots + p.nslot * p.slot_bytes;                // [set][2] output staging tiles (TMA store)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage + (p.tma_store ? Cfg::STAGE_BYTES : 0));
     uint64_t* wbar = bars;
     uint64_t* full_bar = bars + 1;
     uint64_t* empty_bar = full_bar + Cfg::MAX_SLOTS;
@@ -146,7 +150,6 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int items = p.n_img * p.segs * p.strips;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -154,6 +157,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.kchunks2) tma_prefetch_desc(&tmA2);
         if (p.kch_a < KCH) tma_prefetch_desc(&tmAb);
         if (p.kch2_a < p.kchunks2) tma_prefetch_desc(&tmA2b);
+        if (p.tma_store) tma_prefetch_desc(&tmO);
         mbar_init(wbar, 1);
         for (int s = 0; s < Cfg::MAX_SLOTS; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -162,7 +166,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 16; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], Cfg::ROW_SPLIT ? 4 : Cfg::NEW);
+            mbar_init(&tempty_bar[a], Cfg::NEW);
         }
         fence_barrier_init();
     }
@@ -180,14 +184,20 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
 
-    auto decode = [&](int it, int& img, int& hb, int& he, int& w0) {
-        const int strip = it % p.strips;
-        int r = it / p.strips;
-        const int seg = r % p.segs;
-        img = r / p.segs;
-        hb = seg * p.seg_rows;
-        he = min(hb + p.seg_rows, p.H);
-        w0 = strip * 128;
+    // Work distribution: the rows of all (image, strip) columns form one flattened row space of R = n_img * strips * H
+    // rows; CTA group g of G owns the contiguous range [g*R/G, (g+1)*R/G) and walks it as (image, strip, [hb, he))
+    // pieces, so every CTA streams the same number of rows (+-1) and pays the two halo rows once per piece.
+    const int n_groups = gridDim.x / p.nsplit;
+    const int grp = blockIdx.x / p.nsplit;
+    const int n_off = (blockIdx.x - grp * p.nsplit) * BN;          // first output channel of this CTA
+    const long long R_total = static_cast<long long>(p.n_img) * p.strips * p.H;         // < 2^31 (checked by the host)
+    const int row_begin = static_cast<int>(R_total * grp / n_groups), row_end = static_cast<int>(R_total * (grp + 1) / n_groups);
+    auto decode = [&](int row, int& img, int& hb, int& he, int& w0) {
+        const int is = row / p.H;
+        hb = row - is * p.H;
+        he = min(p.H, hb + (row_end - row));
+        img = is / p.strips;
+        w0 = (is - img * p.strips) * 128;
     };
 
     if (warp == 0) {
@@ -202,18 +212,19 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int c = 0; c < KCH; ++c)
                         for (int kh = 0; kh < 3; ++kh)      // packed K order is (kh, kw, cin): see pack_conv_weight
                             tma_load_3d(wsm + (kw * KCH + c) * Cfg::W_STACK + kh * Cfg::KH_BYTES, &tmB, wbar,
-                                        ((kh * 3 + kw) * KCH + c) * BK, 0, 0);
+                                        ((kh * 3 + kw) * KCH + c) * BK, n_off, 0);
                 for (int c = 0; c < p.kchunks2; ++c)
-                    tma_load_3d(wsm + 3 * KCH * Cfg::W_STACK + c * Cfg::W_TILE, &tmB, wbar, (9 * KCH + c) * BK, 0, 0);
+                    tma_load_3d(wsm + 3 * KCH * Cfg::W_STACK + c * Cfg::W_TILE, &tmB, wbar, (9 * KCH + c) * BK, n_off, 0);
             }
             __syncwarp();
             int slot = 0;
             uint32_t phase = 0;
             long long c_wait = 0, c_rows = 0;
             const long long c_start = PNPF_CLK();
-            for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            for (int row = row_begin; row < row_end;) {
                 int img, hb, he, w0;
-                decode(it, img, hb, he, w0);
+                decode(row, img, hb, he, w0);
+                row += he - hb;
                 const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
                 for (int j = j0; j <= j1; ++j) {
                     PNPF_TIMED_WAIT(&empty_bar[slot], phase ^ 1, c_wait);
@@ -256,11 +267,12 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t kch2 = p.kchunks2;
             uint32_t slot = 0, phase = 0;
             uint32_t g0 = 0;                           // running output-row counter (selects the accumulator)
-            long long c_full = 0, c_tempty = 0;
+            long long c_full = 0, c_tempty = 0, c_issue = 0, c_commit = 0;
             const long long c_start = PNPF_CLK();
-            for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            for (int row = row_begin; row < row_end;) {
                 int img, hb, he, w0;
-                decode(it, img, hb, he, w0);
+                decode(row, img, hb, he, w0);
+                row += he - hb;
                 const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
                 for (int j = j0; j <= j1; ++j) {
                     // taps kh = 0,1,2 feed output rows j+1, j, j-1; the valid ones are contiguous in kh
@@ -281,6 +293,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc_fence_after();
                     PNPF_TIMED_WAIT(p.gn ? &ready_bar[slot] : &full_bar[slot], phase, c_full);
                     tc_fence_after();
+                    const long long c_i0 = PNPF_CLK();
                     const uint32_t s_lo0 = s_base_lo + slot * slot16;
                     const uint32_t d0 = tmem_base + blk0 * BN, d1 = tmem_base;
                     const uint32_t i0 = n0 == 3 ? idesc3 : (n0 == 2 ? idesc2 : idesc1);
@@ -313,16 +326,19 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 w2 += WT16;
                             }
                         }
+                        const long long c_i1 = PNPF_CLK();
+                        c_issue += c_i1 - c_i0;
                         umma_commit(&empty_bar[slot]);     // the row slot can be refilled once these MMAs retire
                         if (j - 1 >= hb && j - 1 < he) umma_commit(&tfull_bar[(g0 + static_cast<uint32_t>(j - 1 - hb)) % NACC]);
                         if (j == p.H - 1 && j >= hb && j < he) umma_commit(&tfull_bar[(g0 + static_cast<uint32_t>(j - hb)) % NACC]);
+                        c_commit += PNPF_CLK() - c_i1;
                     }
                     __syncwarp();
                     if (++slot == static_cast<uint32_t>(p.nslot)) { slot = 0; phase ^= 1; }
                 }
                 g0 += static_cast<uint32_t>(he - hb);
             }
-            if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[4] = PNPF_CLK() - c_start; p.dbg[5] = c_full; p.dbg[6] = c_tempty; }
+            if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[4] = PNPF_CLK() - c_start; p.dbg[5] = c_full; p.dbg[6] = c_tempty; p.dbg[16] = c_issue; p.dbg[17] = c_commit; }
         }
         __syncwarp();
     } else if (warp >= 2 + Cfg::NEW) {
@@ -333,11 +349,12 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int Ctot = p.gn_Ca + p.gn_Cb;
             int slot = 0;
             uint32_t phase = 0;
-            long long c_twait = 0, c_tab = 0;
+            long long c_twait = 0, c_tab = 0, c_fence = 0;
             const long long c_tstart = PNPF_CLK();
-            for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            for (int row = row_begin; row < row_end;) {
                 int img, hb, he, w0;
-                decode(it, img, hb, he, w0);
+                decode(row, img, hb, he, w0);
+                row += he - hb;
                 const long long c_t0 = PNPF_CLK();
                 // per-image scale / shift of every input channel (a group may straddle the two concatenated sources)
                 asm volatile("bar.sync 3, %0;" ::"n"(NTT));
@@ -368,95 +385,114 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 constexpr int RPI = NTT / CPR;                     // rows per iteration (16..64, always a multiple of 8)
                 const int q = tt % CPR, row0 = tt / CPR;
                 const int sw = (Cfg::kRowBytes == 128) ? (row0 & 7) : ((row0 >> 1) & 3);
+                // silu(y) = h + h * tanh(h) with h = y / 2: the 1/2 is folded into scale / shift
+                const float fold = p.gn_silu ? 0.5f : 1.f;
                 float tsc[KCH][8], tsh[KCH][8];
 #pragma unroll
                 for (int c = 0; c < KCH; ++c)
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const int ch = c * BK + ((q ^ sw) << 3) + e;
-                        tsc[c][e] = gn_tab[ch];
-                        tsh[c][e] = gn_tab[128 + ch];
+                        tsc[c][e] = fold * gn_tab[ch];
+                        tsh[c][e] = fold * gn_tab[128 + ch];
                     }
                 const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
                 c_tab += PNPF_CLK() - c_t0;
+                // One halo tile: all of a thread's 16-byte chunks are loaded first (independent ld.shared in flight), transformed
+                // as ONE straight-line block (the activation is a compile-time branch, invalid rows are computed and discarded,
+                // so the scheduler interleaves the dependent chains of all chunks) and stored with a predicate.
+                constexpr int NIT = (Cfg::HALO_ROWS + RPI - 1) / RPI;
+                auto transform_tile = [&](auto silu_tag, uint32_t sbase, int c) {
+                    constexpr bool kSilu = decltype(silu_tag)::value;
+                    uint4 u[NIT];
+                    bool ok[NIT];
+#pragma unroll
+                    for (int k = 0; k < NIT; ++k) {
+                        const int r = row0 + k * RPI;
+                        const int wpix = w0 - 1 + r;
+                        ok[k] = (r < Cfg::HALO_ROWS) && (wpix >= 0) && (wpix < p.W);       // conv zero padding stays zero
+                        u[k] = make_uint4(0u, 0u, 0u, 0u);
+                        if (r < Cfg::HALO_ROWS) u[k] = lds128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes);
+                    }
+#pragma unroll
+                    for (int k = 0; k < NIT; ++k) {
+                        uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+                        for (int e2 = 0; e2 < 4; ++e2) {
+                            float y0 = fmaf(__uint_as_float(wds[e2] << 16), tsc[c][2 * e2], tsh[c][2 * e2]);
+                            float y1 = fmaf(__uint_as_float(wds[e2] & 0xFFFF0000u), tsc[c][2 * e2 + 1], tsh[c][2 * e2 + 1]);
+                            if constexpr (kSilu) {
+                                // fp16 tanh (3 more mantissa bits than the bf16 result: the output rounding dominates the error)
+                                const __half2 hh = __floats2half2_rn(y0, y1);
+                                uint32_t hb2 = *reinterpret_cast<const uint32_t*>(&hh), tb;
+                                asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(hb2));
+                                const __half2 th = *reinterpret_cast<const __half2*>(&tb);
+                                const float2 o = __half22float2(__hfma2(hh, th, hh));
+                                y0 = o.x;
+                                y1 = o.y;
+                            }
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
+                            wds[e2] = *reinterpret_cast<uint32_t*>(&b2);
+                        }
+                        u[k] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < NIT; ++k)
+                        if (ok[k]) sts128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes, u[k]);
+                };
                 for (int j = j0; j <= j1; ++j) {
                     {
                         const long long _t0 = PNPF_CLK();
                         mbar_wait_warp(&full_bar[slot], phase, lane);
                         c_twait += PNPF_CLK() - _t0;
                     }
-                    // all of a thread's rows of one tile are loaded first (explicit ld.shared: independent 16-byte loads in
-                    // flight), then transformed, then stored — the per-warp latency chain is paid once per tile, not per row
-                    constexpr int NIT = (Cfg::HALO_ROWS + RPI - 1) / RPI;            // 5 (64-byte rows) or 9 (128-byte rows)
                     const uint32_t sbase = smem_u32(slots) + slot * p.slot_bytes + row0 * Cfg::kRowBytes + q * 16;
+                    if (p.gn_silu) {
 #pragma unroll
-                    for (int c = 0; c < KCH; ++c) {
-                        uint4 u[NIT];
-                        bool ok[NIT];
+                        for (int c = 0; c < KCH; ++c) transform_tile(std::true_type{}, sbase, c);
+                    } else {
 #pragma unroll
-                        for (int k = 0; k < NIT; ++k) {
-                            const int r = row0 + k * RPI;
-                            const int wpix = w0 - 1 + r;
-                            ok[k] = (r < Cfg::HALO_ROWS) && (wpix >= 0) && (wpix < p.W);   // conv zero padding stays zero
-                            if (ok[k]) u[k] = lds128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes);
-                        }
-#pragma unroll
-                        for (int k = 0; k < NIT; ++k) {
-                            if (!ok[k]) continue;
-                            uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-#pragma unroll
-                            for (int e2 = 0; e2 < 4; ++e2) {
-                                float y0 = fmaf(__uint_as_float(wds[e2] << 16), tsc[c][2 * e2], tsh[c][2 * e2]);
-                                float y1 = fmaf(__uint_as_float(wds[e2] & 0xFFFF0000u), tsc[c][2 * e2 + 1], tsh[c][2 * e2 + 1]);
-                                if (p.gn_silu) {                       // silu(y) = h + h * tanh(h), h = y / 2
-                                    // packed fp16 tanh: ONE MUFU op per two elements (the SFU is this stage's bottleneck); fp16 keeps
-                                    // 3 more mantissa bits than the bf16 result, so the rounding of the output dominates the error
-                                    const __half2 hh = __floats2half2_rn(0.5f * y0, 0.5f * y1);
-                                    uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh), tb;
-                                    asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(hb));
-                                    const __half2 th = *reinterpret_cast<const __half2*>(&tb);
-                                    const float2 o = __half22float2(__hfma2(hh, th, hh));
-                                    y0 = o.x;
-                                    y1 = o.y;
-                                }
-                                __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
-                                wds[e2] = *reinterpret_cast<uint32_t*>(&b2);
-                            }
-                            sts128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes, make_uint4(wds[0], wds[1], wds[2], wds[3]));
-                        }
+                        for (int c = 0; c < KCH; ++c) transform_tile(std::false_type{}, sbase, c);
                     }
+                    const long long c_x0 = PNPF_CLK();
                     fence_proxy_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&ready_bar[slot]);
+                    c_fence += PNPF_CLK() - c_x0;
                     if (++slot == p.nslot) { slot = 0; phase ^= 1; }
                 }
             }
-            if (p.dbg && blockIdx.x == 0 && tt == 0) { p.dbg[3] = PNPF_CLK() - c_tstart; p.dbg[7] = c_twait; p.dbg[11] = c_tab; }
+            if (p.dbg && blockIdx.x == 0 && tt == 0) { p.dbg[3] = PNPF_CLK() - c_tstart; p.dbg[7] = c_twait; p.dbg[11] = c_tab; p.dbg[21] = c_fence; }
         }
     } else {
-        // ===================== epilogue: warps 2..5 = set 0 (and warps 6..9 = set 1 for C_out = 64) =====================
+        // ===================== epilogue: warps 2..5 = set 0 (and warps 6..9 = set 1, columns 32..63, for C_out = 64) =====================
         const int set = (warp - 2) >> 2;
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int m = quarter * 32 + lane;            // pixel within the strip
         const int ethread = threadIdx.x - 64;         // 0..255
-        const int colbase = Cfg::ROW_SPLIT ? 0 : set * 32;   // column split: set 1 takes columns 32..63 of C_out = 64
+        const int colbase = set * 32;                 // column split: set 1 takes columns 32..63 of C_out = 64
         float* bsm = bias_sm + set * 64;
         const uint32_t set_bar = 1 + set;             // named barrier id of this warp set (128 threads)
+        const bool leader = (ethread & 127) == 0;     // issues this set's TMA stores
+        const uint32_t stage_lo = smem_u32(stage) + set * 2 * Cfg::STAGE_TILE + m * 64;   // this pixel's 64-byte row in tile 0
+        const uint32_t stage_sw = static_cast<uint32_t>((m >> 1) & 3);                     // SWIZZLE_64B: chunk ^= (row >> 1) & 3
+        uint32_t stage_sel = 0;
         uint32_t g0 = 0;
-        long long c_tfull = 0, c_rows = 0;
+        long long c_tfull = 0, c_rows = 0, c_ld = 0, c_st = 0, c_fin = 0;
         const long long c_start = PNPF_CLK();
-        for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        for (int row = row_begin; row < row_end;) {
             int img, hb, he, w0;
-            decode(it, img, hb, he, w0);
+            decode(row, img, hb, he, w0);
+            row += he - hb;
             // stage bias (+ per-image time-embedding row) of this item once
             asm volatile("bar.sync %0, 128;" ::"r"(set_bar));          // previous item's readers are done
             {
                 const int c = (ethread & 127);
                 if (c < BN) {
                     float b = 0.f;
-                    if (c < p.epi.n_valid) {
-                        if (p.epi.bias) b += __ldg(p.epi.bias + c);
-                        if (p.epi.bias_img) b += __ldg(p.epi.bias_img + img * p.epi.bias_img_stride + c);
+                    if (n_off + c < p.epi.n_valid) {
+                        if (p.epi.bias) b += __ldg(p.epi.bias + n_off + c);
+                        if (p.epi.bias_img) b += __ldg(p.epi.bias_img + img * p.epi.bias_img_stride + n_off + c);
                     }
                     bsm[c] = b;
                 }
@@ -465,7 +501,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float ssum[CPT], ssq[CPT];
 #pragma unroll
             for (int q = 0; q < CPT; ++q) ssum[q] = ssq[q] = 0.f;
-            for (int r = hb + (Cfg::ROW_SPLIT ? set : 0); r < he; r += (Cfg::ROW_SPLIT ? 2 : 1)) {
+            for (int r = hb; r < he; ++r) {
                 const uint32_t g = g0 + static_cast<uint32_t>(r - hb);
                 const uint32_t acc = g % NACC;
                 const long long pix = static_cast<long long>(r) * p.W + w0 + m;
@@ -476,21 +512,27 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 ++c_rows;
                 tc_fence_after();
+                const long long c_e0 = PNPF_CLK();
                 const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ((NACC - 1) - acc) * BN + colbase;
                 uint32_t rr[CPT / 16][16];
 #pragma unroll
                 for (int q = 0; q < CPT / 16; ++q) tmem_ld_x16(t_addr + q * 16, rr[q]);
                 tmem_ld_wait();
+                const long long c_e1 = PNPF_CLK();
 #pragma unroll
                 for (int q = 0; q < CPT / 16; ++q) tmem_zero_x16(t_addr + q * 16);   // re-arm: every MMA accumulates
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);          // accumulator is in registers: release it early
+                const long long c_e2 = PNPF_CLK();
+                c_ld += c_e1 - c_e0;
+                c_st += c_e2 - c_e1;
 #pragma unroll
                 for (int q = 0; q < CPT / 16; ++q) {
-                    const int col0 = colbase + q * 16;
-                    if (col0 >= p.epi.n_valid) continue;
+                    const int col0 = colbase + q * 16;              // column within this CTA's BN block
+                    const int gcol0 = n_off + col0;                  // output channel
+                    if (gcol0 >= p.epi.n_valid) continue;
                     float v[16];
 #pragma unroll
                     for (int jj = 0; jj < 16; jj += 4) {
@@ -502,7 +544,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (p.epi.residual) {
                         // (prefetching these loads ahead of the accumulator wait was measured 4 % SLOWER: profiles/r01_ab_experiments.md)
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.epi.residual + img * p.epi.res_img_stride + pix * p.epi.res_row_stride + col0);
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.epi.residual + img * p.epi.res_img_stride + pix * p.epi.res_row_stride + gcol0);
 #pragma unroll
                         for (int h2 = 0; h2 < 2; ++h2) {
                             const uint4 u = __ldg(rp + h2);
@@ -521,13 +563,40 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             ssq[q * 16 + jj] = fmaf(v[jj], v[jj], ssq[q * 16 + jj]);
                         }
                     }
-                    epilogue_store16(p.epi, img, pix, col0, v);
+                    if constexpr (CPT == 32) {
+                        if (p.tma_store) {                             // pack to bf16 into this pixel's swizzled staging row
+                            uint32_t pk[8];
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) {
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * jj], v[2 * jj + 1]);
+                                pk[jj] = *reinterpret_cast<uint32_t*>(&b2);
+                            }
+                            const uint32_t base = stage_lo + stage_sel * Cfg::STAGE_TILE;
+                            sts128(base + (((2 * q) ^ stage_sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                            sts128(base + (((2 * q + 1) ^ stage_sw) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+                            continue;
+                        }
+                    }
+                    epilogue_store16(p.epi, img, pix, gcol0, v);
+                }
+                if constexpr (CPT == 32) {
+                    if (p.tma_store) {
+                        fence_proxy_async_smem();                      // staging writes -> visible to the TMA unit
+                        if (leader) bulk_wait_read0();                 // the previous row's store (other tile) has left shared memory
+                        asm volatile("bar.sync %0, 128;" ::"r"(set_bar));
+                        if (leader) {
+                            tma_store_4d(&tmO, stage + (set * 2 + stage_sel) * Cfg::STAGE_TILE, n_off + colbase, w0, r, img);
+                            bulk_commit();
+                        }
+                        stage_sel ^= 1;
+                    }
                 }
             }
+            const long long c_f0 = PNPF_CLK();
             if (p.epi.stats) {
 #pragma unroll
                 for (int q = 0; q < CPT / 16; ++q) {
-                    const int col0 = colbase + q * 16;
+                    const int col0 = n_off + colbase + q * 16;
                     // butterfly over the 32 lanes (= 32 pixels): afterwards even lanes hold a channel sum, odd lanes a sum of squares
                     float s[16], qq[16];
 #pragma unroll
@@ -554,7 +623,10 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             g0 += static_cast<uint32_t>(he - hb);
+            c_fin += PNPF_CLK() - c_f0;
         }
+        if (p.tma_store && leader) bulk_wait0();       // all output rows are in global memory before the CTA retires
+        if (p.dbg && blockIdx.x == 0 && ethread == 0) { p.dbg[18] = c_ld; p.dbg[19] = c_st; p.dbg[20] = c_fin; }
         if (p.dbg && blockIdx.x == 0 && ethread == 0) { p.dbg[8] = PNPF_CLK() - c_start; p.dbg[9] = c_tfull; p.dbg[10] = c_rows; }
         if (p.dbg && blockIdx.x == 0 && ethread == 128 && Cfg::NEW == 8) { p.dbg[12] = PNPF_CLK() - c_start; p.dbg[13] = c_tfull; p.dbg[14] = c_rows; }
     }

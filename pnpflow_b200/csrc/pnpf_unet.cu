@@ -5,6 +5,7 @@
 #include "pnpf_ops.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -213,6 +214,15 @@ static int build_layers(pnpf_engine* e) {
     return 0;
 }
 
+// Residual blocks without a shortcut conv on the row-streaming levels add their input through the tensor core: conv2's
+// packed weights get an identity 1x1 block appended (exact: bf16 x 1.0 accumulated in fp32), so the residual rides the
+// kernel's TMA/MMA path instead of per-thread global loads in the epilogue.
+static bool identity_shortcut(const LayerSpec& L) {
+    static const bool off = getenv("PNPF_NO_IDENTITY") != nullptr;     // A/B switch (tools/ab_env.py)
+    if (off) return false;
+    return L.kind == LayerSpec::RES && L.in_ch == L.out_ch && L.skip_ch == 0 && L.side % 128 == 0 && L.out_ch % 32 == 0 && L.out_ch <= 64;
+}
+
 extern "C" int pnpf_create(const pnpf_unet_config* cfg, pnpf_engine** out) {
     PNPF_REQUIRE(cfg && out, "null argument");
     pnpf_engine* e = new pnpf_engine();
@@ -368,6 +378,12 @@ extern "C" int pnpf_finalize_weights(pnpf_engine* e) {
                 pack_conv_weight(d2, W(e, p + ".conv2.weight").data(), L.out_ch, L.out_ch, 3, np, L.out_ch,
                                  sc ? W(e, p + ".shortcut.weight").data() : nullptr, sc ? L.in_ch : 0, 1.f);
                 pack_bias(p + ".conv2.b", np, W(e, p + ".conv2.bias"), sc ? &W(e, p + ".shortcut.bias") : nullptr);
+                if (identity_shortcut(L)) {
+                    std::vector<float> eye((size_t)L.out_ch * L.out_ch, 0.f);
+                    for (int o = 0; o < L.out_ch; ++o) eye[(size_t)o * L.out_ch + o] = 1.f;
+                    bf16* d3 = pk.b16(p + ".conv2.wid", (size_t)np * (9 * L.out_ch + L.out_ch));
+                    pack_conv_weight(d3, W(e, p + ".conv2.weight").data(), L.out_ch, L.out_ch, 3, np, L.out_ch, eye.data(), L.out_ch, 1.f);
+                }
                 break;
             }
             case LayerSpec::ATTN: {
@@ -539,8 +555,13 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
         Op o;
         o.kind = Op::TC; o.name = name;
         d.B = Bm;
+        if (!real && getenv("PNPF_PLAN_DUMP")) {
+            char buf[160];
+            describe_conv_impl(d, buf, sizeof(buf));
+            fprintf(stderr, "plan: %-44s %4dx%-4d Cin=%-3d C2=%-3d N=%-3d %s\n", name.c_str(), d.Hout, d.Wout, d.Cin, d.C2, d.n_valid, buf);
+        }
         if (real) { if (int rc = prepare_conv(o.tc, d)) return rc; }
-        o.flops = 2.0 * d.Hout * d.Wout * (double)d.n_valid * ((double)d.ksize * d.ksize * d.Cin + (d.x2 ? d.C2 : 0));
+        o.flops = 2.0 * d.Hout * d.Wout * (double)d.n_valid * ((double)d.ksize * d.ksize * d.Cin + ((d.x2 && !d.x2_identity) ? d.C2 : 0));
         o.bytes = 2.0 * d.Hin * d.Win * d.Cin + (d.x2 ? 2.0 * d.Hout * d.Wout * d.C2 : 0.0) +   // Cin / C2 are concat totals
                   (d.residual ? 2.0 * d.Hout * d.Wout * d.n_valid : 0.0) +
                   (d.out_mode == 0 ? 2.0 : 4.0) * d.Hout * d.Wout * d.n_valid;
@@ -634,6 +655,13 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 } else {
                     PNPF_REQUIRE(!L.skip_ch, "internal: concat block without shortcut");
                     d2.residual = h.p; d2.res_img_stride = px * L.out_ch; d2.res_row_stride = L.out_ch;
+                    if (identity_shortcut(L)) {                    // residual as an identity 1x1 on the tensor core
+                        ConvDesc di = d2;
+                        di.residual = nullptr;
+                        di.x2 = h.p; di.x2_pitch = h.C; di.C2 = L.in_ch; di.x2_identity = 1;
+                        if (real) di.w = wptr<bf16>(e, p + ".conv2.wid");
+                        if (rowconv_eligible(di)) d2 = di;
+                    }
                 }
                 d2.stats_out = y.stats;
                 d2.out = y.p; d2.out_mode = 0; d2.out_img_stride = px * L.out_ch; d2.out_row_stride = L.out_ch; d2.n_valid = L.out_ch;

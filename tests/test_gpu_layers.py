@@ -65,17 +65,25 @@ def test_conv_stride2(B, H, W, Cin, Cout):
     (2, 128, 128, 32, 32, 0, False), (1, 256, 256, 32, 32, 0, True), (2, 40, 128, 64, 32, 0, False), (1, 128, 256, 96, 32, 0, False),
     (2, 128, 128, 64, 64, 0, True), (1, 64, 128, 32, 64, 32, False), (2, 128, 256, 32, 32, 96, False), (3, 33, 128, 32, 32, 64, False),
     (1, 128, 128, 32, 16, 0, False),
+    # output channels split over CTA pairs (weights of the full C_out do not fit next to the row ring)
+    (2, 128, 128, 128, 64, 0, False), (3, 50, 128, 128, 64, 0, True), (1, 64, 128, 64, 64, 128, False), (2, 37, 256, 64, 64, 96, False),
+    # many short ranges: more CTAs than 8-row pieces, pieces crossing image boundaries
+    (5, 9, 128, 32, 32, 0, True), (7, 3, 128, 64, 64, 64, False),
 ])
-def test_rowconv_wide_maps(B, H, W, Cin, Cout, C2, res):
-    """W % 128 == 0 and Cout <= 64 route to the row-streaming kernel (halo tile + row-shifted UMMA descriptors)."""
-    _conv_case(B, H, W, Cin, Cout, 3, 1, C2=C2, res=res, seed=H + W + Cin)
+@pytest.mark.parametrize("bf16out", [False, True])
+def test_rowconv_wide_maps(B, H, W, Cin, Cout, C2, res, bf16out):
+    """W % 128 == 0 and Cout <= 64 route to the row-streaming kernel (halo tile + row-shifted UMMA descriptors); bf16 NHWC
+    outputs leave through the staging tiles + TMA store, fp32 outputs through per-thread stores."""
+    _conv_case(B, H, W, Cin, Cout, 3, 1, C2=C2, res=res, bf16out=bf16out, seed=H + W + Cin)
 
 
 @pytest.mark.parametrize("B,H,W,Ca,Cb,Cout,silu", [
     (2, 64, 128, 32, 0, 32, 1), (1, 256, 256, 32, 0, 32, 1), (2, 40, 128, 64, 0, 32, 1), (2, 64, 128, 64, 32, 32, 1),
     (1, 128, 256, 32, 32, 32, 1), (2, 64, 128, 64, 0, 64, 1), (2, 33, 128, 32, 0, 16, 1), (1, 64, 128, 32, 0, 64, 0), (2, 64, 256, 64, 32, 32, 1),
+    (2, 64, 128, 64, 64, 64, 1), (3, 21, 128, 64, 32, 64, 1), (1, 128, 128, 128, 0, 64, 1),      # split output channels / 3 K chunks
 ])
-def test_rowconv_fused_groupnorm_two_sources(B, H, W, Ca, Cb, Cout, silu):
+@pytest.mark.parametrize("bf16out", [False, True])
+def test_rowconv_fused_groupnorm_two_sources(B, H, W, Ca, Cb, Cout, silu, bf16out):
     """conv3x3(act(GroupNorm(cat[xa|xb]))) with the normalisation done in shared memory inside the conv kernel."""
     lib, L = _lib()
     torch.backends.cudnn.allow_tf32 = False
@@ -95,14 +103,14 @@ def test_rowconv_fused_groupnorm_two_sources(B, H, W, Ca, Cb, Cout, silu):
     ref = F.conv2d(a.bfloat16().float(), w.to(dev), b.to(dev), padding=1)
     xan = xa.permute(0, 2, 3, 1).contiguous()
     xbn = xb.permute(0, 2, 3, 1).contiguous() if Cb else None
-    out = torch.full((B, H, W, Cout), float("nan"), device=dev)
+    out = torch.full((B, H, W, Cout), float("nan"), device=dev, dtype=torch.bfloat16 if bf16out else torch.float32)
     L.check(lib.pnpf_gn_conv2d_nhwc(xan.data_ptr(), Ca, xbn.data_ptr() if Cb else None, Cb, B, H, W, gamma.data_ptr(), beta.data_ptr(),
-                                    w.data_ptr(), b.data_ptr(), Cout, silu, out.data_ptr(), 1, None))
-    got = out.permute(0, 3, 1, 2)
+                                    w.data_ptr(), b.data_ptr(), Cout, silu, out.data_ptr(), 0 if bf16out else 1, None))
+    got = out.float().permute(0, 3, 1, 2)
     # the engine rounds the normalised activation to bf16 like the reference above; tanh.approx / rounding-boundary
     # flips give rare 1-ulp(bf16) operand differences -> compare in relative L2 and with a loose max
     rel = ((got - ref).norm() / ref.norm()).item()
-    assert rel < 3e-3, rel
+    assert rel < (5e-3 if bf16out else 3e-3), rel          # bf16 output rounding adds ~2^-9 relative
     assert (got - ref).abs().max().item() < 5e-2
 
 

@@ -38,7 +38,11 @@ def test_small3_matches_reference_golden():
     assert _rel(v, ref) < 3e-2, _rel(v, ref)
 
 
-@pytest.mark.parametrize("cfg,B", [(mg.SMALL3, 3), (oracle.UNetConfig(3, 64, 32, (1, 2, 4), 2, (16,)), 2)])
+@pytest.mark.parametrize("cfg,B", [(mg.SMALL3, 3), (oracle.UNetConfig(3, 64, 32, (1, 2, 4), 2, (16,)), 2),
+                                   # row-streaming levels: identity-shortcut residuals (32 ch at 128^2), fused GroupNorm, concat inputs
+                                   (oracle.UNetConfig(3, 128, 32, (1, 2), 2, ()), 2),
+                                   # 64 -> 128+64 channel up path at 128^2: output channels split over CTA pairs
+                                   (oracle.UNetConfig(3, 128, 64, (1, 2), 1, ()), 2)])
 def test_layerwise_taps_vs_oracle(cfg, B):
     """Every layer output the engine can expose (bf16 NHWC) against the oracle's fp32 activation."""
     from pnpflow_b200 import UNetEngine
