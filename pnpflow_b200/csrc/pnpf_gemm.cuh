@@ -148,11 +148,15 @@ struct GemmParams {
         ctr += PNPF_CLK() - _t0;               \
     } while (0)
 
-template <int BK, int BN>
+// PAIR: two CTAs of a cluster run one M = 256 tcgen05.mma (cta_group::2): each stages its own 128-pixel A tile and HALF of the
+// weight tile (BN/2 rows), which removes a quarter (BN = 128) to a third (BN = 256) of the shared-memory traffic per MMA — the
+// resource that bounds this kernel (an SS-mode MMA reads A and B from shared memory and the TMA writes both there first).
+template <int BK, int BN, bool PAIR = false>
 struct GemmCfg {
     static constexpr int kRowBytes = BK * 2;
     static constexpr int A_BYTES = 128 * BK * 2;
-    static constexpr int B_BYTES_RAW = BN * BK * 2;
+    static constexpr int B_ROWS = PAIR ? BN / 2 : BN;        // weight rows staged by this CTA
+    static constexpr int B_BYTES_RAW = B_ROWS * BK * 2;
     static constexpr int B_BYTES = (B_BYTES_RAW + 1023) / 1024 * 1024;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES_FIT = (196 * 1024) / STAGE_BYTES;
@@ -162,6 +166,7 @@ struct GemmCfg {
     static constexpr int THREADS = 192;
     static_assert(BK == 32 || BK == 64, "BK");
     static_assert(BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
+    static_assert(!PAIR || BN >= 128, "CTA pairs are used for the wide tiles only");
 };
 
 __device__ __forceinline__ void decode_tile(const GemmParams& p, int t, int& img, int& h0, int& w0, int& nt) {
@@ -175,11 +180,11 @@ __device__ __forceinline__ void decode_tile(const GemmParams& p, int t, int& img
     w0 = twi * p.TW;
 }
 
-template <int BK, int BN>
-__global__ void __launch_bounds__(GemmCfg<BK, BN>::THREADS, 1)
+template <int BK, int BN, bool PAIR>
+__global__ void __launch_bounds__(GemmCfg<BK, BN, PAIR>::THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
-    using Cfg = GemmCfg<BK, BN>;
+    using Cfg = GemmCfg<BK, BN, PAIR>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -191,9 +196,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int total_tiles = p.n_img * p.tiles_h * p.tiles_w * p.n_tiles_n;
     const int nk_main = p.ntaps * p.kchunks;
     const int nk = nk_main + p.kchunks2;
+    // Work units.  Single CTA: one (M tile, N tile) per unit.  Pair: the two CTAs take M tiles 2u and 2u+1 of the same N tile
+    // (the host only pairs when the M-tile count is even), the pair index strides over the units.
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int total_units = (p.n_img * p.tiles_h * p.tiles_w / (PAIR ? 2 : 1)) * p.n_tiles_n;
+    const int unit0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int unit_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    auto tile_of = [&](int u) {            // flat (M tile, N tile) index of this CTA's tile in unit u (decode_tile order)
+        if (!PAIR) return u;
+        const int nt = u % p.n_tiles_n, mp = u / p.n_tiles_n;
+        return (2 * mp + static_cast<int>(rank)) * p.n_tiles_n + nt;
+    };
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -205,13 +220,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 4);
+            mbar_init(&tempty_bar[a], PAIR ? 8 : 4);          // pair: the epilogue warps of BOTH CTAs release the leader's accumulator
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (warp == 2) {
+        if constexpr (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+        else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();                   // both CTAs' barriers exist before any remote arrive / TMA signal
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -222,9 +241,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t phase = 0;
             long long c_wait = 0, c_tiles = 0;
             const long long c_start = PNPF_CLK();
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int u = unit0; u < total_units; u += unit_step) {
                 int img, h0, w0, nt;
-                decode_tile(p, t, img, h0, w0, nt);
+                decode_tile(p, tile_of(u), img, h0, w0, nt);
                 const int ab = p.a_batched ? img : 0;
                 const int bb = p.b_batched ? img : 0;
                 ++c_tiles;
@@ -233,16 +252,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     if (elect_one_sync()) {
-                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES_RAW);
-                        if (i < nk_main) {
-                            const int tap = i / p.kchunks;
-                            const int ch = i - tap * p.kchunks;
-                            tma_load_4d(sa, &tmA, &full_bar[stage], p.c_base + ch * BK, w0 * p.in_stride + p.dw[tap],
-                                        h0 * p.in_stride + p.dh[tap], ab);
+                        if constexpr (PAIR) {
+                            // both CTAs' tiles complete the LEADER's barrier; only the leader arms it (with both byte counts)
+                            const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES_RAW));
+                            if (i < nk_main) {
+                                const int tap = i / p.kchunks;
+                                const int ch = i - tap * p.kchunks;
+                                tma_load_4d_pair(sa, &tmA, fb, p.c_base + ch * BK, w0 * p.in_stride + p.dw[tap], h0 * p.in_stride + p.dh[tap], ab);
+                            } else {
+                                tma_load_4d_pair(sa, &tmA2, fb, (i - nk_main) * BK, w0, h0, ab);
+                            }
+                            tma_load_3d_pair(sb, &tmB, fb, i * BK, nt * BN + static_cast<int>(rank) * Cfg::B_ROWS, bb);
                         } else {
-                            tma_load_4d(sa, &tmA2, &full_bar[stage], (i - nk_main) * BK, w0, h0, ab);
+                            mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES_RAW);
+                            if (i < nk_main) {
+                                const int tap = i / p.kchunks;
+                                const int ch = i - tap * p.kchunks;
+                                tma_load_4d(sa, &tmA, &full_bar[stage], p.c_base + ch * BK, w0 * p.in_stride + p.dw[tap],
+                                            h0 * p.in_stride + p.dh[tap], ab);
+                            } else {
+                                tma_load_4d(sa, &tmA2, &full_bar[stage], (i - nk_main) * BK, w0, h0, ab);
+                            }
+                            tma_load_3d(sb, &tmB, &full_bar[stage], i * BK, nt * BN, bb);
                         }
-                        tma_load_3d(sb, &tmB, &full_bar[stage], i * BK, nt * BN, bb);
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -252,16 +285,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer: converged warp, one ELECTED lane issues =====================
-        {
-            constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+        // ===================== MMA issuer: converged warp, one ELECTED lane issues (pair: the leader CTA only) =====================
+        if (!PAIR || rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             long long c_full = 0, c_tempty = 0;
             const long long c_start = PNPF_CLK();
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int u = unit0; u < total_units; u += unit_step) {
                 PNPF_TIMED_WAIT(&tempty_bar[acc], acc_phase ^ 1, c_tempty);      // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -275,10 +308,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int kk = 0; kk < BK / 16; ++kk) {
                             // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr>>4) field
-                            umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) ? 1u : 0u);
+                            if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) ? 1u : 0u);
+                            else umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) ? 1u : 0u);
                         }
-                        umma_commit(&empty_bar[stage]);           // frees the smem slot when these MMAs retire
-                        if (i == nk - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+                        if constexpr (PAIR) {
+                            umma_commit_pair(&empty_bar[stage]);  // frees this stage in BOTH CTAs
+                            if (i == nk - 1) umma_commit_pair(&tfull_bar[acc]);
+                        } else {
+                            umma_commit(&empty_bar[stage]);       // frees the smem slot when these MMAs retire
+                            if (i == nk - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+                        }
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -297,9 +336,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t acc_phase = 0;
         long long c_tfull = 0;
         const long long c_start = PNPF_CLK();
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const uint32_t tempty_remote = PAIR ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;      // the leader's tempty_bar[0]
+        for (int u = unit0; u < total_units; u += unit_step) {
             int img, h0, w0, nt;
-            decode_tile(p, t, img, h0, w0, nt);
+            decode_tile(p, tile_of(u), img, h0, w0, nt);
             const int h = h0 + th, w = w0 + tw;
             const bool valid = (h < p.H) && (w < p.W);
             const long long pix = static_cast<long long>(h) * p.W + w;
@@ -331,14 +371,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if constexpr (PAIR) mbar_arrive_cluster(tempty_remote + acc * 8);
+                else mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { p.dbg[8] = PNPF_CLK() - c_start; p.dbg[9] = c_tfull; }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (PAIR) {
+        cluster_sync_all();               // the peer's shared memory / TMEM and the leader's barriers stay alive until both are done
+        if (warp == 2) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    } else {
+        __syncthreads();
+        if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
 }
 
 }  // namespace pnpf

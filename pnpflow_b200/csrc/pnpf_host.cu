@@ -1,6 +1,8 @@
 // Host helpers: error string, tensor-map encoding, GEMM kernel dispatch.
 #include "pnpf_host.h"
 
+#include <cstdlib>
+
 #include <cudaTypedefs.h>
 #include <mutex>
 #include <vector>
@@ -86,30 +88,71 @@ int make_b_tmap(CUtensorMap* m, const void* base, long long K, long long ldk, in
     return encode(m, base, 3, dims, strides, box, estr, bk);
 }
 
-template <int BK, int BN>
+template <int BK, int BN, bool PAIR>
 static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const GemmParams& p,
                     cudaStream_t stream) {
-    using Cfg = GemmCfg<BK, BN>;
+    using Cfg = GemmCfg<BK, BN, PAIR>;
     static bool attr_set = false;
+    static int max_clusters = 0;
     if (!attr_set) {
-        PNPF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BK, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PNPF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BK, BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES));
+        if (PAIR) {                                       // how many CTA pairs (one per TPC) can be resident at once
+            cudaLaunchConfig_t qc = {};
+            qc.gridDim = dim3(num_sms() & ~1);
+            qc.blockDim = dim3(Cfg::THREADS);
+            qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa; qc.numAttrs = 1;
+            PNPF_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, conv_gemm_kernel<BK, BN, PAIR>, &qc));
+            PNPF_REQUIRE(max_clusters >= 1, "no CTA pair of conv_gemm_kernel<%d,%d> fits on this device", BK, BN);
+        }
         attr_set = true;
     }
     const long long tiles = (long long)p.n_img * p.tiles_h * p.tiles_w * p.n_tiles_n;
-    int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    if (grid < 1) return 0;
-    conv_gemm_kernel<BK, BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmB, p);
+    if (tiles < 1) return 0;
+    if (PAIR) {
+        const long long units = tiles / 2;
+        const int clusters = (int)(units < max_clusters ? units : max_clusters);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(Cfg::THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        PNPF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BK, BN, PAIR>, tmA, tmA2, tmB, p));
+        return 0;
+    }
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    conv_gemm_kernel<BK, BN, PAIR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmB, p);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_conv_gemm(int BK, int BN, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
+int launch_conv_gemm(int BK, int BN, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const CUtensorMap& tmB_half,
                      const GemmParams& p, cudaStream_t stream) {
     PNPF_REQUIRE(p.TH * p.TW == 128, "tile %dx%d is not 128 pixels", p.TH, p.TW);
     PNPF_REQUIRE(p.epi.out_mode == 2 || p.epi.n_valid % 16 == 0, "n_valid %d must be a multiple of 16 for row-major output", p.epi.n_valid);
+    // CTA pairs (cta_group::2, M = 256 per MMA) for the wide tiles whenever the M tiles pair up
+    static const bool no_pair = getenv("PNPF_NO_PAIR") != nullptr;          // A/B switch (tools/ab_env.py)
+    // (a pair shares ONE weight tile: with a per-image B operand both M tiles must belong to the same image)
+    const long long m_tiles = (long long)p.n_img * p.tiles_h * p.tiles_w;
+    const bool pairable = p.b_batched ? (p.tiles_h * p.tiles_w) % 2 == 0 : m_tiles % 2 == 0;
+    // Measured (profiles/r01_ab_experiments.md): with pairs the MMA issue runs at the tensor rate and the kernel becomes bound by
+    // the L2 -> shared-memory fill (every input pixel is fetched once per tap): BN = 256 gains 5-6 %, BN = 128 (activation
+    // traffic dominates, not halved by pairing) loses 4 % -> pairs for BN = 256 only (PNPF_PAIR_128=1 forces them for 128).
+    static const bool pair128 = getenv("PNPF_PAIR_128") != nullptr;
+    if (!no_pair && BK == 64 && pairable) {
+        if (BN == 128 && pair128) return launch_t<64, 128, true>(tmA, tmA2, tmB_half, p, stream);
+        if (BN == 256) return launch_t<64, 256, true>(tmA, tmA2, tmB_half, p, stream);
+    }
 #define PNPF_CASE(bk, bn) \
-    if (BK == bk && BN == bn) return launch_t<bk, bn>(tmA, tmA2, tmB, p, stream);
+    if (BK == bk && BN == bn) return launch_t<bk, bn, false>(tmA, tmA2, tmB, p, stream);
     PNPF_CASE(32, 16) PNPF_CASE(32, 32) PNPF_CASE(32, 64) PNPF_CASE(32, 128) PNPF_CASE(32, 256)
     PNPF_CASE(64, 16) PNPF_CASE(64, 32) PNPF_CASE(64, 64) PNPF_CASE(64, 128) PNPF_CASE(64, 256)
 #undef PNPF_CASE

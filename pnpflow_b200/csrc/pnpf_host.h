@@ -47,7 +47,7 @@ int make_b_tmap(CUtensorMap* m, const void* base, long long K, long long ldk, in
                 int bn);
 
 // ---- GEMM launch (dispatch on BK in {32,64} and BN in {16,32,64,128,256}) ----
-int launch_conv_gemm(int BK, int BN, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
+int launch_conv_gemm(int BK, int BN, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const CUtensorMap& tmB_half,
                      const GemmParams& p, cudaStream_t stream);
 
 // tile box for a W-wide feature map: TW = min(pow2ceil(W),128), TH = 128/TW

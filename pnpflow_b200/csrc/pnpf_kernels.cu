@@ -256,13 +256,13 @@ __global__ void temb_kernel(TembWeights w, const float* __restrict__ t, float* _
     __syncthreads();
     for (int o = threadIdx.x; o < w.temb_ch; o += blockDim.x) {
         float acc = w.b0[o];
-        for (int k = 0; k < w.ch; ++k) acc = fmaf(w.w0[o * w.ch + k], emb[k], acc);
+        for (int k = 0; k < w.ch; ++k) acc = fmaf(__ldg(w.w0_t + k * w.temb_ch + o), emb[k], acc);
         h[o] = swishf(acc);
     }
     __syncthreads();
     for (int o = threadIdx.x; o < w.temb_ch; o += blockDim.x) {
         float acc = w.b2[o];
-        for (int k = 0; k < w.temb_ch; ++k) acc = fmaf(w.w2[o * w.temb_ch + k], h[k], acc);
+        for (int k = 0; k < w.temb_ch; ++k) acc = fmaf(__ldg(w.w2_t + k * w.temb_ch + o), h[k], acc);
         sv[o] = swishf(acc);                          // ResidualBlock applies act(temb) before temb_proj (models.py:101)
     }
     __syncthreads();

@@ -28,8 +28,8 @@ int launch_softmax_rows(const float* S, bf16* P, long long rows, int L, cudaStre
 struct TembWeights {
     int ch, temb_ch, total_proj;       // ch=32, temb_ch=128, total_proj = sum of out_ch over all ResBlocks
     const float* freqs;                // [ch/2]
-    const float* w0; const float* b0;  // [temb_ch][ch], [temb_ch]
-    const float* w2; const float* b2;  // [temb_ch][temb_ch], [temb_ch]
+    const float* w0_t; const float* b0;  // dense 0 TRANSPOSED [ch][temb_ch] (coalesced over outputs), bias [temb_ch]
+    const float* w2_t; const float* b2;  // dense 2 TRANSPOSED [temb_ch][temb_ch], bias [temb_ch]
     const float* wp_t; const float* bp;  // projections TRANSPOSED [temb_ch][total_proj], bias [total_proj]
 };
 // out[img][total_proj]

@@ -42,7 +42,7 @@ constexpr int ROWCONV_SMEM_BUDGET = ROWCONV_SMEM_MAX - 2048 - 1024;
 int rowconv_max_smem() { return ROWCONV_SMEM_MAX; }
 
 // Row-streaming kernel: shape analysis shared by rowconv_eligible() and the preparation.
-struct RowShape { int BK, BN, nsplit, kch, kch2, kch_a, kch2_a, w_bytes, slot_bytes, nslot, stage_bytes; };
+struct RowShape { int BK, BN, nsplit, kch, kch2, kch_a, kch2_a, w_bytes, slot_bytes, nslot, stage_bytes, n_epi; };
 static bool rowconv_shape(const ConvDesc& d, RowShape& r) {
     if (!d.allow_rowconv || d.ksize != 3 || d.stride != 1 || d.Wout % 128 != 0 || d.Wout != d.Win || d.Hout != d.Hin) return false;
     if (!(d.N_pad == 16 || d.N_pad == 32 || d.N_pad == 64) || d.c_base != 0) return false;
@@ -67,12 +67,16 @@ static bool rowconv_shape(const ConvDesc& d, RowShape& r) {
         if (BN < 16 || (BN * rowb) % 1024 != 0) continue;        // stacked vertical-tap tiles must keep the swizzle phase
         const int w_tile = (BN * r.BK * 2 + 1023) / 1024 * 1024;
         const int w_bytes = 3 * r.kch * (3 * BN * rowb) + r.kch2 * w_tile;
-        // bf16 NHWC outputs with full 32-channel blocks leave through staging tiles + TMA store (RowCfg::STAGE_BYTES)
-        const int stage = (d.out_mode == 0 && BN >= 32 && d.n_valid == d.N_pad && d.out_col_stride == 1) ? (BN <= 32 ? 1 : 2) * 2 * 128 * 64 : 0;
+        // epilogue / transform warp split (RowCfg).  Measured (profiles/r01_ab_experiments.md): the fused GroupNorm transform takes
+        // the same time with 4 or 8 warps (it contends with the MMA operand reads for shared-memory bandwidth), while a single
+        // epilogue set is slower than two -> 8 epilogue + 4 transform warps everywhere.
+        const int n_epi = 8;
+        // bf16 NHWC outputs with full 32-channel blocks are transposed through per-warp staging tiles (RowCfg::STAGE_BYTES)
+        const int stage = (d.out_mode == 0 && BN >= 32 && d.n_valid == d.N_pad && d.out_col_stride == 1) ? n_epi * 32 * 64 : 0;
         int nslot = (ROWCONV_SMEM_BUDGET - w_bytes - stage) / r.slot_bytes;
         if (nslot > 8) nslot = 8;
         if (nslot >= (nsplit == 1 ? 4 : 3)) {
-            r.BN = BN; r.nsplit = nsplit; r.w_bytes = w_bytes; r.nslot = nslot; r.stage_bytes = stage;
+            r.BN = BN; r.nsplit = nsplit; r.w_bytes = w_bytes; r.nslot = nslot; r.stage_bytes = stage; r.n_epi = n_epi;
             return true;
         }
     }
@@ -85,8 +89,8 @@ bool rowconv_eligible(const ConvDesc& d) {
 void describe_conv_impl(const ConvDesc& d, char* buf, size_t n) {
     RowShape r;
     if (rowconv_shape(d, r))
-        snprintf(buf, n, "rowconv<%d,%d,%d> nsplit=%d nslot=%d kch2=%d w=%dKB slot=%dKB stage=%dKB gn=%d", r.BK, r.BN, r.kch, r.nsplit, r.nslot,
-                 r.kch2, r.w_bytes / 1024, r.slot_bytes / 1024, r.stage_bytes / 1024, d.gn_gamma ? 1 : 0);
+        snprintf(buf, n, "rowconv<%d,%d,%d> nsplit=%d nslot=%d kch2=%d w=%dKB slot=%dKB stage=%dKB epi_warps=%d gn=%d", r.BK, r.BN, r.kch, r.nsplit,
+                 r.nslot, r.kch2, r.w_bytes / 1024, r.slot_bytes / 1024, r.stage_bytes / 1024, r.n_epi, d.gn_gamma ? 1 : 0);
     else
         snprintf(buf, n, "conv_gemm<%d,%d> k=%d s=%d", (d.Cin % 64 == 0 && d.C2 % 64 == 0) ? 64 : 32, d.N_pad > 256 ? 256 : d.N_pad, d.ksize, d.stride);
 }
@@ -101,7 +105,8 @@ static int try_prepare_rowconv(TcOp& op, const ConvDesc& d) {
     r.H = d.Hout; r.W = d.Wout; r.n_img = d.B;
     r.strips = d.Wout / 128;
     r.nsplit = sh.nsplit;
-    r.tma_store = sh.stage_bytes > 0;
+    r.staged_store = sh.stage_bytes > 0;
+    op.n_epi = sh.n_epi;
     PNPF_REQUIRE((long long)d.B * r.strips * d.Hout < (1LL << 31) / 256, "row conv: batch * rows too large for 32-bit row indices");
     r.kchunks = sh.kch; r.kchunks2 = sh.kch2; r.nslot = sh.nslot; r.slot_bytes = sh.slot_bytes;
     r.kch_a = sh.kch_a; r.kch2_a = sh.kch2_a;
@@ -125,11 +130,8 @@ static int try_prepare_rowconv(TcOp& op, const ConvDesc& d) {
         if (d.C2b) { if (int e = make_act_tmap(&op.tmA2b, d.x2b, d.C2b, d.x2b_pitch, d.Wout, d.Hout, d.B, BK, 128, 1, 1)) return e; }
     }
     if (int e = make_b_tmap(&op.tmB, d.w, Ktot, Ktot, d.N_pad, 1, 0, BK, BN)) return e;
-    op.tmO = op.tmA;
-    if (r.tma_store) {
-        PNPF_REQUIRE(d.out_img_stride == (long long)d.Hout * d.Wout * d.out_row_stride, "row conv: TMA store needs a dense NHWC output");
-        if (int e = make_act_tmap(&op.tmO, d.out, d.n_valid, d.out_row_stride, d.Wout, d.Hout, d.B, 32, 128, 1, 1)) return e;
-    }
+    if (r.staged_store)
+        PNPF_REQUIRE(d.out_row_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0, "row conv: staged store needs 16-byte aligned output rows");
     op.flops = 2.0 * d.B * d.Hout * d.Wout * (double)d.n_valid * (double)(Ktot - (d.x2_identity ? d.C2 : 0));
     return 0;
 }
@@ -180,6 +182,8 @@ int prepare_conv(TcOp& op, const ConvDesc& d) {
         op.tmA2 = op.tmA;
     }
     if (int e = make_b_tmap(&op.tmB, d.w, Ktot, Ktot, d.N_pad, 1, 0, BK, BN)) return e;
+    op.tmBh = op.tmB;                 // CTA-pair launches stage half of the weight tile per CTA (box of BN/2 rows)
+    if (BK == 64 && BN >= 128) { if (int e = make_b_tmap(&op.tmBh, d.w, Ktot, Ktot, d.N_pad, 1, 0, BK, BN / 2)) return e; }
     op.flops = 2.0 * d.B * d.Hout * d.Wout * (double)d.n_valid * (double)Ktot;
     return 0;
 }
@@ -226,19 +230,21 @@ int prepare_gemm(TcOp& op, const GemmDesc& d) {
     }
     op.tmA2 = op.tmA;
     if (int e = make_b_tmap(&op.tmB, d.Bm, d.K, d.ldb, d.N, d.b_batched ? d.batch : 1, d.b_bstride, BK, BN)) return e;
+    op.tmBh = op.tmB;
+    if (BN >= 128) { if (int e = make_b_tmap(&op.tmBh, d.Bm, d.K, d.ldb, d.N, d.b_batched ? d.batch : 1, d.b_bstride, BK, BN / 2)) return e; }
     op.flops = 2.0 * d.batch * (double)d.M * d.N * d.K;
     return 0;
 }
 
-template <int BK, int BN, int KCH>
+template <int BK, int BN, int KCH, int NEW>
 static int launch_row_t(const TcOp& op, cudaStream_t stream) {
-    using Cfg = RowCfg<BK, BN>;
+    using Cfg = RowCfg<BK, BN, NEW>;
     const RowConvParams& r = op.rp;
-    const int smem = 3 * r.kchunks * Cfg::W_STACK + r.kchunks2 * Cfg::W_TILE + r.nslot * r.slot_bytes + (r.tma_store ? Cfg::STAGE_BYTES : 0) +
+    const int smem = 3 * r.kchunks * Cfg::W_STACK + r.kchunks2 * Cfg::W_TILE + r.nslot * r.slot_bytes + (r.staged_store ? Cfg::STAGE_BYTES : 0) +
                      Cfg::BAR_BYTES + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        PNPF_CHECK_CUDA(cudaFuncSetAttribute(rowconv_kernel<BK, BN, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowconv_max_smem()));
+        PNPF_CHECK_CUDA(cudaFuncSetAttribute(rowconv_kernel<BK, BN, KCH, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowconv_max_smem()));
         attr_set = true;
     }
     PNPF_REQUIRE(smem <= rowconv_max_smem(), "row conv shared memory %d exceeds the budget", smem);
@@ -248,25 +254,25 @@ static int launch_row_t(const TcOp& op, cudaStream_t stream) {
     if (groups > (rows + 7) / 8) groups = (rows + 7) / 8;
     const int grid = (int)groups * r.nsplit;
     if (grid < 1) return 0;
-    rowconv_kernel<BK, BN, KCH><<<grid, Cfg::THREADS, smem, stream>>>(op.tmA, op.tmAb, op.tmA2, op.tmA2b, op.tmB, op.tmO, r);
+    rowconv_kernel<BK, BN, KCH, NEW><<<grid, Cfg::THREADS, smem, stream>>>(op.tmA, op.tmAb, op.tmA2, op.tmA2b, op.tmB, r);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_tc(const TcOp& op, cudaStream_t s) {
     if (op.kind == 1) {
-#define PNPF_RCASE(bk, bn)                                                                \
-    if (op.BK == bk && op.BN == bn) {                                                     \
-        if (op.rp.kchunks == 1) return launch_row_t<bk, bn, 1>(op, s);                    \
-        if (op.rp.kchunks == 2) return launch_row_t<bk, bn, 2>(op, s);                    \
-        if (op.rp.kchunks == 3) return launch_row_t<bk, bn, 3>(op, s);                    \
+#define PNPF_RCASE(bk, bn, ne)                                                            \
+    if (op.BK == bk && op.BN == bn && op.n_epi == ne) {                                   \
+        if (op.rp.kchunks == 1) return launch_row_t<bk, bn, 1, ne>(op, s);                \
+        if (op.rp.kchunks == 2) return launch_row_t<bk, bn, 2, ne>(op, s);                \
+        if (op.rp.kchunks == 3) return launch_row_t<bk, bn, 3, ne>(op, s);                \
     }
-        PNPF_RCASE(32, 16) PNPF_RCASE(32, 32) PNPF_RCASE(32, 64) PNPF_RCASE(64, 16) PNPF_RCASE(64, 32) PNPF_RCASE(64, 64)
+        PNPF_RCASE(32, 16, 8) PNPF_RCASE(32, 32, 8) PNPF_RCASE(32, 64, 8) PNPF_RCASE(64, 16, 8) PNPF_RCASE(64, 32, 8) PNPF_RCASE(64, 64, 8)
 #undef PNPF_RCASE
-        set_error("no rowconv instantiation for BK=%d BN=%d", op.BK, op.BN);
+        set_error("no rowconv instantiation for BK=%d BN=%d epilogue warps %d", op.BK, op.BN, op.n_epi);
         return 2;
     }
-    return launch_conv_gemm(op.BK, op.BN, op.tmA, op.tmA2, op.tmB, op.p, s);
+    return launch_conv_gemm(op.BK, op.BN, op.tmA, op.tmA2, op.tmB, op.tmBh, op.p, s);
 }
 
 static inline bf16 f2bf(float f) { return __float2bfloat16_rn(f); }

@@ -10,11 +10,12 @@ typedef __nv_bfloat16 bf16;
 // ------------------------------------------------------------------ tensor-core ops
 struct TcOp {               // a prepared conv_gemm launch
     CUtensorMap tmA, tmAb, tmA2, tmA2b, tmB;   // *b: second source of a channel concat (row conv only)
-    CUtensorMap tmO;                            // output map of the row conv's TMA-store epilogue
+    CUtensorMap tmBh;                           // weight map with a box of BN/2 rows (CTA-pair launches of conv_gemm_kernel)
     GemmParams p;
     RowConvParams rp;       // kind == 1: row-streaming conv (pnpf_rowconv.cuh)
     int kind = 0;           // 0: conv_gemm_kernel, 1: rowconv_kernel
     int BK = 0, BN = 0;
+    int n_epi = 8;          // row conv: epilogue warps (RowCfg::NEW), the other worker warps run the GroupNorm transform
     double flops = 0;       // algorithmic 2*M*N*K (for reporting)
 };
 

@@ -110,6 +110,64 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------ CTA pairs (cta_group::2)
+// Two CTAs of a cluster (ranks 0/1, one TPC) execute ONE tcgen05.mma of M = 256: each CTA supplies its own 128 rows of A and
+// HALF of B (N/2 rows) from its shared memory and receives its 128 accumulator rows in its own TMEM, so the per-CTA
+// shared-memory traffic for B halves.  Rank 0 (the leader) issues the MMAs and owns the barriers the MMA warp waits on.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {     // every thread of both CTAs
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {   // the same warp of BOTH CTAs, same dst offset
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(kCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols));
+}
+// TMA loads into the executing CTA's shared memory that signal an mbarrier given as a shared::cluster address (the leader's)
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// D[tmem, both CTAs] (+)= A (128 rows per CTA) * B (N/2 rows per CTA), issued by ONE thread of the leader CTA
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in BOTH CTAs when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+
 // ------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are kRowBytes (=swizzle span) wide:
 //   kRowBytes = 128 -> SWIZZLE_128B (layout_type 2), 8-row group stride 1024 B

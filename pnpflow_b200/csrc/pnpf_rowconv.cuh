@@ -46,12 +46,12 @@ struct RowConvParams {
     const float* gn_beta;
     const double* gn_st_a; // [img][Ca][2]
     const double* gn_st_b; // [img][Cb][2]
-    int tma_store;         // bf16 NHWC output through the staging tiles + TMA store (tmO); else per-thread global stores
+    int staged_store;      // bf16 NHWC output through the per-warp staging tiles (coalesced); else per-thread global stores
     long long* dbg;        // optional [32] cycle counters of CTA 0 (profiling experiments), else nullptr
     EpiParams epi;
 };
 
-template <int BK, int BN>
+template <int BK, int BN, int NEW_>
 struct RowCfg {
     static constexpr int kRowBytes = BK * 2;
     static constexpr int HALO_ROWS = 130;
@@ -65,17 +65,21 @@ struct RowCfg {
     static constexpr int NACC = (512 / BN) > 16 ? 16 : (512 / BN);
     static constexpr int TMEM_COLS = NACC * BN;              // 256 (BN=16) or 512
     static constexpr int MAX_SLOTS = 8;
-    // 12 worker warps besides the producer and the MMA issuer.  The GroupNorm transform (one MUFU + ~7 issue slots per
-    // element, 130 * C_in elements per row) is the heaviest stage, so thin outputs (BN <= 32: one epilogue warp set drains a
-    // whole row) give it eight warps; C_out = 64 keeps two epilogue sets that split the columns.
-    static constexpr int NEW = BN <= 32 ? 4 : 8;             // epilogue warps (sets of 4: one per TMEM lane quarter)
-    static constexpr int NSETS = NEW / 4;
+    // 12 worker warps besides the producer and the MMA issuer, split between the epilogue (sets of 4 warps, one per TMEM lane
+    // quarter) and the GroupNorm transform.  Both are per-warp LATENCY chains (barrier wait, tcgen05.ld/st round trips or
+    // ld/st.shared + fence.proxy.async).  NEW = 8 (two epilogue sets: alternate rows for BN <= 32, split columns for BN = 64,
+    // 4 transform warps) is what the host uses; NEW = 4 (one set, 8 transform warps) measured the same or slower because the
+    // transform is limited by shared-memory bandwidth, not by its warp count (profiles/r01_ab_experiments.md).
+    static constexpr int NEW = NEW_;
+    static_assert(NEW == 4 || NEW == 8, "epilogue warps");
+    static_assert(BN <= 32 || NEW == 8, "C_out = 64 needs two epilogue sets");
+    static constexpr bool ROW_SPLIT = BN <= 32 && NEW == 8;  // the two sets alternate rows (else set s owns columns [32 s, 32 s + 32))
     static constexpr int NTW = 12 - NEW;                     // transform warps
-    // bf16 NHWC outputs leave through shared memory: each epilogue set packs its 128 pixels x 32 channels into a 64B-swizzled
-    // staging tile and one thread issues a TMA store (coalesced 64-byte pixel rows instead of 16-byte stores at a 64/128-byte
-    // stride, which cost one L1 wavefront per lane).  Two tiles per set: the store of row r overlaps the packing of row r+1.
-    static constexpr int STAGE_TILE = 128 * 64;
-    static constexpr int STAGE_BYTES = BN >= 32 ? NSETS * 2 * STAGE_TILE : 0;
+    // bf16 NHWC outputs are transposed through a per-warp staging tile (32 pixels x 64 bytes, 64B-swizzled): a lane packs its
+    // pixel's 32 channels with four conflict-free st.shared.v4, then the warp stores eight whole 64-byte pixel rows per
+    // instruction (per-lane 16-byte stores at a 64/128-byte stride cost one L1 wavefront per lane).  Warp-local: no barrier.
+    static constexpr int STAGE_WARP = 32 * 64;
+    static constexpr int STAGE_BYTES = BN >= 32 ? NEW * STAGE_WARP : 0;
     static constexpr int THREADS = 64 + 12 * 32;
     static constexpr int CPT = BN > 32 ? 32 : BN;            // columns per epilogue thread
     static constexpr int BAR_BYTES = 2048;                   // barriers + tmem slot | bias staging (2 x 64 floats) | GN scale/shift (2 x 128)
@@ -108,27 +112,28 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
+// ld/st.shared of the transform stage: volatile keeps them (and their relative order), but without a memory clobber, so the
+// arithmetic of later chunks can be scheduled across the stores of earlier ones
+__device__ __forceinline__ uint4 lds128_nc(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
 }
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sts128_nc(uint32_t saddr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
 // one lane polls, the warp follows
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
     if (lane == 0) mbar_wait(bar, parity);
     __syncwarp();
 }
 
-template <int BK, int BN, int KCH>
-__global__ void __launch_bounds__(RowCfg<BK, BN>::THREADS, 1)
+template <int BK, int BN, int KCH, int NEW_>
+__global__ void __launch_bounds__(RowCfg<BK, BN, NEW_>::THREADS, 1)
 rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAb,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA2b,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
-               const __grid_constant__ RowConvParams p) {
-    using Cfg = RowCfg<BK, BN>;
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ RowConvParams p) {
+    using Cfg = RowCfg<BK, BN, NEW_>;
     constexpr int NACC = Cfg::NACC;
     constexpr int CPT = Cfg::CPT;
     extern __shared__ uint8_t smem_raw[];
@@ -136,8 +141,8 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* wsm = smem;                                  // [kw][chunk] stacked tiles, then the shortcut tiles
     const int w_bytes = 3 * KCH * Cfg::W_STACK + p.kchunks2 * Cfg::W_TILE;
     uint8_t* slots = smem + w_bytes;
-    uint8_t* stage = slots + p.nslot * p.slot_bytes;                // [set][2] output staging tiles (TMA store)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stage + (p.tma_store ? Cfg::STAGE_BYTES : 0));
+    uint8_t* stage = slots + p.nslot * p.slot_bytes;                // [epilogue warp] output staging tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage + (p.staged_store ? Cfg::STAGE_BYTES : 0));
     uint64_t* wbar = bars;
     uint64_t* full_bar = bars + 1;
     uint64_t* empty_bar = full_bar + Cfg::MAX_SLOTS;
@@ -157,7 +162,6 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.kchunks2) tma_prefetch_desc(&tmA2);
         if (p.kch_a < KCH) tma_prefetch_desc(&tmAb);
         if (p.kch2_a < p.kchunks2) tma_prefetch_desc(&tmA2b);
-        if (p.tma_store) tma_prefetch_desc(&tmO);
         mbar_init(wbar, 1);
         for (int s = 0; s < Cfg::MAX_SLOTS; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -166,7 +170,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 16; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], Cfg::NEW);
+            mbar_init(&tempty_bar[a], Cfg::ROW_SPLIT ? 4 : Cfg::NEW);
         }
         fence_barrier_init();
     }
@@ -398,9 +402,9 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
                 c_tab += PNPF_CLK() - c_t0;
-                // One halo tile: all of a thread's 16-byte chunks are loaded first (independent ld.shared in flight), transformed
-                // as ONE straight-line block (the activation is a compile-time branch, invalid rows are computed and discarded,
-                // so the scheduler interleaves the dependent chains of all chunks) and stored with a predicate.
+                // One halo tile: all of a thread's 16-byte chunks are loaded first (independent ld.shared in flight), then
+                // transformed as one straight-line block (the activation is a compile-time branch and invalid rows are computed
+                // and discarded, so the scheduler can interleave the dependent chains) and stored with a predicate.
                 constexpr int NIT = (Cfg::HALO_ROWS + RPI - 1) / RPI;
                 auto transform_tile = [&](auto silu_tag, uint32_t sbase, int c) {
                     constexpr bool kSilu = decltype(silu_tag)::value;
@@ -412,7 +416,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int wpix = w0 - 1 + r;
                         ok[k] = (r < Cfg::HALO_ROWS) && (wpix >= 0) && (wpix < p.W);       // conv zero padding stays zero
                         u[k] = make_uint4(0u, 0u, 0u, 0u);
-                        if (r < Cfg::HALO_ROWS) u[k] = lds128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes);
+                        if (r < Cfg::HALO_ROWS) u[k] = lds128_nc(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes);
                     }
 #pragma unroll
                     for (int k = 0; k < NIT; ++k) {
@@ -434,11 +438,9 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
                             wds[e2] = *reinterpret_cast<uint32_t*>(&b2);
                         }
-                        u[k] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                        // stored as soon as it is ready: the fence below waits for the stores still in flight
+                        if (ok[k]) sts128_nc(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes, make_uint4(wds[0], wds[1], wds[2], wds[3]));
                     }
-#pragma unroll
-                    for (int k = 0; k < NIT; ++k)
-                        if (ok[k]) sts128(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes, u[k]);
                 };
                 for (int j = j0; j <= j1; ++j) {
                     {
@@ -470,13 +472,13 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int m = quarter * 32 + lane;            // pixel within the strip
         const int ethread = threadIdx.x - 64;         // 0..255
-        const int colbase = set * 32;                 // column split: set 1 takes columns 32..63 of C_out = 64
+        const int colbase = Cfg::ROW_SPLIT ? 0 : set * 32;   // column split: set 1 takes columns 32..63 of C_out = 64
         float* bsm = bias_sm + set * 64;
         const uint32_t set_bar = 1 + set;             // named barrier id of this warp set (128 threads)
-        const bool leader = (ethread & 127) == 0;     // issues this set's TMA stores
-        const uint32_t stage_lo = smem_u32(stage) + set * 2 * Cfg::STAGE_TILE + m * 64;   // this pixel's 64-byte row in tile 0
-        const uint32_t stage_sw = static_cast<uint32_t>((m >> 1) & 3);                     // SWIZZLE_64B: chunk ^= (row >> 1) & 3
-        uint32_t stage_sel = 0;
+        // staging tile of this warp: write phase = own pixel row, read phase = 8 pixels x 4 chunks per instruction
+        const uint32_t stage_w = smem_u32(stage) + (warp - 2) * Cfg::STAGE_WARP;
+        const uint32_t st_wr = stage_w + lane * 64, st_wr_sw = static_cast<uint32_t>((lane >> 1) & 3);
+        const int rd_pix = lane >> 2, rd_chunk = lane & 3;
         uint32_t g0 = 0;
         long long c_tfull = 0, c_rows = 0, c_ld = 0, c_st = 0, c_fin = 0;
         const long long c_start = PNPF_CLK();
@@ -501,7 +503,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float ssum[CPT], ssq[CPT];
 #pragma unroll
             for (int q = 0; q < CPT; ++q) ssum[q] = ssq[q] = 0.f;
-            for (int r = hb; r < he; ++r) {
+            for (int r = hb + (Cfg::ROW_SPLIT ? set : 0); r < he; r += (Cfg::ROW_SPLIT ? 2 : 1)) {
                 const uint32_t g = g0 + static_cast<uint32_t>(r - hb);
                 const uint32_t acc = g % NACC;
                 const long long pix = static_cast<long long>(r) * p.W + w0 + m;
@@ -564,31 +566,35 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     if constexpr (CPT == 32) {
-                        if (p.tma_store) {                             // pack to bf16 into this pixel's swizzled staging row
+                        if (p.staged_store) {                          // pack to bf16 into this pixel's swizzled staging row
                             uint32_t pk[8];
 #pragma unroll
                             for (int jj = 0; jj < 8; ++jj) {
                                 __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * jj], v[2 * jj + 1]);
                                 pk[jj] = *reinterpret_cast<uint32_t*>(&b2);
                             }
-                            const uint32_t base = stage_lo + stage_sel * Cfg::STAGE_TILE;
-                            sts128(base + (((2 * q) ^ stage_sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-                            sts128(base + (((2 * q + 1) ^ stage_sw) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+                            sts128(st_wr + (((2 * q) ^ st_wr_sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                            sts128(st_wr + (((2 * q + 1) ^ st_wr_sw) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
                             continue;
                         }
                     }
                     epilogue_store16(p.epi, img, pix, gcol0, v);
                 }
                 if constexpr (CPT == 32) {
-                    if (p.tma_store) {
-                        fence_proxy_async_smem();                      // staging writes -> visible to the TMA unit
-                        if (leader) bulk_wait_read0();                 // the previous row's store (other tile) has left shared memory
-                        asm volatile("bar.sync %0, 128;" ::"r"(set_bar));
-                        if (leader) {
-                            tma_store_4d(&tmO, stage + (set * 2 + stage_sel) * Cfg::STAGE_TILE, n_off + colbase, w0, r, img);
-                            bulk_commit();
+                    if (p.staged_store) {
+                        __syncwarp();
+                        // 4 instructions x (8 pixels x 64 bytes): whole 64-byte pixel rows per store
+                        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.epi.out) + img * p.epi.out_img_stride +
+                                              (static_cast<long long>(r) * p.W + w0 + quarter * 32) * p.epi.out_row_stride + n_off + colbase + rd_chunk * 8;
+                        uint4 o4[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int pr = i * 8 + rd_pix;
+                            o4[i] = lds128(stage_w + pr * 64 + ((rd_chunk ^ ((pr >> 1) & 3)) << 4));
                         }
-                        stage_sel ^= 1;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(orow + (i * 8 + rd_pix) * p.epi.out_row_stride) = o4[i];
+                        __syncwarp();                                  // the tile is rewritten by the next row
                     }
                 }
             }
@@ -625,7 +631,6 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             g0 += static_cast<uint32_t>(he - hb);
             c_fin += PNPF_CLK() - c_f0;
         }
-        if (p.tma_store && leader) bulk_wait0();       // all output rows are in global memory before the CTA retires
         if (p.dbg && blockIdx.x == 0 && ethread == 0) { p.dbg[18] = c_ld; p.dbg[19] = c_st; p.dbg[20] = c_fin; }
         if (p.dbg && blockIdx.x == 0 && ethread == 0) { p.dbg[8] = PNPF_CLK() - c_start; p.dbg[9] = c_tfull; p.dbg[10] = c_rows; }
         if (p.dbg && blockIdx.x == 0 && ethread == 128 && Cfg::NEW == 8) { p.dbg[12] = PNPF_CLK() - c_start; p.dbg[13] = c_tfull; p.dbg[14] = c_rows; }

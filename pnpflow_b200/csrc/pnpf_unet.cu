@@ -318,9 +318,15 @@ extern "C" int pnpf_finalize_weights(pnpf_engine* e) {
             float* d = pk.f32(dst, v.size());
             memcpy(d, v.data(), v.size() * 4);
         };
-        cp("temb.w0", "temb_net.main.0.weight");
+        auto cp_t = [&](const char* dst, const std::string& src, int rows, int cols) {      // [rows][cols] -> [cols][rows]
+            const std::vector<float>& v = W(e, src);
+            float* d = pk.f32(dst, v.size());
+            for (int r = 0; r < rows; ++r)
+                for (int q = 0; q < cols; ++q) d[(size_t)q * rows + r] = v[(size_t)r * cols + q];
+        };
+        cp_t("temb.w0_t", "temb_net.main.0.weight", temb_ch, c.ch);
         cp("temb.b0", "temb_net.main.0.bias");
-        cp("temb.w2", "temb_net.main.2.weight");
+        cp_t("temb.w2_t", "temb_net.main.2.weight", temb_ch, temb_ch);
         cp("temb.b2", "temb_net.main.2.bias");
         // NB: Packer pointers are invalidated by the next reserve() (vector growth): reserve both, then take pointers
         const size_t wp_off = pk.reserve("temb.wp_t", (size_t)temb_ch * e->total_proj * sizeof(float));
@@ -848,8 +854,8 @@ static int run_ops(pnpf_engine* e, const float* x, const float* t, float* v, int
                 TembWeights w;
                 w.ch = c.ch; w.temb_ch = c.ch * 4; w.total_proj = e->total_proj;
                 w.freqs = wptr<float>(e, "temb.freqs");
-                w.w0 = wptr<float>(e, "temb.w0"); w.b0 = wptr<float>(e, "temb.b0");
-                w.w2 = wptr<float>(e, "temb.w2"); w.b2 = wptr<float>(e, "temb.b2");
+                w.w0_t = wptr<float>(e, "temb.w0_t"); w.b0 = wptr<float>(e, "temb.b0");
+                w.w2_t = wptr<float>(e, "temb.w2_t"); w.b2 = wptr<float>(e, "temb.b2");
                 w.wp_t = wptr<float>(e, "temb.wp_t"); w.bp = wptr<float>(e, "temb.bp");
                 rc = launch_temb(w, t, batch, e->tproj, st);
                 break;
