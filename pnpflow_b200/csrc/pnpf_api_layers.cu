@@ -58,6 +58,7 @@ extern "C" int pnpf_conv2d_nhwc(const void* x, int B, int Hin, int Win, int Cin,
         cudaMemset(dbg, 0, 32 * sizeof(long long));
         op.rp.dbg = dbg;
         op.p.dbg = dbg;
+        op.pp.dbg = dbg;
     }
     if (!rc) rc = launch_tc(op, s);
     cudaError_t e = cudaStreamSynchronize(s);
@@ -67,6 +68,10 @@ extern "C" int pnpf_conv2d_nhwc(const void* x, int B, int Hin, int Win, int Cin,
         printf("%s producer: total %lld wait_empty %lld rows/tiles %lld | mma: total %lld wait_full %lld wait_tempty %lld | "
                "epi0: total %lld wait_tfull %lld rows %lld | epi1: total %lld wait_tfull %lld rows %lld\n", op.kind == 1 ? "ROWCONV_DBG" : "GEMM_DBG",
                h[0], h[1], h[2], h[4], h[5], h[6], h[8], h[9], h[10], h[12], h[13], h[14]);
+        if (op.kind == 2)
+            printf("PATCH_DBG tiles %lld | patch producer: total %lld wait_empty %lld | weight producer: total %lld wait_empty %lld | mma: total %lld "
+                   "wait_patch %lld wait_weights %lld wait_tempty %lld | epi: total %lld wait_tfull %lld\n", h[2], h[0], h[1], h[12], h[13], h[4], h[5], h[7], h[6],
+                   h[8], h[9]);
         if (op.kind == 1)
             printf("   mma: issue %lld commit %lld | epi0: tmem_ld %lld tmem_st+arrive %lld stats_flush %lld\n", h[16], h[17], h[18], h[19], h[20]);
         fflush(stdout);

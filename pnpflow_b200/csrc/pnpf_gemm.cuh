@@ -118,6 +118,83 @@ __device__ __forceinline__ int colsum16_col(int lane) {
     return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
+// Two adjacent 16-column chunks of one accumulator row at once: every global load (bias, time-embedding row, residual) of
+// both chunks is issued BEFORE the accumulator wait, invalid lanes load from pixel 0 and are masked afterwards (no divergent
+// branch), and the two statistics butterflies are independent instruction streams the scheduler interleaves — the epilogue
+// is a per-warp latency chain, so halving the number of chains per tile is what shortens it.
+__device__ __forceinline__ void epilogue_chunk32(const EpiParams& p, uint32_t t_addr, int img, long long pix, bool valid, int col0, int lane) {
+    const bool on0 = col0 < p.n_valid, on1 = col0 + 16 < p.n_valid;             // warp-uniform
+    const long long pix_s = valid ? pix : 0;
+    float4 b[2][4], bi[2][4];
+    uint4 rs[2][2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            b[h][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            bi[h][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        rs[h][0] = rs[h][1] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (p.bias) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (h == 0 ? on0 : on1)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[h][j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 16 * h) + j);
+    }
+    if (p.bias_img) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (h == 0 ? on0 : on1)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bi[h][j] = __ldg(reinterpret_cast<const float4*>(p.bias_img + img * p.bias_img_stride + col0 + 16 * h) + j);
+    }
+    if (p.residual) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (h == 0 ? on0 : on1) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + img * p.res_img_stride + pix_s * p.res_row_stride + col0 + 16 * h);
+                rs[h][0] = __ldg(rp);
+                rs[h][1] = __ldg(rp + 1);
+            }
+    }
+    uint32_t r[2][16];
+    tmem_ld_x16(t_addr + col0, r[0]);
+    tmem_ld_x16(t_addr + col0 + 16, r[1]);
+    tmem_ld_wait();
+    float v[2][16];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[h][4 * j] = __uint_as_float(r[h][4 * j]) + b[h][j].x + bi[h][j].x;
+            v[h][4 * j + 1] = __uint_as_float(r[h][4 * j + 1]) + b[h][j].y + bi[h][j].y;
+            v[h][4 * j + 2] = __uint_as_float(r[h][4 * j + 2]) + b[h][j].z + bi[h][j].z;
+            v[h][4 * j + 3] = __uint_as_float(r[h][4 * j + 3]) + b[h][j].w + bi[h][j].w;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t uu[4] = {rs[h][q].x, rs[h][q].y, rs[h][q].z, rs[h][q].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[h][q * 8 + 2 * j] += __uint_as_float(uu[j] << 16);
+                v[h][q * 8 + 2 * j + 1] += __uint_as_float(uu[j] & 0xFFFF0000u);
+            }
+        }
+    }
+    if (p.stats) {
+        const float t0 = warp_colsum16(v[0], valid && on0, lane);
+        const float t1 = warp_colsum16(v[1], valid && on1, lane);
+        const int cs = col0 + colsum16_col(lane);
+        double* sp = p.stats + (static_cast<long long>(img) * p.n_valid + cs) * 2 + (lane & 1);
+        if (on0) atomicAdd(sp, static_cast<double>(t0));
+        if (on1) atomicAdd(sp + 32, static_cast<double>(t1));
+    }
+    if (valid && on0) epilogue_store16(p, img, pix, col0, v[0]);
+    if (valid && on1) epilogue_store16(p, img, pix, col0 + 16, v[1]);
+}
+
 struct GemmParams {
     int H, W;              // output extent in the A-box coordinate space (plain GEMM: H=1, W=M)
     int TH, TW;            // tile box, TH*TW == 128

@@ -86,11 +86,40 @@ bool rowconv_eligible(const ConvDesc& d) {
     RowShape r;
     return rowconv_shape(d, r);
 }
+// Patch-streaming kernel: shape analysis.
+struct PatchShape { int P, NR, patch_bytes, na, nb, nb_pair, tiles_per_img; };
+constexpr int PATCH_SMEM_MAX = 227 * 1024;
+static bool patchconv_shape(const ConvDesc& d, PatchShape& r) {
+    static const bool off = getenv("PNPF_NO_PATCH") != nullptr;          // A/B switch (tools/ab_env.py)
+    if (off || !d.allow_rowconv || d.ksize != 3 || d.stride != 1 || d.Wout != d.Win || d.Hout != d.Hin || d.Wout > 128) return false;
+    if (!(d.N_pad == 128 || d.N_pad == 256) || d.c_base != 0 || d.xb || d.x2b || d.gn_gamma) return false;
+    if (d.Cin % 64 || d.C2 % 64 || d.Cin < 64) return false;
+    r.P = d.Wout + 2;
+    r.NR = (r.P - 1 + 127) / r.P + 1 + 2;          // rows a tile of 128 positions can touch, plus the two halo rows
+    r.patch_bytes = (r.NR * r.P * 128 + 1023) / 1024 * 1024;
+    r.tiles_per_img = (d.Hout * r.P + 127) / 128;
+    // rings: weight tiles of the non-pair variant (the larger) must fit: >= 2 patches + >= 4 weight tiles
+    const int b_bytes = d.N_pad * 128;
+    const int budget = PATCH_SMEM_MAX - 1024 - 512;
+    r.na = 3;
+    while (r.na > 2 && budget - r.na * r.patch_bytes < 4 * b_bytes) --r.na;
+    r.nb = (budget - r.na * r.patch_bytes) / b_bytes;
+    if (r.nb > 12) r.nb = 12;
+    r.nb_pair = (budget - r.na * r.patch_bytes) / (b_bytes / 2);      // CTA pairs stage half tiles: twice the depth
+    if (r.nb_pair > 12) r.nb_pair = 12;
+    return r.nb >= 4;
+}
+bool patchconv_eligible(const ConvDesc& d) {
+    PatchShape r;
+    return patchconv_shape(d, r);
+}
 void describe_conv_impl(const ConvDesc& d, char* buf, size_t n) {
     RowShape r;
     if (rowconv_shape(d, r))
         snprintf(buf, n, "rowconv<%d,%d,%d> nsplit=%d nslot=%d kch2=%d w=%dKB slot=%dKB stage=%dKB epi_warps=%d gn=%d", r.BK, r.BN, r.kch, r.nsplit,
                  r.nslot, r.kch2, r.w_bytes / 1024, r.slot_bytes / 1024, r.stage_bytes / 1024, r.n_epi, d.gn_gamma ? 1 : 0);
+    else if (PatchShape ps; patchconv_shape(d, ps))
+        snprintf(buf, n, "patchconv<%d> P=%d NR=%d patch=%dKB na=%d nb=%d tiles/img=%d", d.N_pad, ps.P, ps.NR, ps.patch_bytes / 1024, ps.na, ps.nb, ps.tiles_per_img);
     else
         snprintf(buf, n, "conv_gemm<%d,%d> k=%d s=%d", (d.Cin % 64 == 0 && d.C2 % 64 == 0) ? 64 : 32, d.N_pad > 256 ? 256 : d.N_pad, d.ksize, d.stride);
 }
@@ -136,10 +165,35 @@ static int try_prepare_rowconv(TcOp& op, const ConvDesc& d) {
     return 0;
 }
 
+static int try_prepare_patchconv(TcOp& op, const ConvDesc& d) {
+    PatchShape sh;
+    if (!patchconv_shape(d, sh)) return -1;
+    PatchConvParams& q = op.pp;
+    memset(&q, 0, sizeof(q));
+    q.H = d.Hout; q.W = d.Wout; q.P = sh.P; q.NR = sh.NR; q.n_img = d.B; q.tiles_per_img = sh.tiles_per_img;
+    q.kchunks = d.Cin / 64; q.kchunks2 = d.x2 ? d.C2 / 64 : 0;
+    q.patch_bytes = sh.patch_bytes; q.na = sh.na; q.nb = sh.nb;
+    op.patch_nb_pair = sh.nb_pair;
+    fill_epi(q.epi, d);
+    op.kind = 2; op.BK = 64; op.BN = d.N_pad;
+    const long long Ktot = 9LL * d.Cin + (d.x2 ? d.C2 : 0);
+    if (int e = make_act_tmap(&op.tmA, d.x, d.Cin, d.x_pitch, d.Win, d.Hin, d.B, 64, sh.P, sh.NR, 1)) return e;
+    op.tmA2 = op.tmA;
+    if (d.x2) { if (int e = make_act_tmap(&op.tmA2, d.x2, d.C2, d.x2_pitch, d.Wout, d.Hout, d.B, 64, sh.P, sh.NR, 1)) return e; }
+    if (int e = make_b_tmap(&op.tmB, d.w, Ktot, Ktot, d.N_pad, 1, 0, 64, d.N_pad)) return e;
+    if (int e = make_b_tmap(&op.tmBh, d.w, Ktot, Ktot, d.N_pad, 1, 0, 64, d.N_pad / 2)) return e;
+    op.flops = 2.0 * d.B * d.Hout * d.Wout * (double)d.n_valid * (double)Ktot;
+    return 0;
+}
+
 int prepare_conv(TcOp& op, const ConvDesc& d) {
     PNPF_REQUIRE(d.ksize == 1 || d.ksize == 3, "conv kernel size %d unsupported (1 or 3)", d.ksize);
     {
         const int rc = try_prepare_rowconv(op, d);
+        if (rc >= 0) return rc;
+    }
+    {
+        const int rc = try_prepare_patchconv(op, d);
         if (rc >= 0) return rc;
     }
     PNPF_REQUIRE(!d.xb && !d.x2b && !d.gn_gamma, "two-source / fused-GroupNorm convolution needs the row-streaming kernel "
@@ -259,7 +313,60 @@ static int launch_row_t(const TcOp& op, cudaStream_t stream) {
     return 0;
 }
 
+template <int BN, bool PAIR>
+static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
+    using Cfg = PatchCfg<BN, PAIR>;
+    PatchConvParams q = op.pp;
+    if (PAIR) q.nb = op.patch_nb_pair;
+    const int smem = q.na * q.patch_bytes + q.nb * Cfg::B_BYTES + 512 + 1024;
+    static bool attr_set = false;
+    static int max_clusters = 0;
+    if (!attr_set) {
+        PNPF_CHECK_CUDA(cudaFuncSetAttribute(patchconv_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, PATCH_SMEM_MAX));
+        if (PAIR) {
+            cudaLaunchConfig_t qc = {};
+            qc.gridDim = dim3(num_sms() & ~1);
+            qc.blockDim = dim3(Cfg::THREADS);
+            qc.dynamicSmemBytes = PATCH_SMEM_MAX;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa; qc.numAttrs = 1;
+            PNPF_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, patchconv_kernel<BN, PAIR>, &qc));
+            PNPF_REQUIRE(max_clusters >= 1, "no CTA pair of patchconv_kernel<%d> fits on this device", BN);
+        }
+        attr_set = true;
+    }
+    PNPF_REQUIRE(smem <= PATCH_SMEM_MAX, "patch conv shared memory %d exceeds the budget", smem);
+    const long long units = (long long)(q.n_img / (PAIR ? 2 : 1)) * q.tiles_per_img;
+    if (units < 1) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    if (PAIR) {
+        const int clusters = (int)(units < max_clusters ? units : max_clusters);
+        cfg.gridDim = dim3(2 * clusters);
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+    } else {
+        cfg.gridDim = dim3((unsigned)(units < num_sms() ? units : num_sms()));
+    }
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    PNPF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, patchconv_kernel<BN, PAIR>, op.tmA, op.tmA2, PAIR ? op.tmBh : op.tmB, q));
+    return 0;
+}
+
 int launch_tc(const TcOp& op, cudaStream_t s) {
+    if (op.kind == 2) {
+        static const bool no_pair = getenv("PNPF_NO_PAIR") != nullptr;
+        const bool pair = !no_pair && op.pp.n_img % 2 == 0;
+        if (op.BN == 128) return pair ? launch_patch_t<128, true>(op, s) : launch_patch_t<128, false>(op, s);
+        if (op.BN == 256) return pair ? launch_patch_t<256, true>(op, s) : launch_patch_t<256, false>(op, s);
+        set_error("no patchconv instantiation for BN=%d", op.BN);
+        return 2;
+    }
     if (op.kind == 1) {
 #define PNPF_RCASE(bk, bn, ne)                                                            \
     if (op.BK == bk && op.BN == bn && op.n_epi == ne) {                                   \

@@ -2,6 +2,7 @@
 #pragma once
 #include "pnpf_host.h"
 #include "pnpf_rowconv.cuh"
+#include "pnpf_patchconv.cuh"
 
 namespace pnpf {
 
@@ -13,7 +14,9 @@ struct TcOp {               // a prepared conv_gemm launch
     CUtensorMap tmBh;                           // weight map with a box of BN/2 rows (CTA-pair launches of conv_gemm_kernel)
     GemmParams p;
     RowConvParams rp;       // kind == 1: row-streaming conv (pnpf_rowconv.cuh)
-    int kind = 0;           // 0: conv_gemm_kernel, 1: rowconv_kernel
+    PatchConvParams pp;     // kind == 2: patch-streaming conv (pnpf_patchconv.cuh)
+    int patch_nb_pair = 0;  // weight-ring depth of the CTA-pair launch (half tiles)
+    int kind = 0;           // 0: conv_gemm_kernel, 1: rowconv_kernel, 2: patchconv_kernel
     int BK = 0, BN = 0;
     int n_epi = 8;          // row conv: epilogue warps (RowCfg::NEW), the other worker warps run the GroupNorm transform
     double flops = 0;       // algorithmic 2*M*N*K (for reporting)
@@ -65,6 +68,7 @@ struct ConvDesc {
 };
 int prepare_conv(TcOp& op, const ConvDesc& d);
 bool rowconv_eligible(const ConvDesc& d);     // would prepare_conv pick the row-streaming kernel?
+bool patchconv_eligible(const ConvDesc& d);   // ... the patch-streaming kernel (3x3 stride 1, W <= 128, C_out 128 / 256)?
 int rowconv_max_smem();
 void describe_conv_impl(const ConvDesc& d, char* buf, size_t n);   // which kernel prepare_conv would pick (PNPF_PLAN_DUMP)
 
