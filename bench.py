@@ -292,25 +292,66 @@ def main():
     torch.cuda.synchronize()
     unet_replay_ms = e0.elapsed_time(e1) / 5
 
-    # ---------------- roofline of the dominant kernel class (tcgen05 implicit-GEMM), per-op CUDA events ----------------
+    # ---------------- rooflines from per-op CUDA events of one U-Net evaluation (pnpf_profile_forward) ----------------
+    # Every op has algorithmic FLOPs and algorithmic HBM bytes (each operand read once, each output written once), so its
+    # roof is the slower of FLOPs / measured bf16 peak and bytes / measured copy bandwidth.  `roofline` proper is the
+    # DOMINANT kernel = the template instantiation with the largest share of the evaluation; the other kernels and the
+    # tensor-core aggregate (the north star's "fraction of the conv-GEMM roofline") are listed next to it.
     prof = eng.profile(S * B)
+    pk = peaks()
+    pk_fl, pk_by = pk["tflops"] * 1e12, pk["hbm"] * 1e9
+
+    def kernel_of(o):
+        impl = o.get("impl", "?")
+        return impl.split(">")[0] + ">" if "<" in impl else impl.split(" ")[0]
+
+    fams = {}
+    for o in prof:
+        f = fams.setdefault(kernel_of(o), dict(launches=0, ms=0.0, flops=0.0, bytes=0.0, roof_ms=0.0, tensor_roof_ms=0.0, hbm_roof_ms=0.0))
+        f["launches"] += 1; f["ms"] += o["ms"]; f["flops"] += o["flops"]; f["bytes"] += o["bytes"]
+        t_fl, t_by = o["flops"] / pk_fl * 1e3, o["bytes"] / pk_by * 1e3
+        f["roof_ms"] += max(t_fl, t_by); f["tensor_roof_ms"] += t_fl; f["hbm_roof_ms"] += t_by
+    total_ms = sum(f["ms"] for f in fams.values())
+    kernels = []
+    for name, f in sorted(fams.items(), key=lambda kv: -kv[1]["ms"]):
+        if f["ms"] <= 0:
+            continue
+        bound = "tensor" if f["tensor_roof_ms"] >= f["hbm_roof_ms"] else "hbm"
+        kernels.append({"kernel": name, "launches": f["launches"], "ms": f["ms"], "share": f["ms"] / total_ms, "bound": bound,
+                        "tflops": f["flops"] / (f["ms"] * 1e-3) / 1e12, "gbs": f["bytes"] / (f["ms"] * 1e-3) / 1e9,
+                        "frac_of_roof": f["roof_ms"] / f["ms"]})
+    dom = kernels[0]
+    domf = fams[dom["kernel"]]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_dominant_kernel_dram_bytes.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            if tj.get("kernel") == dom["kernel"]:
+                traffic = tj.get("dram_bytes_per_launch_mean")
+        except Exception:
+            traffic = None
     tc = [o for o in prof if o["kind"] == "tc"]
     simt = [o for o in prof if o["kind"] == "simt"]
     tc_ms, tc_fl = sum(o["ms"] for o in tc), sum(o["flops"] for o in tc)
     simt_ms, simt_by = sum(o["ms"] for o in simt), sum(o["bytes"] for o in simt)
-    pk = peaks()
     ach = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_conv_gemm_dram_bytes.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch_mean")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "tensor", "kernel": "rowconv_kernel<BK,BN,KCH> + conv_gemm_kernel<BK,BN> (all tensor-core launches of one U-Net evaluation)",
-                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"] if pk["tflops"] else None,
-                "traffic": traffic, "peak_source": pk["src"], "launches": len(tc),
-                "flops_per_eval_batch": tc_fl, "tc_ms_per_eval": tc_ms, "tc_share_of_eval": tc_ms / (tc_ms + simt_ms) if tc_ms + simt_ms > 0 else None,
+    if dom["bound"] == "hbm":
+        r_ach, r_peak, r_unit = domf["bytes"] / domf["launches"] / (domf["ms"] / domf["launches"] * 1e-3) / 1e9, pk["hbm"], "GB/s"
+        per_launch = domf["bytes"] / domf["launches"]
+    else:
+        r_ach, r_peak, r_unit = domf["flops"] / domf["launches"] / (domf["ms"] / domf["launches"] * 1e-3) / 1e12, pk["tflops"], "TFLOP/s"
+        per_launch = domf["flops"] / domf["launches"]
+    roofline = {"bound": dom["bound"], "kernel": dom["kernel"], "achieved": r_ach, "peak": r_peak, "unit": r_unit,
+                "frac": r_ach / r_peak if r_peak else None, "traffic": traffic, "peak_source": pk["src"],
+                "launches": dom["launches"], "avg_launch_ms": domf["ms"] / domf["launches"], "algorithmic_per_launch": per_launch,
+                "share_of_unet_eval": dom["share"],
+                "kernels": kernels,
+                "step_frac_of_roof": sum(f["roof_ms"] for f in fams.values()) / total_ms,
+                "tensor_aggregate": {"kernel": "all tensor-core launches of one U-Net evaluation (rowconv + patchconv + conv_gemm)",
+                                     "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"] if pk["tflops"] else None,
+                                     "launches": len(tc), "flops_per_eval_batch": tc_fl, "tc_ms_per_eval": tc_ms,
+                                     "tc_share_of_eval": tc_ms / (tc_ms + simt_ms) if tc_ms + simt_ms > 0 else None},
                 "simt": {"achieved_gbs": simt_by / (simt_ms * 1e-3) / 1e9 if simt_ms > 0 else None, "peak_gbs": pk["hbm"],
                          "ms_per_eval": simt_ms, "algorithmic_bytes": simt_by},
                 "whole_step_conv_gemm_frac": (value * T * S * eng.flops_per_image / world) / (pk["tflops"] * 1e12) if pk["tflops"] else None}

@@ -80,6 +80,8 @@ int pnpf_debug_forward_partial(pnpf_engine* e, const float* x, const float* t, i
 int pnpf_debug_read_op_output(pnpf_engine* e, int i, int batch, float* dst, size_t dst_elems, int dims[3], void* stream);
 /* per-op accounting (per image): kind 1 = tensor-core conv/GEMM op, 0 = SIMT; algorithmic FLOPs and HBM bytes */
 int pnpf_debug_op_info(pnpf_engine* e, int i, int* kind, double* flops, double* bytes);
+/* which kernel runs op i: "rowconv<BK,BN,KCH> ...", "patchconv<BN> ...", "conv_gemm<BK,BN> ...", "gn_apply", ... (reports) */
+const char* pnpf_debug_op_impl(pnpf_engine* e, int i);
 /* one forward with CUDA events around every op: host_ms[n], n == pnpf_debug_num_ops(). Synchronous (bench/roofline). */
 int pnpf_profile_forward(pnpf_engine* e, const float* x, const float* t, float* v, int batch, float* host_ms, int n,
                          void* stream);

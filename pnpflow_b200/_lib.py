@@ -48,6 +48,7 @@ SYMBOLS = {
     "pnpf_debug_forward_partial": (_I, [_VP, _VP, _VP, _I, _I, _VP]),
     "pnpf_debug_read_op_output": (_I, [_VP, _I, _I, _VP, _SZ, C.POINTER(C.c_int * 3), _VP]),
     "pnpf_debug_op_info": (_I, [_VP, _I, C.POINTER(_I), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "pnpf_debug_op_impl": (C.c_char_p, [_VP, _I]),
     "pnpf_profile_forward": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _I, _VP]),
     "pnpf_unet_flops_per_image": (C.c_double, [_VP]),
     "pnpf_unet_num_launches": (_I, [_VP]),

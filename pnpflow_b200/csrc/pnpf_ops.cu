@@ -92,7 +92,7 @@ constexpr int PATCH_SMEM_MAX = 227 * 1024;
 static bool patchconv_shape(const ConvDesc& d, PatchShape& r) {
     static const bool off = getenv("PNPF_NO_PATCH") != nullptr;          // A/B switch (tools/ab_env.py)
     if (off || !d.allow_rowconv || d.ksize != 3 || d.stride != 1 || d.Wout != d.Win || d.Hout != d.Hin || d.Wout > 128) return false;
-    if (!(d.N_pad == 128 || d.N_pad == 256) || d.c_base != 0 || d.xb || d.x2b || d.gn_gamma) return false;
+    if (!(d.N_pad == 64 || d.N_pad == 128 || d.N_pad == 256) || d.c_base != 0 || d.xb || d.x2b || d.gn_gamma) return false;
     if (d.Cin % 64 || d.C2 % 64 || d.Cin < 64) return false;
     r.P = d.Wout + 2;
     r.NR = (r.P - 1 + 127) / r.P + 1 + 2;          // rows a tile of 128 positions can touch, plus the two halo rows
@@ -362,6 +362,7 @@ int launch_tc(const TcOp& op, cudaStream_t s) {
     if (op.kind == 2) {
         static const bool no_pair = getenv("PNPF_NO_PAIR") != nullptr;
         const bool pair = !no_pair && op.pp.n_img % 2 == 0;
+        if (op.BN == 64) return pair ? launch_patch_t<64, true>(op, s) : launch_patch_t<64, false>(op, s);
         if (op.BN == 128) return pair ? launch_patch_t<128, true>(op, s) : launch_patch_t<128, false>(op, s);
         if (op.BN == 256) return pair ? launch_patch_t<256, true>(op, s) : launch_patch_t<256, false>(op, s);
         set_error("no patchconv instantiation for BN=%d", op.BN);

@@ -68,7 +68,7 @@ struct ConvDesc {
 };
 int prepare_conv(TcOp& op, const ConvDesc& d);
 bool rowconv_eligible(const ConvDesc& d);     // would prepare_conv pick the row-streaming kernel?
-bool patchconv_eligible(const ConvDesc& d);   // ... the patch-streaming kernel (3x3 stride 1, W <= 128, C_out 128 / 256)?
+bool patchconv_eligible(const ConvDesc& d);   // ... the patch-streaming kernel (3x3 stride 1, W <= 128, C_out 64 / 128 / 256)?
 int rowconv_max_smem();
 void describe_conv_impl(const ConvDesc& d, char* buf, size_t n);   // which kernel prepare_conv would pick (PNPF_PLAN_DUMP)
 

@@ -1,5 +1,5 @@
 // Patch-streaming 3x3 (stride 1) implicit-GEMM convolution for the NARROW, WIDE-CHANNEL levels of the U-Net (W <= 128,
-// C_out 128 / 256: the 64^2 and 32^2 levels and the nearest-up convs).  The per-tap kernel of pnpf_gemm.cuh fetches every
+// C_out 64 / 128 / 256: the 64^2 and 32^2 levels, the nearest-up convs and the level-1 blocks the row kernel cannot hold).  The per-tap kernel of pnpf_gemm.cuh fetches every
 // input pixel nine times and is bound by the L2 -> shared-memory fill; the row kernel of pnpf_rowconv.cuh needs W % 128 == 0
 // and resident weights.  Here the image is addressed in a PADDED-LINEAR space:
 //
@@ -42,7 +42,7 @@ struct PatchCfg {
     // [BN/2, BN)).  The epilogue is a per-warp latency chain (tcgen05.ld, bias / residual loads, statistics butterfly,
     // stores) of ~1200 clocks per 16 columns: with one warp set a 128 x 128 tile took longer to drain than to compute.
     static constexpr int THREADS = 11 * 32;
-    static_assert(BN == 128 || BN == 256, "patch conv is for wide outputs");
+    static_assert(BN == 64 || BN == 128 || BN == 256, "patch conv output widths");
 };
 
 template <int BN, bool PAIR>

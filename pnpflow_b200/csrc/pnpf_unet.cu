@@ -58,6 +58,7 @@ struct Op {
     int L = 0;
     const bf16* up_src = nullptr; // upsample
     int up_side = 0, up_C = 0;
+    std::string impl;             // kernel that runs the op (pnpf_debug_op_impl)
     double flops = 0;             // algorithmic 2*MAC per image (tensor-core ops)
     double bytes = 0;             // algorithmic HBM bytes per image: every operand read once + every output written once
     // debug view of the output (bf16 NHWC), C == 0 -> not readable
@@ -550,7 +551,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                       bf16* raw) {
         const int C = src.C1 + src.C2;
         Op a;
-        a.kind = Op::GN_APPLY; a.name = name; a.gsrc = src; a.HW = side * side;
+        a.kind = Op::GN_APPLY; a.name = name; a.gsrc = src; a.HW = side * side; a.impl = "gn_apply";
         if (real) { a.gamma = wptr<float>(e, wname + ".gamma"); a.beta = wptr<float>(e, wname + ".beta"); }
         a.silu = silu; a.dst = dst; a.raw_dst = raw;
         a.bytes = (raw ? 6.0 : 4.0) * C * side * side;
@@ -561,8 +562,13 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
         Op o;
         o.kind = Op::TC; o.name = name;
         d.B = Bm;
+        {
+            char buf[200];
+            describe_conv_impl(d, buf, sizeof(buf));
+            o.impl = buf;
+        }
         if (!real && getenv("PNPF_PLAN_DUMP")) {
-            char buf[160];
+            char buf[200];
             describe_conv_impl(d, buf, sizeof(buf));
             fprintf(stderr, "plan: %-44s %4dx%-4d Cin=%-3d C2=%-3d N=%-3d %s\n", name.c_str(), d.Hout, d.Wout, d.Cin, d.C2, d.n_valid, buf);
         }
@@ -579,6 +585,11 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
     auto add_gemm = [&](const std::string& name, GemmDesc d) -> int {
         Op o;
         o.kind = Op::TC; o.name = name;
+        {
+            char buf[96];
+            snprintf(buf, sizeof(buf), "conv_gemm<64,%d> gemm M=%d N=%d K=%d", d.N > 256 ? 256 : d.N, d.M, d.N, d.K);
+            o.impl = buf;
+        }
         d.batch = Bm;
         if (real) { if (int rc = prepare_gemm(o.tc, d)) return rc; }
         o.flops = 2.0 * (double)d.M * d.N * d.K;
@@ -895,6 +906,19 @@ extern "C" int pnpf_unet_forward(pnpf_engine* e, const float* x, const float* t,
 }
 
 extern "C" int pnpf_debug_num_ops(pnpf_engine* e) { return e ? (int)e->ops.size() : 0; }
+extern "C" const char* pnpf_debug_op_impl(pnpf_engine* e, int i) {
+    if (!e || i < 0 || i >= (int)e->ops.size()) return nullptr;
+    const Op& o = e->ops[i];
+    if (!o.impl.empty()) return o.impl.c_str();
+    switch (o.kind) {
+        case Op::MEMSET: return "cudaMemsetAsync";
+        case Op::IN_SHIM: return "nchw_to_nhwc_pad";
+        case Op::TEMB: return "temb";
+        case Op::SOFTMAX: return "softmax_rows";
+        case Op::UPSAMPLE: return "upsample2x";
+        default: return "?";
+    }
+}
 extern "C" const char* pnpf_debug_op_name(pnpf_engine* e, int i) {
     return (e && i >= 0 && i < (int)e->ops.size()) ? e->ops[i].name.c_str() : nullptr;
 }

@@ -164,7 +164,7 @@ class UNetEngine:
             kind, fl, by = C.c_int(), C.c_double(), C.c_double()
             _lib.check(self.lib.pnpf_debug_op_info(self._h, i, C.byref(kind), C.byref(fl), C.byref(by)))
             out.append(dict(name=name, kind="tc" if kind.value == 1 else "simt", ms=float(ms[i]),
-                            flops=fl.value * batch, bytes=by.value * batch))
+                            flops=fl.value * batch, bytes=by.value * batch, impl=self.lib.pnpf_debug_op_impl(self._h, i).decode()))
         return out
 
     def op_names(self):
