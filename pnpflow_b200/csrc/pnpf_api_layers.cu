@@ -73,7 +73,8 @@ extern "C" int pnpf_conv2d_nhwc(const void* x, int B, int Hin, int Win, int Cin,
                    "wait_patch %lld wait_weights %lld wait_tempty %lld | epi: total %lld wait_tfull %lld\n", h[2], h[0], h[1], h[12], h[13], h[4], h[5], h[7], h[6],
                    h[8], h[9]);
         if (op.kind == 1)
-            printf("   mma: issue %lld commit %lld | epi0: tmem_ld %lld tmem_st+arrive %lld stats_flush %lld\n", h[16], h[17], h[18], h[19], h[20]);
+            printf("   mma: issue %lld commit %lld | epi0: tmem_ld %lld tmem_st+arrive %lld math+stage %lld store %lld stats_flush %lld\n", h[16], h[17], h[18],
+                   h[19], h[22], h[23], h[20]);
         fflush(stdout);
         cudaFree(dbg);
     }
@@ -155,6 +156,7 @@ extern "C" int pnpf_gn_conv2d_nhwc(const void* xa, int Ca, const void* xb, int C
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
         printf("ROWCONV_GN_DBG producer: total %lld wait_empty %lld rows %lld | transform: total %lld wait_full %lld table %lld | mma: total %lld "
                "wait_ready %lld wait_tempty %lld | epi0: total %lld wait_tfull %lld\n", h[0], h[1], h[2], h[3], h[7], h[11], h[4], h[5], h[6], h[8], h[9]);
+        printf("   epi0: math+stage %lld store %lld\n", h[22], h[23]);
         printf("   mma: issue %lld commit %lld | epi0: tmem_ld %lld tmem_st+arrive %lld stats_flush %lld | transform: fence+arrive %lld\n", h[16], h[17], h[18],
                h[19], h[20], h[21]);
         fflush(stdout);

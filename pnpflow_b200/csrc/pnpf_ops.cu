@@ -39,6 +39,7 @@ static void fill_epi(EpiParams& e, const ConvDesc& d) {
 // Shared memory of the row kernel: 227 KB per CTA on sm_100 minus barriers/tables (RowCfg::BAR_BYTES) and alignment slack.
 constexpr int ROWCONV_SMEM_MAX = 227 * 1024;
 constexpr int ROWCONV_SMEM_BUDGET = ROWCONV_SMEM_MAX - 2048 - 1024;
+constexpr int ROWCONV_DUAL_SMEM = 110 * 1024;        // two CTAs per SM: 2 x (110 KB + 1 KB reserved) < 228 KB
 int rowconv_max_smem() { return ROWCONV_SMEM_MAX; }
 
 // Row-streaming kernel: shape analysis shared by rowconv_eligible() and the preparation.
@@ -67,14 +68,20 @@ static bool rowconv_shape(const ConvDesc& d, RowShape& r) {
         if (BN < 16 || (BN * rowb) % 1024 != 0) continue;        // stacked vertical-tap tiles must keep the swizzle phase
         const int w_tile = (BN * r.BK * 2 + 1023) / 1024 * 1024;
         const int w_bytes = 3 * r.kch * (3 * BN * rowb) + r.kch2 * w_tile;
-        // epilogue / transform warp split (RowCfg).  Measured (profiles/r01_ab_experiments.md): the fused GroupNorm transform takes
-        // the same time with 4 or 8 warps (it contends with the MMA operand reads for shared-memory bandwidth), while a single
-        // epilogue set is slower than two -> 8 epilogue + 4 transform warps everywhere.
-        const int n_epi = 8;
         // bf16 NHWC outputs with full 32-channel blocks are transposed through per-warp staging tiles (RowCfg::STAGE_BYTES)
-        const int stage = (d.out_mode == 0 && BN >= 32 && d.n_valid == d.N_pad && d.out_col_stride == 1) ? n_epi * 32 * 64 : 0;
-        int nslot = (ROWCONV_SMEM_BUDGET - w_bytes - stage) / r.slot_bytes;
-        if (nslot > 8) nslot = 8;
+        const bool staged = d.out_mode == 0 && BN >= 32 && d.n_valid == d.N_pad && d.out_col_stride == 1;
+        // Warp-role configuration (RowCfg): WIDE (n_epi = 12: 8 epilogue + 8 transform warps) for the fused-GroupNorm layers;
+        // DUAL (n_epi = 4: two half-sized CTAs per SM) is an opt-in experiment.  Both accumulate the output statistics in the
+        // staged store, so they need it (the only unstaged outputs without statistics are fp32 NCHW).
+        static const bool no_wide = getenv("PNPF_NO_WIDE") != nullptr;    // A/B switches (tools/ab_env.py)
+        static const bool want_dual = getenv("PNPF_ROW_DUAL") != nullptr;
+        const bool dual = want_dual && nsplit == 1 && r.kch == 1 && BN <= 32 && (staged || d.out_mode == 2);
+        const bool wide = !dual && !no_wide && staged && d.gn_gamma != nullptr;
+        const int n_epi = dual ? 4 : (wide ? 12 : 8);
+        const int n_epi_warps = dual ? 4 : 8;
+        const int stage = staged ? n_epi_warps * 32 * 64 : 0;
+        int nslot = ((dual ? ROWCONV_DUAL_SMEM - 2048 - 1024 : ROWCONV_SMEM_BUDGET) - w_bytes - stage) / r.slot_bytes;
+        if (nslot > (dual ? 6 : 8)) nslot = dual ? 6 : 8;
         if (nslot >= (nsplit == 1 ? 4 : 3)) {
             r.BN = BN; r.nsplit = nsplit; r.w_bytes = w_bytes; r.nslot = nslot; r.stage_bytes = stage; r.n_epi = n_epi;
             return true;
@@ -136,6 +143,7 @@ static int try_prepare_rowconv(TcOp& op, const ConvDesc& d) {
     r.nsplit = sh.nsplit;
     r.staged_store = sh.stage_bytes > 0;
     op.n_epi = sh.n_epi;
+    PNPF_REQUIRE(sh.n_epi == 8 || r.staged_store || !d.stats_out, "row conv (DUAL / WIDE): output statistics need the staged store");
     PNPF_REQUIRE((long long)d.B * r.strips * d.Hout < (1LL << 31) / 256, "row conv: batch * rows too large for 32-bit row indices");
     r.kchunks = sh.kch; r.kchunks2 = sh.kch2; r.nslot = sh.nslot; r.slot_bytes = sh.slot_bytes;
     r.kch_a = sh.kch_a; r.kch2_a = sh.kch2_a;
@@ -298,13 +306,36 @@ static int launch_row_t(const TcOp& op, cudaStream_t stream) {
                      Cfg::BAR_BYTES + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        PNPF_CHECK_CUDA(cudaFuncSetAttribute(rowconv_kernel<BK, BN, KCH, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowconv_max_smem()));
+        PNPF_CHECK_CUDA(cudaFuncSetAttribute(rowconv_kernel<BK, BN, KCH, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::DUAL ? ROWCONV_DUAL_SMEM : rowconv_max_smem()));
+        if (Cfg::DUAL)
+            PNPF_CHECK_CUDA(cudaFuncSetAttribute(rowconv_kernel<BK, BN, KCH, NEW>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                 cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    PNPF_REQUIRE(smem <= rowconv_max_smem(), "row conv shared memory %d exceeds the budget", smem);
+    PNPF_REQUIRE(smem <= (Cfg::DUAL ? ROWCONV_DUAL_SMEM : rowconv_max_smem()), "row conv shared memory %d exceeds the budget", smem);
+    // CTAs resident per SM: 1, or 2 for the DUAL configuration (each allocates Cfg::TMEM_COLS <= 512 / ctas_per_sm columns, so
+    // co-resident CTAs can never starve each other's tcgen05.alloc)
+    int ctas_per_sm = 1;
+    if (Cfg::DUAL) {
+        // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for EVERY kernel that contains tcgen05.alloc, whatever its
+        // resources, while the hardware does co-schedule such CTAs (tools/probes/tmem_occupancy_probe.cu: 2 x 148 CTAs with
+        // 256 columns each all run pairwise on one SM).  So the residency is computed here: shared memory (+ 1 KB reserved per
+        // CTA) against 228 KB, and registers per SM sub-partition (its 16 K registers hold ceil(warps / 4) warps of each CTA).
+        static int fit = -1;
+        if (fit < 0) {
+            cudaFuncAttributes fa;
+            PNPF_CHECK_CUDA(cudaFuncGetAttributes(&fa, rowconv_kernel<BK, BN, KCH, NEW>));
+            const int warps_pp = (Cfg::THREADS / 32 + 3) / 4;
+            fit = (2 * (ROWCONV_DUAL_SMEM + 1024) <= 228 * 1024 && 2 * warps_pp * 32 * fa.numRegs <= 16384 && 2 * Cfg::TMEM_COLS <= 512) ? 2 : 1;
+            if (getenv("PNPF_PLAN_DUMP"))
+                fprintf(stderr, "[pnpf] rowconv<%d,%d,%d> DUAL: %d registers, %d TMEM columns -> %d CTAs/SM\n", BK, BN, KCH, fa.numRegs, Cfg::TMEM_COLS, fit);
+        }
+        ctas_per_sm = fit;
+    }
     // one CTA group (nsplit CTAs) per contiguous range of the flattened row space; at least 8 rows per range
     const long long rows = (long long)r.n_img * r.strips * r.H;
-    long long groups = num_sms() / r.nsplit;
+    long long groups = (long long)num_sms() * ctas_per_sm / r.nsplit;
     if (groups > (rows + 7) / 8) groups = (rows + 7) / 8;
     const int grid = (int)groups * r.nsplit;
     if (grid < 1) return 0;
@@ -375,6 +406,11 @@ int launch_tc(const TcOp& op, cudaStream_t s) {
         if (op.rp.kchunks == 2) return launch_row_t<bk, bn, 2, ne>(op, s);                \
         if (op.rp.kchunks == 3) return launch_row_t<bk, bn, 3, ne>(op, s);                \
     }
+#define PNPF_RDUAL(bk, bn) \
+    if (op.BK == bk && op.BN == bn && op.n_epi == 4 && op.rp.kchunks == 1) return launch_row_t<bk, bn, 1, 4>(op, s);
+        PNPF_RDUAL(32, 16) PNPF_RDUAL(32, 32) PNPF_RDUAL(64, 16) PNPF_RDUAL(64, 32)
+#undef PNPF_RDUAL
+        PNPF_RCASE(32, 32, 12) PNPF_RCASE(32, 64, 12) PNPF_RCASE(64, 32, 12) PNPF_RCASE(64, 64, 12)
         PNPF_RCASE(32, 16, 8) PNPF_RCASE(32, 32, 8) PNPF_RCASE(32, 64, 8) PNPF_RCASE(64, 16, 8) PNPF_RCASE(64, 32, 8) PNPF_RCASE(64, 64, 8)
 #undef PNPF_RCASE
         set_error("no rowconv instantiation for BK=%d BN=%d epilogue warps %d", op.BK, op.BN, op.n_epi);

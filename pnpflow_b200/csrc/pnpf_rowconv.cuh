@@ -62,25 +62,47 @@ struct RowCfg {
     static constexpr int KH_BYTES = BN * kRowBytes;                         // one vertical tap inside a stacked tile
     static constexpr int W_STACK = 3 * KH_BYTES;                            // [kh][BN][BK] weights of one (kw, chunk)
     static_assert(KH_BYTES % 1024 == 0, "stacked tap tiles must keep the swizzle phase");
-    static constexpr int NACC = (512 / BN) > 16 ? 16 : (512 / BN);
-    static constexpr int TMEM_COLS = NACC * BN;              // 256 (BN=16) or 512
+    // Warp-role configurations (third template argument):
+    //   8  : 8 epilogue warps (two sets) + 4 GroupNorm-transform warps, 128 registers            (no fused GroupNorm: transform idle)
+    //   12 : WIDE = 8 epilogue + 8 transform warps, 96 registers — for the fused-GroupNorm layers, where the 4-warp transform
+    //        (one latency chain per scheduler: ld.shared -> unpack -> fma -> tanh -> pack -> st.shared, issuing 26 % of the time)
+    //        is as slow as the MMA issuer
+    //   4  : DUAL = two CTAs per SM, each 4 epilogue + 4 transform warps, 256 TMEM columns, 80 registers (experiment: measured
+    //        slower, opt-in with PNPF_ROW_DUAL=1; profiles/r01_ab_experiments.md)
+    static constexpr bool DUAL = NEW_ == 4;
+    static constexpr bool WIDE = NEW_ == 12;
+    static constexpr int MIN_CTAS = DUAL ? 2 : 1;
+    // Below 128 registers the per-thread GroupNorm statistics of the output (2 x 32 accumulators) would spill, so they are
+    // accumulated in the READ phase of the staged store instead (a lane sees 8 channels of 4 pixels per row: 16 accumulators), on
+    // the bf16 values that are actually stored — exactly the tensor the next GroupNorm normalises.  The host selects these
+    // configurations only together with the staged store.
+    static constexpr bool STAGED_STATS = DUAL || WIDE;
+    static constexpr int TMEM_BUDGET = DUAL ? 256 : 512;
+    static constexpr int NACC = (TMEM_BUDGET / BN) > 16 ? 16 : (TMEM_BUDGET / BN);
+    static constexpr int TMEM_COLS = NACC * BN;              // 256 (BN=16 or DUAL) or 512
     static constexpr int MAX_SLOTS = 8;
-    // 12 worker warps besides the producer and the MMA issuer, split between the epilogue (sets of 4 warps, one per TMEM lane
-    // quarter) and the GroupNorm transform.  Both are per-warp LATENCY chains (barrier wait, tcgen05.ld/st round trips or
-    // ld/st.shared + fence.proxy.async).  NEW = 8 (two epilogue sets: alternate rows for BN <= 32, split columns for BN = 64,
-    // 4 transform warps) is what the host uses; NEW = 4 (one set, 8 transform warps) measured the same or slower because the
-    // transform is limited by shared-memory bandwidth, not by its warp count (profiles/r01_ab_experiments.md).
-    static constexpr int NEW = NEW_;
+    // Worker warps besides the producer and the MMA issuer: NEW epilogue warps (sets of 4, one warp per TMEM lane quarter) and
+    // 4 GroupNorm-transform warps.  Both are per-warp LATENCY chains (barrier wait, tcgen05.ld/st round trips or ld/st.shared +
+    // fence.proxy.async).  NEW = 8: two epilogue sets (alternate rows for BN <= 32, split columns for BN = 64).  One set + 8
+    // transform warps in ONE CTA measured the same or slower: the transform is limited by shared-memory bandwidth, not by its
+    // warp count (profiles/r01_ab_experiments.md).
+    static constexpr int NEW = WIDE ? 8 : NEW_;
     static_assert(NEW == 4 || NEW == 8, "epilogue warps");
     static_assert(BN <= 32 || NEW == 8, "C_out = 64 needs two epilogue sets");
+    static_assert(NACC >= 8, "accumulator ring too shallow");
     static constexpr bool ROW_SPLIT = BN <= 32 && NEW == 8;  // the two sets alternate rows (else set s owns columns [32 s, 32 s + 32))
-    static constexpr int NTW = 12 - NEW;                     // transform warps
+    static constexpr int NTW = WIDE ? 8 : 4;                 // transform warps
     // bf16 NHWC outputs are transposed through a per-warp staging tile (32 pixels x 64 bytes, 64B-swizzled): a lane packs its
     // pixel's 32 channels with four conflict-free st.shared.v4, then the warp stores eight whole 64-byte pixel rows per
     // instruction (per-lane 16-byte stores at a 64/128-byte stride cost one L1 wavefront per lane).  Warp-local: no barrier.
     static constexpr int STAGE_WARP = 32 * 64;
     static constexpr int STAGE_BYTES = BN >= 32 ? NEW * STAGE_WARP : 0;
-    static constexpr int THREADS = 64 + 12 * 32;
+    static constexpr int THREADS = 64 + (NEW + NTW) * 32;
+    // Register budget: the register file is split over the four SM sub-partitions (16 K registers each) and the 10 warps of a
+    // DUAL CTA land 3/3/2/2 on them, so two co-resident CTAs need 6 warps x 32 x regs <= 16384 -> 80 registers per thread
+    // (a bound of 96, which 2 x 320 threads would suggest, leaves ONE CTA per SM).  Declaring 384 threads makes ptxas pick 80.
+    // WIDE: 18 warps are allocated as 5 per sub-partition -> 5 x 32 x regs <= 16384 -> 96 registers (= the bound of 640 threads).
+    static constexpr int BOUND_THREADS = DUAL ? 384 : (WIDE ? 640 : THREADS);
     static constexpr int CPT = BN > 32 ? 32 : BN;            // columns per epilogue thread
     static constexpr int BAR_BYTES = 2048;                   // barriers + tmem slot | bias staging (2 x 64 floats) | GN scale/shift (2 x 128)
     static_assert(BN == 16 || BN == 32 || BN == 64, "row conv is for thin outputs");
@@ -122,6 +144,12 @@ __device__ __forceinline__ uint4 lds128_nc(uint32_t saddr) {
 __device__ __forceinline__ void sts128_nc(uint32_t saddr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
+// named barrier of epilogue warp set 0 / 1 (128 threads).  The id must be an immediate: with a register id ptxas reserves all
+// 16 hardware barriers for the CTA and a second CTA can never become resident on the SM.
+__device__ __forceinline__ void bar_sync_set(int set) {
+    if (set == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
 // one lane polls, the warp follows
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
     if (lane == 0) mbar_wait(bar, parity);
@@ -129,7 +157,7 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
 }
 
 template <int BK, int BN, int KCH, int NEW_>
-__global__ void __launch_bounds__(RowCfg<BK, BN, NEW_>::THREADS, 1)
+__global__ void __launch_bounds__(RowCfg<BK, BN, NEW_>::BOUND_THREADS, RowCfg<BK, BN, NEW_>::MIN_CTAS)
 rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAb,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA2b,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ RowConvParams p) {
@@ -474,20 +502,19 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ethread = threadIdx.x - 64;         // 0..255
         const int colbase = Cfg::ROW_SPLIT ? 0 : set * 32;   // column split: set 1 takes columns 32..63 of C_out = 64
         float* bsm = bias_sm + set * 64;
-        const uint32_t set_bar = 1 + set;             // named barrier id of this warp set (128 threads)
         // staging tile of this warp: write phase = own pixel row, read phase = 8 pixels x 4 chunks per instruction
         const uint32_t stage_w = smem_u32(stage) + (warp - 2) * Cfg::STAGE_WARP;
         const uint32_t st_wr = stage_w + lane * 64, st_wr_sw = static_cast<uint32_t>((lane >> 1) & 3);
         const int rd_pix = lane >> 2, rd_chunk = lane & 3;
         uint32_t g0 = 0;
-        long long c_tfull = 0, c_rows = 0, c_ld = 0, c_st = 0, c_fin = 0;
+        long long c_tfull = 0, c_rows = 0, c_ld = 0, c_st = 0, c_fin = 0, c_math = 0, c_out = 0;
         const long long c_start = PNPF_CLK();
         for (int row = row_begin; row < row_end;) {
             int img, hb, he, w0;
             decode(row, img, hb, he, w0);
             row += he - hb;
             // stage bias (+ per-image time-embedding row) of this item once
-            asm volatile("bar.sync %0, 128;" ::"r"(set_bar));          // previous item's readers are done
+            bar_sync_set(set);          // previous item's readers are done
             {
                 const int c = (ethread & 127);
                 if (c < BN) {
@@ -499,10 +526,11 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     bsm[c] = b;
                 }
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(set_bar));
-            float ssum[CPT], ssq[CPT];
+            bar_sync_set(set);
+            constexpr int NST = Cfg::STAGED_STATS ? 8 : CPT;
+            float ssum[NST], ssq[NST];
 #pragma unroll
-            for (int q = 0; q < CPT; ++q) ssum[q] = ssq[q] = 0.f;
+            for (int q = 0; q < NST; ++q) ssum[q] = ssq[q] = 0.f;
             for (int r = hb + (Cfg::ROW_SPLIT ? set : 0); r < he; r += (Cfg::ROW_SPLIT ? 2 : 1)) {
                 const uint32_t g = g0 + static_cast<uint32_t>(r - hb);
                 const uint32_t acc = g % NACC;
@@ -558,11 +586,13 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                     }
-                    if (p.epi.stats) {
+                    if constexpr (!Cfg::STAGED_STATS) {
+                        if (p.epi.stats) {
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            ssum[q * 16 + jj] += v[jj];
-                            ssq[q * 16 + jj] = fmaf(v[jj], v[jj], ssq[q * 16 + jj]);
+                            for (int jj = 0; jj < 16; ++jj) {
+                                ssum[q * 16 + jj] += v[jj];
+                                ssq[q * 16 + jj] = fmaf(v[jj], v[jj], ssq[q * 16 + jj]);
+                            }
                         }
                     }
                     if constexpr (CPT == 32) {
@@ -580,6 +610,8 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     epilogue_store16(p.epi, img, pix, gcol0, v);
                 }
+                const long long c_e3 = PNPF_CLK();
+                c_math += c_e3 - c_e2;
                 if constexpr (CPT == 32) {
                     if (p.staged_store) {
                         __syncwarp();
@@ -594,12 +626,51 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(orow + (i * 8 + rd_pix) * p.epi.out_row_stride) = o4[i];
+                        if constexpr (Cfg::STAGED_STATS) {
+                            if (p.epi.stats) {             // channels 8 rd_chunk .. + 7 of pixels rd_pix, 8 + rd_pix, ...
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const uint32_t ww[4] = {o4[i].x, o4[i].y, o4[i].z, o4[i].w};
+#pragma unroll
+                                    for (int e2 = 0; e2 < 4; ++e2) {
+                                        const float f0 = __uint_as_float(ww[e2] << 16), f1 = __uint_as_float(ww[e2] & 0xFFFF0000u);
+                                        ssum[2 * e2] += f0;
+                                        ssq[2 * e2] = fmaf(f0, f0, ssq[2 * e2]);
+                                        ssum[2 * e2 + 1] += f1;
+                                        ssq[2 * e2 + 1] = fmaf(f1, f1, ssq[2 * e2 + 1]);
+                                    }
+                                }
+                            }
+                        }
                         __syncwarp();                                  // the tile is rewritten by the next row
                     }
                 }
+                c_out += PNPF_CLK() - c_e3;
             }
             const long long c_f0 = PNPF_CLK();
-            if (p.epi.stats) {
+            if constexpr (Cfg::STAGED_STATS) {
+                if (p.epi.stats) {
+                    // the 8 lanes with the same rd_chunk hold partial sums of the same 8 channels: xor-reduce over lane bits 2..4,
+                    // then lane (rd_pix = e) adds channel 8 rd_chunk + e
+#pragma unroll
+                    for (int bit = 4; bit <= 16; bit <<= 1)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            ssum[e] += __shfl_xor_sync(0xffffffffu, ssum[e], bit);
+                            ssq[e] += __shfl_xor_sync(0xffffffffu, ssq[e], bit);
+                        }
+                    float ts = 0.f, tq = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (rd_pix == e) { ts = ssum[e]; tq = ssq[e]; }
+                    const int c = n_off + colbase + rd_chunk * 8 + rd_pix;
+                    if (c < p.epi.n_valid) {
+                        double* sp2 = p.epi.stats + (static_cast<long long>(img) * p.epi.n_valid + c) * 2;
+                        atomicAdd(sp2, static_cast<double>(ts));
+                        atomicAdd(sp2 + 1, static_cast<double>(tq));
+                    }
+                }
+            } else if (p.epi.stats) {
 #pragma unroll
                 for (int q = 0; q < CPT / 16; ++q) {
                     const int col0 = n_off + colbase + q * 16;
@@ -631,7 +702,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             g0 += static_cast<uint32_t>(he - hb);
             c_fin += PNPF_CLK() - c_f0;
         }
-        if (p.dbg && blockIdx.x == 0 && ethread == 0) { p.dbg[18] = c_ld; p.dbg[19] = c_st; p.dbg[20] = c_fin; }
+        if (p.dbg && blockIdx.x == 0 && ethread == 0) { p.dbg[18] = c_ld; p.dbg[19] = c_st; p.dbg[20] = c_fin; p.dbg[22] = c_math; p.dbg[23] = c_out; }
         if (p.dbg && blockIdx.x == 0 && ethread == 0) { p.dbg[8] = PNPF_CLK() - c_start; p.dbg[9] = c_tfull; p.dbg[10] = c_rows; }
         if (p.dbg && blockIdx.x == 0 && ethread == 128 && Cfg::NEW == 8) { p.dbg[12] = PNPF_CLK() - c_start; p.dbg[13] = c_tfull; p.dbg[14] = c_rows; }
     }
