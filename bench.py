@@ -11,6 +11,7 @@ Workload at every N: cfg4 of BASELINE.json (AFHQ-Cat 256x256x3, 4x super-resolut
 reference default of config/method_config/pnp_flow.yaml), 16 images per GPU (128 over 8) -> weak scaling.
 
 engine arm:      pnpflow_b200 (hand-written sm_100a CUDA behind the C ABI), bf16 tensor-core operands / fp32 accumulate.
+torch_gpu_baseline: the reference's own GPU path like for like (oracle port, eager PyTorch + cuDNN TF32 on the same B200).
 reference arm:   the reference algorithm on the host CPU cores (oracle port; the reference itself is pure PyTorch and
                  its tree does not exist on the GPU box), rank 0 only, a bounded sample extrapolated linearly.
 """
@@ -142,6 +143,48 @@ def cpu_reference(cfgname, steps, warmup):
     return dict(value=value, per_step_s=per_step, cores=cores, sample=sample, batch=Bs)
 
 
+def torch_gpu_reference(cfgname, steps, warmup, dev):
+    """The reference's own GPU path, like for like: the oracle port of PNP_FLOW.solve_ip + UNet.forward run
+    EAGERLY in PyTorch on the same B200 (cuDNN convolutions with TF32 allowed = the reference's defaults, S sequential U-Net
+    passes per step at the config's per-GPU batch).  A reported baseline next to cpu_baseline, never on the product path."""
+    import oracle
+    c = CONFIGS[cfgname]
+    ocfg = oracle.AFHQ_256 if c["net"] == "afhq256" else oracle.CELEBA_128
+    side, B = ocfg.input_height, c["b_per_gpu"]
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = True, False      # torch defaults = reference
+    sd = {k: v.to(dev) for k, v in oracle.init_state_dict(ocfg, seed=0).items()}
+    deg, sigma, alpha = oracle.make_degradation(c["problem"], side, 3, dev)
+    g = torch.Generator().manual_seed(1234)
+    clean = (torch.rand(B, 3, side, side, generator=g) * 2 - 1).to(dev)
+    y = oracle.loop.synthesize_measurement(clean, deg.H, sigma, 0)
+    ev = []
+
+    class _Stop(Exception):
+        pass
+
+    def trace(it, x):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        ev.append(e)
+        if it + 1 >= warmup + steps:
+            raise _Stop()
+    try:
+        oracle.pnp_flow_restore(lambda a, b: oracle.unet_forward(sd, ocfg, a, b), y, deg, sigma, steps_pnp=c["T"],
+                                num_samples=c["S"], alpha=alpha, trace=trace)
+    except _Stop:
+        pass
+    torch.cuda.synchronize()
+    per_step_ms = ev[warmup - 1].elapsed_time(ev[-1]) / steps
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    del sd
+    torch.cuda.empty_cache()
+    return {"value": B / (c["T"] * per_step_ms / 1e3), "unit": UNIT, "ms_per_step": per_step_ms, "kind": "port",
+            "what": "oracle port of the reference loop + U-Net, eager PyTorch fp32 on this GPU (cuDNN, TF32 allowed = reference defaults), "
+                    f"batch {B}, S={c['S']} sequential passes per step",
+            "sample": f"{steps} PnP steps after {warmup} warm-up, extrapolated linearly to T={c['T']}"}
+
+
 # ------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -152,6 +195,7 @@ def main():
     ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     a = ap.parse_args()
     K, W = a.steps, max(a.warmup, 3 if a.impl == "engine" else 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -361,12 +405,19 @@ def main():
         r = cpu_reference(a.config, a.cpu_steps, 1)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
+    tgpu = None
+    if not a.no_gpu_baseline and world == 1:
+        try:
+            tgpu = torch_gpu_reference(a.config, 3, 2, dev)
+        except Exception as ex:                        # a reported extra: never fail the bench line over it
+            tgpu = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "impl": "engine", "config": cfg_desc, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": y_host.numel() * 4, "d2h_bytes_per_step": x_host.numel() * 4,
                     "ms_per_step": ms_e / K},
-            "gpu_launches": K * sess.launches_per_step, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": K * sess.launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "torch_gpu_baseline": tgpu,
             "finite": finite, "unet_flops_per_image": eng.flops_per_image, "unet_launches_per_eval": eng.num_launches,
             "unet_graph_replay_ms": unet_replay_ms, "scatter_ms": scatter_ms, "gather_ms": gather_ms, "workspace_gb": eng.workspace_bytes / 2 ** 30}
     print(json.dumps(line), flush=True)

@@ -46,6 +46,7 @@ struct RowConvParams {
     const float* gn_beta;
     const double* gn_st_a; // [img][Ca][2]
     const double* gn_st_b; // [img][Cb][2]
+    int mma2;              // 1: two MMA-issuing warps on alternate input rows (RowCfg::NMMA == 2 only)
     int staged_store;      // bf16 NHWC output through the per-warp staging tiles (coalesced); else per-thread global stores
     long long* dbg;        // optional [32] cycle counters of CTA 0 (profiling experiments), else nullptr
     EpiParams epi;
@@ -97,7 +98,11 @@ struct RowCfg {
     // instruction (per-lane 16-byte stores at a 64/128-byte stride cost one L1 wavefront per lane).  Warp-local: no barrier.
     static constexpr int STAGE_WARP = 32 * 64;
     static constexpr int STAGE_BYTES = BN >= 32 ? NEW * STAGE_WARP : 0;
-    static constexpr int THREADS = 64 + (NEW + NTW) * 32;
+    // WIDE also has a SECOND MMA-issuing warp (the last warp of the CTA): the two issuers take alternate input rows, which halves
+    // the per-row cost of the single issuing thread (6 MMAs + commits + barrier waits ~ 950 clocks per row: the limit of the
+    // 32 -> 32 layers once the transform has 8 warps).  RowConvParams::mma2 = 0 leaves the second warp idle (A/B switch).
+    static constexpr int NMMA = WIDE ? 2 : 1;
+    static constexpr int THREADS = 64 + (NEW + NTW) * 32 + (NMMA - 1) * 32;
     // Register budget: the register file is split over the four SM sub-partitions (16 K registers each) and the 10 warps of a
     // DUAL CTA land 3/3/2/2 on them, so two co-resident CTAs need 6 warps x 32 x regs <= 16384 -> 80 registers per thread
     // (a bound of 96, which 2 x 320 threads would suggest, leaves ONE CTA per SM).  Declaring 384 threads makes ptxas pick 80.
@@ -178,11 +183,13 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tempty_bar = tfull_bar + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 16);
     uint64_t* ready_bar = tempty_bar + 17;                          // [MAX_SLOTS] transform -> MMA (GroupNorm fusion)
+    uint64_t* issued_bar = ready_bar + Cfg::MAX_SLOTS;              // [2] MMA issuer k has issued the MMAs of its n-th row (bytes 464..479)
     float* bias_sm = reinterpret_cast<float*>(bars) + 128;          // [2 sets][64] floats at byte offset 512
     float* gn_tab = reinterpret_cast<float*>(bars) + 256;           // scale[128] | shift[128] at byte offset 1024
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int n_mma = (Cfg::NMMA == 2 && p.mma2) ? 2 : 1;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -196,8 +203,10 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&empty_bar[s], 1);
             mbar_init(&ready_bar[s], Cfg::NTW);
         }
+        mbar_init(&issued_bar[0], 1);
+        mbar_init(&issued_bar[1], 1);
         for (int a = 0; a < 16; ++a) {
-            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tfull_bar[a], n_mma);   // one tcgen05.commit per contributing issuer
             mbar_init(&tempty_bar[a], Cfg::ROW_SPLIT ? 4 : Cfg::NEW);
         }
         fence_barrier_init();
@@ -281,9 +290,21 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[0] = PNPF_CLK() - c_start; p.dbg[1] = c_wait; p.dbg[2] = c_rows; }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ===================== MMA issuer (converged warp, elected lane issues) =====================
-        {
+    } else if (warp == 1 || warp == 2 + Cfg::NEW + Cfg::NTW) {
+        // ===================== MMA issuer(s) (converged warp, elected lane issues) =====================
+        // With two issuers (n_mma == 2) warp 1 takes the even and the last warp the odd input rows of the running row sequence.
+        // The MMAs themselves are still ISSUED in row order (issuer of row q waits on issued_bar until row q-1 has been issued,
+        // with tcgen05 fences on both sides), so every accumulator receives its taps in the same order as with one issuer and
+        // the results stay bit-reproducible; what overlaps is everything around the issue: barrier waits, commits, bookkeeping
+        // (~ 600 of the ~ 1000 clocks one issuer spends per row).  Who signals what:
+        //   * output row r receives taps from input rows r-1 (kh = 0), r (kh = 1), r+1 (kh = 2); rows r-1 and r+1 belong to one
+        //     issuer, row r to the other, and a tcgen05.commit only covers the MMAs of the committing thread.  tfull[r] therefore
+        //     expects two arrivals: the issuer of row r commits to it after its centre tap, the other one after row r+1 (its last
+        //     tap; at the bottom image edge, where row r+1 does not exist, after row r-1);
+        //   * each issuer waits for the drained (re-zeroed) accumulator before ITS first tap into it: rows j+1 and j every row,
+        //     row j-1 only at the top of an item (otherwise it touched that accumulator two rows ago).
+        const int mw = warp == 1 ? 0 : 1;
+        if (mw < n_mma) {
             // descriptor words: hi is shared by every operand tile; lo = (addr >> 4) | LBO bit
             const uint64_t proto = make_smem_desc<Cfg::kRowBytes>(0);
             const uint32_t desc_hi = static_cast<uint32_t>(proto >> 32);
@@ -297,8 +318,10 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t s_base_lo = (smem_u32(slots) >> 4) | lo_flags;
             const uint32_t slot16 = static_cast<uint32_t>(p.slot_bytes) >> 4;
             const uint32_t kch2 = p.kchunks2;
+            const bool two = n_mma == 2;
             uint32_t slot = 0, phase = 0;
             uint32_t g0 = 0;                           // running output-row counter (selects the accumulator)
+            uint32_t q = 0;                            // running input-row counter (selects the issuer)
             long long c_full = 0, c_tempty = 0, c_issue = 0, c_commit = 0;
             const long long c_start = PNPF_CLK();
             for (int row = row_begin; row < row_end;) {
@@ -306,7 +329,8 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 decode(row, img, hb, he, w0);
                 row += he - hb;
                 const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
-                for (int j = j0; j <= j1; ++j) {
+                for (int j = j0; j <= j1; ++j, ++q) {
+                    if (!two || (q & 1u) == static_cast<uint32_t>(mw)) {
                     // taps kh = 0,1,2 feed output rows j+1, j, j-1; the valid ones are contiguous in kh
                     const int k0 = (j + 1 < he) ? 0 : ((j < he) ? 1 : 2);
                     const int k1 = (j - 1 >= hb) ? 2 : ((j >= hb) ? 1 : 0);
@@ -318,12 +342,25 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // taps k0.. occupy blocks blk0, blk0+1, ... until the ring wraps at NACC
                     const uint32_t n0 = min(ntap, static_cast<uint32_t>(NACC) - blk0);
                     const uint32_t n1 = ntap - n0;                                                  // wrapped part starts at block 0
-                    if (k0 == 0)                       // tap 0 opens a fresh accumulator (row j+1): it must have been drained
-                        PNPF_TIMED_WAIT(&tempty_bar[acc_top], ((g_top / NACC) & 1) ^ 1, c_tempty);
-                    if (j == 0)                        // top image row (hb == 0): row 0 is opened by its centre tap
-                        PNPF_TIMED_WAIT(&tempty_bar[g0 % NACC], ((g0 / NACC) & 1) ^ 1, c_tempty);
+                    if (!two) {
+                        if (k0 == 0)                   // tap 0 opens a fresh accumulator (row j+1): it must have been drained
+                            PNPF_TIMED_WAIT(&tempty_bar[acc_top], ((g_top / NACC) & 1) ^ 1, c_tempty);
+                        if (j == 0)                    // top image row (hb == 0): row 0 is opened by its centre tap
+                            PNPF_TIMED_WAIT(&tempty_bar[g0 % NACC], ((g0 / NACC) & 1) ^ 1, c_tempty);
+                    } else {
+                        // first tap of THIS issuer into the accumulators of rows j+1 and j (and j-1 at the top of the item)
+                        const int r_lo = (j - 2 >= j0) ? j : j - 1;
+                        for (int r = j + 1; r >= r_lo; --r)
+                            if (r >= hb && r < he) {
+                                const uint32_t g = g0 + static_cast<uint32_t>(r - hb);
+                                PNPF_TIMED_WAIT(&tempty_bar[g % NACC], ((g / NACC) & 1) ^ 1, c_tempty);
+                            }
+                    }
                     tc_fence_after();
                     PNPF_TIMED_WAIT(p.gn ? &ready_bar[slot] : &full_bar[slot], phase, c_full);
+                    if (two && q > 0) {                // row q-1 (other issuer, its row number (q-1)/2) has been issued
+                        mbar_wait(&issued_bar[mw ^ 1], ((q - 1) >> 1) & 1);
+                    }
                     tc_fence_after();
                     const long long c_i0 = PNPF_CLK();
                     const uint32_t s_lo0 = s_base_lo + slot * slot16;
@@ -358,19 +395,31 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 w2 += WT16;
                             }
                         }
+                        if (two) {                         // hand the issue order to the other warp before the (slow) commits
+                            tc_fence_before();
+                            mbar_arrive(&issued_bar[mw]);
+                        }
                         const long long c_i1 = PNPF_CLK();
                         c_issue += c_i1 - c_i0;
                         umma_commit(&empty_bar[slot]);     // the row slot can be refilled once these MMAs retire
-                        if (j - 1 >= hb && j - 1 < he) umma_commit(&tfull_bar[(g0 + static_cast<uint32_t>(j - 1 - hb)) % NACC]);
-                        if (j == p.H - 1 && j >= hb && j < he) umma_commit(&tfull_bar[(g0 + static_cast<uint32_t>(j - hb)) % NACC]);
+                        const bool out_c = j >= hb && j < he, out_m = j - 1 >= hb && j - 1 < he;
+                        if (out_m) umma_commit(&tfull_bar[(g0 + static_cast<uint32_t>(j - 1 - hb)) % NACC]);     // last tap of row j-1
+                        if (!two) {
+                            if (j == p.H - 1 && out_c) umma_commit(&tfull_bar[(g0 + static_cast<uint32_t>(j - hb)) % NACC]);
+                        } else {
+                            if (out_c) umma_commit(&tfull_bar[(g0 + static_cast<uint32_t>(j - hb)) % NACC]);     // this issuer's only tap of row j
+                            if (j + 1 == p.H - 1 && j + 1 < he)      // bottom image edge: no row j+2 will carry the second arrival of row j+1
+                                umma_commit(&tfull_bar[(g0 + static_cast<uint32_t>(j + 1 - hb)) % NACC]);
+                        }
                         c_commit += PNPF_CLK() - c_i1;
                     }
                     __syncwarp();
+                    }
                     if (++slot == static_cast<uint32_t>(p.nslot)) { slot = 0; phase ^= 1; }
                 }
                 g0 += static_cast<uint32_t>(he - hb);
             }
-            if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[4] = PNPF_CLK() - c_start; p.dbg[5] = c_full; p.dbg[6] = c_tempty; p.dbg[16] = c_issue; p.dbg[17] = c_commit; }
+            if (p.dbg && blockIdx.x == 0 && lane == 0 && mw == 0) { p.dbg[4] = PNPF_CLK() - c_start; p.dbg[5] = c_full; p.dbg[6] = c_tempty; p.dbg[16] = c_issue; p.dbg[17] = c_commit; }
         }
         __syncwarp();
     } else if (warp >= 2 + Cfg::NEW) {
