@@ -366,13 +366,12 @@ def main():
                         "frac_of_roof": f["roof_ms"] / f["ms"]})
     dom = kernels[0]
     domf = fams[dom["kernel"]]
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (tools/summarize_profiles.py), per launch
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_dominant_kernel_dram_bytes.json")
+    tp = os.path.join(ROOT, "profiles", "r01_kernel_dram_bytes.json")
     if os.path.exists(tp):
         try:
-            tj = json.load(open(tp))
-            if tj.get("kernel") == dom["kernel"]:
-                traffic = tj.get("dram_bytes_per_launch_mean")
+            traffic = json.load(open(tp))["kernels"].get(dom["kernel"], {}).get("dram_bytes_per_launch_mean")
         except Exception:
             traffic = None
     tc = [o for o in prof if o["kind"] == "tc"]
@@ -389,6 +388,7 @@ def main():
     roofline = {"bound": dom["bound"], "kernel": dom["kernel"], "achieved": r_ach, "peak": r_peak, "unit": r_unit,
                 "frac": r_ach / r_peak if r_peak else None, "traffic": traffic, "peak_source": pk["src"],
                 "launches": dom["launches"], "avg_launch_ms": domf["ms"] / domf["launches"], "algorithmic_per_launch": per_launch,
+                "algorithmic_bytes_per_launch": domf["bytes"] / domf["launches"],
                 "share_of_unet_eval": dom["share"],
                 "kernels": kernels,
                 "step_frac_of_roof": sum(f["roof_ms"] for f in fams.values()) / total_ms,

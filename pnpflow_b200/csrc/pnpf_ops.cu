@@ -144,7 +144,7 @@ static int try_prepare_rowconv(TcOp& op, const ConvDesc& d) {
     r.staged_store = sh.stage_bytes > 0;
     op.n_epi = sh.n_epi;
     static const bool no_mma2 = getenv("PNPF_NO_MMA2") != nullptr;       // A/B switch (tools/ab_env.py)
-    r.mma2 = (sh.n_epi == 12 && !no_mma2 && d.Hout >= 2) ? 1 : 0;         // second MMA-issuing warp (RowCfg::NMMA)
+    r.mma2 = (sh.n_epi != 4 && !no_mma2 && d.Hout >= 2) ? 1 : 0;         // second MMA-issuing warp (RowCfg::NMMA)
     PNPF_REQUIRE(sh.n_epi == 8 || r.staged_store || !d.stats_out, "row conv (DUAL / WIDE): output statistics need the staged store");
     PNPF_REQUIRE((long long)d.B * r.strips * d.Hout < (1LL << 31) / 256, "row conv: batch * rows too large for 32-bit row indices");
     r.kchunks = sh.kch; r.kchunks2 = sh.kch2; r.nslot = sh.nslot; r.slot_bytes = sh.slot_bytes;

@@ -98,10 +98,11 @@ struct RowCfg {
     // instruction (per-lane 16-byte stores at a 64/128-byte stride cost one L1 wavefront per lane).  Warp-local: no barrier.
     static constexpr int STAGE_WARP = 32 * 64;
     static constexpr int STAGE_BYTES = BN >= 32 ? NEW * STAGE_WARP : 0;
-    // WIDE also has a SECOND MMA-issuing warp (the last warp of the CTA): the two issuers take alternate input rows, which halves
-    // the per-row cost of the single issuing thread (6 MMAs + commits + barrier waits ~ 950 clocks per row: the limit of the
-    // 32 -> 32 layers once the transform has 8 warps).  RowConvParams::mma2 = 0 leaves the second warp idle (A/B switch).
-    static constexpr int NMMA = WIDE ? 2 : 1;
+    // A SECOND MMA-issuing warp (the last warp of the CTA): the two issuers take alternate input rows, which overlaps the
+    // barrier waits, commits and bookkeeping of one row (~ 600 of the ~ 1000 clocks a single issuer spends per row: the limit of
+    // the 32 -> 32 layers once the transform has 8 warps) with the MMA issue of the next.  RowConvParams::mma2 = 0 leaves the
+    // second warp idle (A/B switch).
+    static constexpr int NMMA = DUAL ? 1 : 2;
     static constexpr int THREADS = 64 + (NEW + NTW) * 32 + (NMMA - 1) * 32;
     // Register budget: the register file is split over the four SM sub-partitions (16 K registers each) and the 10 warps of a
     // DUAL CTA land 3/3/2/2 on them, so two co-resident CTAs need 6 warps x 32 x regs <= 16384 -> 80 registers per thread

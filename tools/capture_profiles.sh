@@ -1,15 +1,23 @@
 #!/bin/bash
-# Round evidence (run under gpurun on one B200): launch list of the bench command + `ncu --set full` captures of the three
-# tensor-core kernels.  Outputs land in gpurun_out/; tools/summarize_profiles.py turns them into profiles/<tag>_*.json.
+# Round evidence (run under gpurun on one B200): launch list of the bench command + `ncu --set full` captures of the
+# tensor-core kernels and gn_apply.  The raw metric pages are exported to CSV ON THE BOX and the .ncu-rep files deleted unless
+# KEEP_REP=1 (gpurun copies back at most 64 MiB; a capture with --import-source is ~17 MB).  Outputs land in gpurun_out/;
+# tools/summarize_profiles.py turns them into profiles/<tag>_*.json.
 TAG=${1:-r01}
+SRC=${KEEP_REP:+--import-source on}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_launches_bench.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/${TAG}_launches_bench.log 2>&1
+cap() {   # name, kernel regex, first launch, count
+    ncu --set full --clock-control none $SRC -k regex:$2 -s $3 -c $4 -o gpurun_out/${TAG}_$1 -f python tools/ncu_unet.py > gpurun_out/${TAG}_ncu_$1.log 2>&1
+    ncu -i gpurun_out/${TAG}_$1.ncu-rep --page raw --csv > gpurun_out/${TAG}_$1.raw.csv 2>/dev/null
+    [ -z "$KEEP_REP" ] && rm -f gpurun_out/${TAG}_$1.ncu-rep
+}
 # row kernel: launches 1.. = level-0 down blocks (fused GroupNorm 32->32, identity shortcut), 26.. = level-1 up blocks (split C_out)
-ncu --set full --clock-control none --import-source on -k regex:rowconv -s 1 -c 2 -o gpurun_out/${TAG}_rowconv_l0 -f python tools/ncu_unet.py > gpurun_out/${TAG}_ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:rowconv -s 26 -c 2 -o gpurun_out/${TAG}_rowconv_l1up -f python tools/ncu_unet.py > gpurun_out/${TAG}_ncu2.log 2>&1
-# patch kernel: launches 0.. = level-2 down blocks (128->128), 12.. = level 3 (256->256, CTA pairs)
-ncu --set full --clock-control none --import-source on -k regex:patchconv -s 1 -c 2 -o gpurun_out/${TAG}_patchconv_l2 -f python tools/ncu_unet.py > gpurun_out/${TAG}_ncu3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:patchconv -s 13 -c 2 -o gpurun_out/${TAG}_patchconv_l3 -f python tools/ncu_unet.py > gpurun_out/${TAG}_ncu4.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gn_apply -s 2 -c 2 -o gpurun_out/${TAG}_gn_apply -f python tools/ncu_unet.py > gpurun_out/${TAG}_ncu5.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+cap rowconv_l0 rowconv 1 2
+cap rowconv_l1up rowconv 26 2
+# patch kernel: launches 1.. = level-2 down blocks (128->128), 13.. = level 3 (256->256, CTA pairs)
+cap patchconv_l2 patchconv 1 2
+cap patchconv_l3 patchconv 13 2
+cap gn_apply gn_apply 2 2
+ls -la gpurun_out/ | head -30

@@ -34,9 +34,25 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg", "sm__cycles_active.avg"]
+def family(kname):
+    """ncu kernel name -> the family name bench.py uses (rowconv<BK,BN,KCH>, patchconv<BN>, conv_gemm<BK,BN>, gn_apply, ...)"""
+    m = re.match(r"(\w+?)(_kernel)?<([^>]*)>", kname)
+    if not m:
+        return kname.replace("_kernel", "")
+    base, args = m.group(1), [a.strip().replace("(int)", "").replace("(bool)", "") for a in m.group(3).split(",")]
+    keep = {"rowconv": 3, "patchconv": 1, "conv_gemm": 2}.get(base, 0)
+    return f"{base}<{','.join(args[:keep])}>" if keep else base
+
+dram = collections.defaultdict(list)
 for f in sorted(os.listdir(G)):
-    if not f.endswith(".ncu-rep"): continue
-    raw = subprocess.run(["ncu", "-i", os.path.join(G, f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if not f.startswith(tag): continue
+    if f.endswith(".raw.csv"):                       # exported on the GPU box by tools/capture_profiles.sh
+        raw = open(os.path.join(G, f)).read()
+        f = f.replace(".raw.csv", ".ncu-rep")
+    elif f.endswith(".ncu-rep") and not os.path.exists(os.path.join(G, f.replace(".ncu-rep", ".raw.csv"))):
+        raw = subprocess.run(["ncu", "-i", os.path.join(G, f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
+        continue
     rows = list(csv.reader(raw.splitlines()))
     if len(rows) < 3: continue
     hdr, units = rows[0], rows[1]
@@ -47,10 +63,21 @@ for f in sorted(os.listdir(G)):
             if h in KEYS or any(h.endswith(k) for k in KEYS):
                 d[h.split(".TriageCompute.")[-1] + (f" [{u}]" if u else "")] = v
         res.append(d)
+        try:
+            rd = [float(v.replace(",", "")) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[k.split("[")[1].rstrip("]")]
+                  for k, v in d.items() if k.startswith("dram__bytes_read.sum") or k.startswith("dram__bytes_write.sum")]
+            if len(rd) == 2:
+                dram[family(d["kernel"])].append(sum(rd))
+        except Exception:
+            pass
     name = f if f.startswith(tag) else f"{tag}_{f}"
     json.dump(dict(source=f, command="ncu --set full --clock-control none --import-source on (see tools/, DESIGN.md §5)", launches=res),
               open(os.path.join(P, name.replace(".ncu-rep", "_ncu.json")), "w"), indent=1)
     print(f, [(d["kernel"][:30], d.get("gpu__time_duration.sum [us]")) for d in res])
+if dram:
+    json.dump(dict(source=f"{tag}_*_ncu.json (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                   kernels={k: dict(dram_bytes_per_launch=v, dram_bytes_per_launch_mean=sum(v) / len(v)) for k, v in dram.items()}),
+              open(os.path.join(P, f"{tag}_kernel_dram_bytes.json"), "w"), indent=1)
 for src, dst in (("unet_profile_afhq256_b80.json", f"{tag}_unet_ops_afhq256_b80.json"), ("parity_report.json", f"{tag}_parity_report.json"),
                  ("rate_probe3.json", f"{tag}_umma_rate_probe.json"), ("offset_probe.json", f"{tag}_umma_row_offset_probe.json")):
     if os.path.exists(os.path.join(G, src)):
