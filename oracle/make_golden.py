@@ -43,6 +43,7 @@ def operator_cases():
         ('blur', lambda D: D.GaussianDeblurring(1.0, 61, "fft", 3, 64, "cpu"),
          lambda: oracle.GaussianDeblurring(1.0, 61, "fft", 3, 64, "cpu")),
         ('sr2', lambda D: D.Superresolution(2, 64, device="cpu"), lambda: oracle.Superresolution(2, 64)),
+        ('sr2_bicubic', lambda D: D.Superresolution(2, 64, mode="bicubic", device="cpu"), lambda: oracle.Superresolution(2, 64, mode="bicubic")),
     ]
 
 

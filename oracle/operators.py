@@ -125,21 +125,50 @@ class GaussianDeblurring(Degradation):
         return torch.real(torch.fft.ifft2(torch.fft.fft2(x.to(self.device)) * torch.conj(torch.fft.fft2(self.filter))))
 
 
-class Superresolution(Degradation):
-    """degradations.py:92-127, mode None: keep the upper-left pixel of every sf x sf patch (utils.py:302-310);
-    adjoint = zero-filled upsampling (utils.py:283-299).  The reference constructor also materialises a dense
-    (H^2/sf^2) x H^2 one-hot matrix (:110-111) that pnp_flow never reads; it is not restated."""
-    def __init__(self, sf, dim_image, mode=None, device="cpu"):
-        assert mode is None
-        self.sf, self.mode = sf, mode
+def bicubic_filter(factor: int = 2) -> torch.Tensor:
+    """utils.py:365-396 (a = -0.5 cubic kernel sampled at 4*factor points, outer product, normalised), [1,1,4f,4f]."""
+    x = np.arange(start=-2 * factor + 0.5, stop=2 * factor, step=1) / factor
+    a = -0.5
+    x = np.abs(x)
+    w = ((a + 2) * np.power(x, 3) - (a + 3) * np.power(x, 2) + 1) * (x <= 1)
+    w += (a * np.power(x, 3) - 5 * a * np.power(x, 2) + 8 * a * x - 4 * a) * (x > 1) * (x < 2)
+    w = np.outer(w, w)
+    w = w / np.sum(w)
+    return torch.Tensor(w).unsqueeze(0).unsqueeze(0)
 
-    def H(self, x):
+
+class Superresolution(Degradation):
+    """degradations.py:92-127.  mode None: keep the upper-left pixel of every sf x sf patch (utils.py:302-310); adjoint =
+    zero-filled upsampling (utils.py:283-299).  mode 'bicubic' (:97-109,117-127): circular convolution with the 4sf x 4sf
+    bicubic filter (zero-padded to the image, rolled by -(4sf-1)//2) through the FFT, then decimation; adjoint = zero-filled
+    upsampling, then the conjugate filter.  The reference constructor also materialises a dense (H^2/sf^2) x H^2 one-hot
+    matrix (:110-111) that pnp_flow never reads; it is not restated."""
+    def __init__(self, sf, dim_image, mode=None, device="cpu"):
+        assert mode in (None, "bicubic")
+        self.sf, self.mode = sf, mode
+        if mode == "bicubic":
+            k = bicubic_filter(sf).to(device)
+            f = torch.zeros((1, 3) + (dim_image, dim_image), device=device)
+            f[..., : k.shape[-1], : k.shape[-1]] = k
+            self.filter = torch.roll(f, shifts=(-(k.shape[-1] - 1) // 2, -(k.shape[-1] - 1) // 2), dims=(2, 3))
+
+    def _down(self, x):
         return x[..., 0::self.sf, 0::self.sf]
 
-    def H_adj(self, x):
+    def _up(self, x):
         z = torch.zeros((x.shape[0], x.shape[1], x.shape[2] * self.sf, x.shape[3] * self.sf)).type_as(x)
         z[..., 0::self.sf, 0::self.sf].copy_(x)
         return z
+
+    def H(self, x):
+        if self.mode is None:
+            return self._down(x)
+        return self._down(torch.real(torch.fft.ifft2(torch.fft.fft2(x) * torch.fft.fft2(self.filter))))
+
+    def H_adj(self, x):
+        if self.mode is None:
+            return self._up(x)
+        return torch.real(torch.fft.ifft2(torch.fft.fft2(self._up(x)) * torch.conj(torch.fft.fft2(self.filter))))
 
 
 # problem name -> (constructor(dim, channels, device), sigma_noise gaussian, tuned alpha)   main.py:120-179,

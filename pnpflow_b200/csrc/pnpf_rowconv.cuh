@@ -11,11 +11,14 @@
 //   * vertical taps: input row j feeds output rows j+1, j, j-1 with the SAME A operand, so the three taps are stacked
 //     along N: the resident weight tile of (kw, chunk) holds [kh][cout] rows and the accumulators of consecutive output
 //     rows occupy DEcreasing TMEM column blocks; one tcgen05.mma with N = 3*C_out updates three output rows.
-// With N = 32 an MMA is only 16 tensor clocks, so the kernel is organised around the single issuing thread:
+// With N = 32 an MMA is only 16 tensor clocks, so the kernel is organised around the MMA-issuing threads:
 //   * every MMA accumulates (the epilogue re-zeroes an accumulator block with tcgen05.st after draining it), which
 //     removes all per-instruction special cases; descriptor words live in registers, the tap loops are fully unrolled
 //     (template KCH = channel chunks) and only add immediates;
-//   * waits are issued by one lane per warp; one epilogue warp set per 32 output columns, the other worker warps transform;
+//   * two issuer warps take alternate input rows: the MMAs are issued in row order (mbarrier hand-over), the barrier waits,
+//     commits and bookkeeping around them overlap (see the MMA role below);
+//   * waits are issued by one lane per warp; two epilogue warp sets (alternate rows, or the two 32-column halves of C_out = 64),
+//     4 or 8 GroupNorm-transform warps (RowCfg);
 //   * bias (+ the per-image time-embedding row) is staged in shared memory once per work item;
 //   * GroupNorm statistics of the OUTPUT tensor are accumulated per thread across the rows of an item and reduced with
 //     warp shuffles + one fp64 atomic per lane per item.
