@@ -145,6 +145,15 @@ int pnpf_conv2d_nhwc(const void* x, int B, int Hin, int Win, int Cin, const floa
 int pnpf_gn_conv2d_nhwc(const void* xa, int Ca, const void* xb, int Cb, int B, int H, int W, const float* host_gamma,
                         const float* host_beta, const float* host_w, const float* host_bias, int Cout, int silu, void* out,
                         int out_f32, void* stream);
+/* Sub-pixel form of Upsample (models.py:41-47: F.interpolate(scale 2, nearest) followed by a 3x3 conv): the 3x3 weights
+ * host_w [Cout,Cin,3,3] folded into the 2x2 weights host_out [Cout,Cin,2,2] that output pixels (2h+a, 2w+b) apply to the
+ * low-resolution pixels (h-1+a+i, w-1+b+j).  Host-only (no GPU needed). */
+int pnpf_fold_subpixel_weights(const float* host_w, int Cout, int Cin, int a, int b, float* host_out);
+/* conv3x3(nearest_x2(x)) + bias computed as four sub-pixel phases on the low-resolution tensor (patch-streaming kernel,
+ * opt-in in the U-Net plan with PNPF_SUBPIXEL_UP=1).  x: device bf16 [B,H,W,Cin]; out: device bf16 [B,2H,2W,Cout];
+ * W <= 128, Cin % 64 == 0, Cout in {64,128,256}.  Synchronous. */
+int pnpf_upconv2x_nhwc(const void* x, int B, int H, int W, int Cin, const float* host_w, const float* host_bias, int Cout,
+                       void* out, void* stream);
 /* out[b] = A[b] (M x K) * Bm[b]^T (N x K), bf16 row-major operands, fp32 (out_f32=1) or bf16 output. Synchronous. */
 int pnpf_gemm_nt(const void* A, const void* Bm, void* out, int batch, int M, int N, int K, int out_f32, void* stream);
 

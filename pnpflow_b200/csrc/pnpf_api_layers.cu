@@ -85,6 +85,61 @@ extern "C" int pnpf_conv2d_nhwc(const void* x, int B, int Hin, int Win, int Cin,
     return 0;
 }
 
+extern "C" int pnpf_fold_subpixel_weights(const float* host_w, int Cout, int Cin, int a, int b, float* host_out) {
+    PNPF_REQUIRE(host_w && host_out && Cout > 0 && Cin > 0 && (a | b) >= 0 && (a | b) <= 1, "fold_subpixel_weights: bad arguments");
+    fold_subpixel_weights(host_w, Cout, Cin, a, b, host_out);
+    return 0;
+}
+
+extern "C" int pnpf_upconv2x_nhwc(const void* x, int B, int H, int W, int Cin, const float* host_w, const float* host_bias, int Cout,
+                                  void* out, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PNPF_REQUIRE(x && host_w && out, "null pointer");
+    const int N_pad = round_up_n(Cout);
+    PNPF_REQUIRE(Cout == N_pad, "sub-pixel up conv needs Cout in {64, 128, 256} (got %d)", Cout);
+    std::vector<float> bp(N_pad, 0.f);
+    if (host_bias)
+        for (int i = 0; i < Cout; ++i) bp[i] = host_bias[i];
+    const size_t wn = (size_t)N_pad * 4 * Cin;
+    std::vector<bf16> wp(4 * wn);
+    std::vector<float> f((size_t)Cout * Cin * 4);
+    for (int ph = 0; ph < 4; ++ph) {
+        fold_subpixel_weights(host_w, Cout, Cin, ph >> 1, ph & 1, f.data());
+        pack_conv_weight(wp.data() + ph * wn, f.data(), Cout, Cin, 2, N_pad, Cin, nullptr, 0, 1.0f);
+    }
+    bf16* dw = nullptr;
+    float* db = nullptr;
+    PNPF_CHECK_CUDA(cudaMalloc(&dw, wp.size() * sizeof(bf16)));
+    PNPF_CHECK_CUDA(cudaMalloc(&db, bp.size() * sizeof(float)));
+    PNPF_CHECK_CUDA(cudaMemcpyAsync(dw, wp.data(), wp.size() * sizeof(bf16), cudaMemcpyHostToDevice, s));
+    PNPF_CHECK_CUDA(cudaMemcpyAsync(db, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = 0;
+    for (int ph = 0; ph < 4 && !rc; ++ph) {
+        ConvDesc d;
+        d.x = static_cast<const bf16*>(x);
+        d.B = B; d.Hin = d.Hout = H; d.Win = d.Wout = W; d.Cin = Cin; d.x_pitch = Cin;
+        d.w = dw + ph * wn; d.N_pad = N_pad; d.ksize = 3; d.stride = 1;
+        d.subpix = 1; d.sp_a = ph >> 1; d.sp_b = ph & 1;
+        d.out = out; d.out_mode = 0;
+        d.out_img_stride = 4LL * H * W * Cout; d.out_row_stride = Cout; d.n_valid = Cout;
+        d.bias = db;
+        TcOp op;
+        if (!patchconv_eligible(d)) {
+            set_error("sub-pixel up conv: shape %dx%d Cin=%d Cout=%d is not a patch-kernel shape", H, W, Cin, Cout);
+            rc = 2;
+            break;
+        }
+        rc = prepare_conv(op, d);
+        if (!rc) rc = launch_tc(op, s);
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(dw);
+    cudaFree(db);
+    if (rc) return rc;
+    PNPF_CHECK_CUDA(e);
+    return 0;
+}
+
 extern "C" int pnpf_gemm_nt(const void* A, const void* Bm, void* out, int batch, int M, int N, int K, int out_f32, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     GemmDesc d;

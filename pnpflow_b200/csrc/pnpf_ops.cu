@@ -46,6 +46,7 @@ int rowconv_max_smem() { return ROWCONV_SMEM_MAX; }
 struct RowShape { int BK, BN, nsplit, kch, kch2, kch_a, kch2_a, w_bytes, slot_bytes, nslot, stage_bytes, n_epi; };
 static bool rowconv_shape(const ConvDesc& d, RowShape& r) {
     if (!d.allow_rowconv || d.ksize != 3 || d.stride != 1 || d.Wout % 128 != 0 || d.Wout != d.Win || d.Hout != d.Hin) return false;
+    if (d.subpix) return false;                       // sub-pixel phases exist in the patch kernel only
     if (!(d.N_pad == 16 || d.N_pad == 32 || d.N_pad == 64) || d.c_base != 0) return false;
     const int Ca = d.Cin - d.Cb, C2a = d.C2 - d.C2b;
     if (d.Cin % 32 || d.C2 % 32 || Ca % 32 || d.Cb % 32 || C2a % 32 || d.C2b % 32 || Ca <= 0) return false;
@@ -101,6 +102,7 @@ static bool patchconv_shape(const ConvDesc& d, PatchShape& r) {
     if (off || !d.allow_rowconv || d.ksize != 3 || d.stride != 1 || d.Wout != d.Win || d.Hout != d.Hin || d.Wout > 128) return false;
     if (!(d.N_pad == 64 || d.N_pad == 128 || d.N_pad == 256) || d.c_base != 0 || d.xb || d.x2b || d.gn_gamma) return false;
     if (d.Cin % 64 || d.C2 % 64 || d.Cin < 64) return false;
+    if (d.subpix && (d.x2 || d.C2 || d.residual || d.out_mode != 0)) return false;
     r.P = d.Wout + 2;
     r.NR = (r.P - 1 + 127) / r.P + 1 + 2;          // rows a tile of 128 positions can touch, plus the two halo rows
     r.patch_bytes = (r.NR * r.P * 128 + 1023) / 1024 * 1024;
@@ -126,7 +128,8 @@ void describe_conv_impl(const ConvDesc& d, char* buf, size_t n) {
         snprintf(buf, n, "rowconv<%d,%d,%d> nsplit=%d nslot=%d kch2=%d w=%dKB slot=%dKB stage=%dKB epi_warps=%d gn=%d", r.BK, r.BN, r.kch, r.nsplit,
                  r.nslot, r.kch2, r.w_bytes / 1024, r.slot_bytes / 1024, r.stage_bytes / 1024, r.n_epi, d.gn_gamma ? 1 : 0);
     else if (PatchShape ps; patchconv_shape(d, ps))
-        snprintf(buf, n, "patchconv<%d> P=%d NR=%d patch=%dKB na=%d nb=%d tiles/img=%d", d.N_pad, ps.P, ps.NR, ps.patch_bytes / 1024, ps.na, ps.nb, ps.tiles_per_img);
+        snprintf(buf, n, "patchconv<%d> P=%d NR=%d patch=%dKB na=%d nb=%d tiles/img=%d%s", d.N_pad, ps.P, ps.NR, ps.patch_bytes / 1024, ps.na, ps.nb,
+                 ps.tiles_per_img, d.subpix ? " subpix" : "");
     else
         snprintf(buf, n, "conv_gemm<%d,%d> k=%d s=%d", (d.Cin % 64 == 0 && d.C2 % 64 == 0) ? 64 : 32, d.N_pad > 256 ? 256 : d.N_pad, d.ksize, d.stride);
 }
@@ -184,9 +187,12 @@ static int try_prepare_patchconv(TcOp& op, const ConvDesc& d) {
     q.kchunks = d.Cin / 64; q.kchunks2 = d.x2 ? d.C2 / 64 : 0;
     q.patch_bytes = sh.patch_bytes; q.na = sh.na; q.nb = sh.nb;
     op.patch_nb_pair = sh.nb_pair;
+    op.patch_subpix = d.subpix ? 1 : 0;
+    q.sp_a = d.sp_a; q.sp_b = d.sp_b;
+    PNPF_REQUIRE(!d.subpix || ((d.sp_a | d.sp_b) & ~1) == 0, "sub-pixel phase (%d,%d) must be 0/1", d.sp_a, d.sp_b);
     fill_epi(q.epi, d);
     op.kind = 2; op.BK = 64; op.BN = d.N_pad;
-    const long long Ktot = 9LL * d.Cin + (d.x2 ? d.C2 : 0);
+    const long long Ktot = d.subpix ? 4LL * d.Cin : 9LL * d.Cin + (d.x2 ? d.C2 : 0);
     if (int e = make_act_tmap(&op.tmA, d.x, d.Cin, d.x_pitch, d.Win, d.Hin, d.B, 64, sh.P, sh.NR, 1)) return e;
     op.tmA2 = op.tmA;
     if (d.x2) { if (int e = make_act_tmap(&op.tmA2, d.x2, d.C2, d.x2_pitch, d.Wout, d.Hout, d.B, 64, sh.P, sh.NR, 1)) return e; }
@@ -206,6 +212,7 @@ int prepare_conv(TcOp& op, const ConvDesc& d) {
         const int rc = try_prepare_patchconv(op, d);
         if (rc >= 0) return rc;
     }
+    PNPF_REQUIRE(!d.subpix, "sub-pixel convolution needs the patch-streaming kernel: check patchconv_eligible() first");
     PNPF_REQUIRE(!d.xb && !d.x2b && !d.gn_gamma, "two-source / fused-GroupNorm convolution needs the row-streaming kernel "
                  "(3x3 stride 1, W %% 128 == 0, C_out <= 64): check rowconv_eligible() first");
     op.kind = 0;
@@ -346,7 +353,7 @@ static int launch_row_t(const TcOp& op, cudaStream_t stream) {
     return 0;
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool SUBPIX = false>
 static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
     using Cfg = PatchCfg<BN, PAIR>;
     PatchConvParams q = op.pp;
@@ -355,7 +362,7 @@ static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
     static bool attr_set = false;
     static int max_clusters = 0;
     if (!attr_set) {
-        PNPF_CHECK_CUDA(cudaFuncSetAttribute(patchconv_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, PATCH_SMEM_MAX));
+        PNPF_CHECK_CUDA(cudaFuncSetAttribute(patchconv_kernel<BN, PAIR, SUBPIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, PATCH_SMEM_MAX));
         if (PAIR) {
             cudaLaunchConfig_t qc = {};
             qc.gridDim = dim3(num_sms() & ~1);
@@ -365,7 +372,7 @@ static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
             qa[0].id = cudaLaunchAttributeClusterDimension;
             qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
             qc.attrs = qa; qc.numAttrs = 1;
-            PNPF_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, patchconv_kernel<BN, PAIR>, &qc));
+            PNPF_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, patchconv_kernel<BN, PAIR, SUBPIX>, &qc));
             PNPF_REQUIRE(max_clusters >= 1, "no CTA pair of patchconv_kernel<%d> fits on this device", BN);
         }
         attr_set = true;
@@ -387,7 +394,7 @@ static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
     cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    PNPF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, patchconv_kernel<BN, PAIR>, op.tmA, op.tmA2, PAIR ? op.tmBh : op.tmB, q));
+    PNPF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, patchconv_kernel<BN, PAIR, SUBPIX>, op.tmA, op.tmA2, PAIR ? op.tmBh : op.tmB, q));
     return 0;
 }
 
@@ -395,6 +402,11 @@ int launch_tc(const TcOp& op, cudaStream_t s) {
     if (op.kind == 2) {
         static const bool no_pair = getenv("PNPF_NO_PAIR") != nullptr;
         const bool pair = !no_pair && op.pp.n_img % 2 == 0;
+        if (op.patch_subpix) {
+            if (op.BN == 64) return pair ? launch_patch_t<64, true, true>(op, s) : launch_patch_t<64, false, true>(op, s);
+            if (op.BN == 128) return pair ? launch_patch_t<128, true, true>(op, s) : launch_patch_t<128, false, true>(op, s);
+            if (op.BN == 256) return pair ? launch_patch_t<256, true, true>(op, s) : launch_patch_t<256, false, true>(op, s);
+        }
         if (op.BN == 64) return pair ? launch_patch_t<64, true>(op, s) : launch_patch_t<64, false>(op, s);
         if (op.BN == 128) return pair ? launch_patch_t<128, true>(op, s) : launch_patch_t<128, false>(op, s);
         if (op.BN == 256) return pair ? launch_patch_t<256, true>(op, s) : launch_patch_t<256, false>(op, s);
@@ -436,6 +448,20 @@ void pack_conv_weight(bf16* dst, const float* w, int O, int Cin, int ks, int N_p
         if (w2)
             for (int c = 0; c < C2; ++c) row[(long long)ks * ks * Cin_pad + c] = f2bf(w2[(long long)o * C2 + c]);
     }
+}
+
+void fold_subpixel_weights(const float* w, int O, int Cin, int a, int b, float* out) {
+    // rows of the 3x3 kernel that land on low-resolution row h-1+a+i for an output row 2h+a (same for columns): see pnpf_ops.h
+    auto lo = [](int ph, int i) { return ph == 0 ? (i == 0 ? 0 : 1) : (i == 0 ? 0 : 2); };
+    auto hi = [](int ph, int i) { return ph == 0 ? (i == 0 ? 0 : 2) : (i == 0 ? 1 : 2); };
+    for (long long oc = 0; oc < (long long)O * Cin; ++oc)
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) {
+                float acc = 0.f;
+                for (int kh = lo(a, i); kh <= hi(a, i); ++kh)
+                    for (int kw = lo(b, j); kw <= hi(b, j); ++kw) acc += w[oc * 9 + kh * 3 + kw];
+                out[oc * 4 + i * 2 + j] = acc;
+            }
 }
 
 }  // namespace pnpf

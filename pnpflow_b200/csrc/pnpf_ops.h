@@ -16,6 +16,7 @@ struct TcOp {               // a prepared conv_gemm launch
     RowConvParams rp;       // kind == 1: row-streaming conv (pnpf_rowconv.cuh)
     PatchConvParams pp;     // kind == 2: patch-streaming conv (pnpf_patchconv.cuh)
     int patch_nb_pair = 0;  // weight-ring depth of the CTA-pair launch (half tiles)
+    int patch_subpix = 0;   // patch conv computes one phase of a sub-pixel (nearest x2 + 3x3) convolution
     int kind = 0;           // 0: conv_gemm_kernel, 1: rowconv_kernel, 2: patchconv_kernel
     int BK = 0, BN = 0;
     int n_epi = 8;          // row conv: epilogue warps (RowCfg::NEW), the other worker warps run the GroupNorm transform
@@ -65,6 +66,10 @@ struct ConvDesc {
     const double* gn_stats_b = nullptr;
     int gn_groups = 32, gn_silu = 1;
     float gn_eps = 1e-6f;
+    // ---- patch-streaming kernel only: one phase (sp_a, sp_b) of "nearest x2 upsampling + 3x3 conv" on the LOW-resolution input.
+    // Hin/Win/Hout/Wout describe the low-resolution grid, the out_* strides the high-resolution tensor [B][2H][2W][C];
+    // w = folded 2x2 weights of this phase, packed [N_pad][4*Cin] in (i, j, cin) order (fold_subpixel_weights + pack).
+    int subpix = 0, sp_a = 0, sp_b = 0;
 };
 int prepare_conv(TcOp& op, const ConvDesc& d);
 bool rowconv_eligible(const ConvDesc& d);     // would prepare_conv pick the row-streaming kernel?
@@ -94,5 +99,8 @@ int launch_tc(const TcOp& op, cudaStream_t s);
 // optionally followed by the 1x1 shortcut weights w2 [O][C2]; rows >= O and channels >= Cin are zero.
 void pack_conv_weight(bf16* dst, const float* w, int O, int Cin, int ks, int N_pad, int Cin_pad, const float* w2, int C2,
                       float scale);
+// 3x3 weights [O][Cin][3][3] -> the 2x2 weights [O][Cin][2][2] of phase (a, b) of the equivalent sub-pixel convolution:
+// out[o][c][i][j] = sum_{kh in R(a,i)} sum_{kw in R(b,j)} w[o][c][kh][kw],  R(0,0)={0}, R(0,1)={1,2}, R(1,0)={0,1}, R(1,1)={2}
+void fold_subpixel_weights(const float* w, int O, int Cin, int a, int b, float* out);
 
 }  // namespace pnpf

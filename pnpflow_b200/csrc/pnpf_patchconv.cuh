@@ -14,6 +14,13 @@
 // ~1.3-1.7x instead of 9x; the weights stream through their own ring, one [BN x 64] tile per (chunk, tap).
 // PAIR: two CTAs (cta_group::2) take the SAME tile of two consecutive images — one MMA instruction carries one A descriptor
 // for both CTAs, so their patch origins must coincide — and each stages half of every weight tile (see pnpf_gemm.cuh).
+//
+// SUBPIX (opt-in, PNPF_SUBPIXEL_UP=1): one PHASE of "nearest-neighbour x2 upsampling followed by a 3x3 conv" (models.py:41-47)
+// computed directly on the LOW-resolution tensor.  Output pixel (2h+a, 2w+b) only sees the 2x2 low-resolution pixels
+// (h-1+a+i, w-1+b+j), i,j in {0,1}, with the 3x3 weights folded into 2x2 (fold_subpixel_weights): four launches (a,b) with
+// 4 taps each replace one launch with 9 taps on a 4x larger tensor — 2.25x fewer FLOPs, and the upsampled tensor is never
+// materialised.  In the padded-linear space tap (i,j) is simply patch-row offset (a+i)*P + (b+j); the epilogue scatters the
+// tile to the stride-2 lattice of the high-resolution output.
 #pragma once
 #include "pnpf_gemm.cuh"
 
@@ -29,6 +36,7 @@ struct PatchConvParams {
     int na, nb;            // ring depths: patches, weight tiles
     long long* dbg;
     EpiParams epi;
+    int sp_a, sp_b;        // SUBPIX: phase (row, column parity of the output pixels this launch produces)
 };
 
 template <int BN, bool PAIR>
@@ -45,7 +53,7 @@ struct PatchCfg {
     static_assert(BN == 64 || BN == 128 || BN == 256, "patch conv output widths");
 };
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool SUBPIX = false>
 __global__ void __launch_bounds__(PatchCfg<BN, PAIR>::THREADS, 1)
 patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ PatchConvParams p) {
@@ -138,13 +146,13 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const long long c_start = PNPF_CLK();
         for (int u = unit0; u < total_units; u += unit_step) {
             for (int c = 0; c < nch; ++c) {
-                const int ntap = c < p.kchunks ? 9 : 1;
+                const int ntap = c < p.kchunks ? (SUBPIX ? 4 : 9) : 1;
                 for (int t = 0; t < ntap; ++t) {
                     PNPF_TIMED_WAIT(&b_empty[slot], phase ^ 1, c_wait);
                     uint8_t* dst = b_ring + slot * Cfg::B_BYTES;
                     if (elect_one_sync()) {
                         // packed K order (pack_conv_weight): (kh, kw, cin) for the 3x3 part, then the 1x1 source channels
-                        const int tap = (t + tap_rot) % 9;
+                        const int tap = SUBPIX ? t : (t + tap_rot) % 9;      // SUBPIX: packed K order (i, j, cin), 4 taps
                         const int k0 = c < p.kchunks ? (tap * p.kchunks + c) * 64 : (9 * p.kchunks + (c - p.kchunks)) * 64;
                         if constexpr (PAIR) {
                             const uint32_t fb = mapa_u32(smem_u32(&b_full[slot]), 0);
@@ -183,12 +191,19 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     PNPF_TIMED_WAIT(&a_full[aslot], aphase, c_afull);
                     tc_fence_after();
                     const uint32_t pa = smem_u32(a_ring + aslot * p.patch_bytes);
-                    const int ntap = c < p.kchunks ? 9 : 1;
+                    const int ntap = c < p.kchunks ? (SUBPIX ? 4 : 9) : 1;
                     for (int t = 0; t < ntap; ++t) {
                         PNPF_TIMED_WAIT(&b_full[bslot], bphase, c_bfull);
                         tc_fence_after();
-                        const int tap = ntap == 9 ? (t + tap_rot) % 9 : 4;
-                        const int kh = tap / 3, kw = tap - 3 * kh;
+                        int kh, kw;
+                        if constexpr (SUBPIX) {
+                            kh = p.sp_a + (t >> 1);
+                            kw = p.sp_b + (t & 1);
+                        } else {
+                            const int tap = ntap == 9 ? (t + tap_rot) % 9 : 4;
+                            kh = tap / 3;
+                            kw = tap - 3 * kh;
+                        }
                         const uint64_t adesc = make_smem_desc<128>(pa + static_cast<uint32_t>((kh * p.P + kw + a_shift) * 128));
                         const uint64_t bdesc = make_smem_desc<128>(smem_u32(b_ring + bslot * Cfg::B_BYTES));
                         if (elect_one_sync()) {
@@ -235,7 +250,8 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int o = o0 + m;
             const int h = o / p.P, wp = o - h * p.P;
             const bool valid = (h < p.H) && (wp < p.W);
-            const long long pix = static_cast<long long>(h) * p.W + wp;
+            const long long pix = SUBPIX ? static_cast<long long>(2 * h + p.sp_a) * (2 * p.W) + 2 * wp + p.sp_b      // stride-2 lattice
+                                         : static_cast<long long>(h) * p.W + wp;
             {
                 const long long _t0 = PNPF_CLK();
                 if (lane == 0) mbar_wait(&tfull_bar[acc], acc_phase);

@@ -98,6 +98,12 @@ struct pnpf_engine {
 // ------------------------------------------------------------------------------------------------
 // plan construction
 // ------------------------------------------------------------------------------------------------
+// opt-in (PNPF_SUBPIXEL_UP=1): the three nearest-x2 + 3x3 convs run as four sub-pixel phases on the low-resolution tensor
+static bool subpixel_up_enabled() {
+    static const bool on = getenv("PNPF_SUBPIXEL_UP") != nullptr;
+    return on;
+}
+
 static bool has_attn(const pnpf_unet_config& c, int side) {
     for (int i = 0; i < c.num_attn_resolutions; ++i)
         if (c.attn_resolutions[i] == side) return true;
@@ -371,6 +377,15 @@ extern "C" int pnpf_finalize_weights(pnpf_engine* e) {
                 bf16* d = pk.b16(p + ".w", (size_t)np * 9 * L.in_ch);
                 pack_conv_weight(d, W(e, p + ".weight").data(), L.out_ch, L.in_ch, 3, np, L.in_ch, nullptr, 0, 1.f);
                 pack_bias(p + ".b", np, W(e, p + ".bias"), nullptr);
+                if (L.kind == LayerSpec::UP && subpixel_up_enabled()) {
+                    // sub-pixel form of nearest x2 + 3x3 conv: four folded 2x2 weight sets, packed [np][4*Cin] in (i, j, cin) order
+                    std::vector<float> f((size_t)L.out_ch * L.in_ch * 4);
+                    for (int ph = 0; ph < 4; ++ph) {
+                        fold_subpixel_weights(W(e, p + ".weight").data(), L.out_ch, L.in_ch, ph >> 1, ph & 1, f.data());
+                        bf16* ds = pk.b16(p + ".w_sp" + std::to_string(ph), (size_t)np * 4 * L.in_ch);
+                        pack_conv_weight(ds, f.data(), L.out_ch, L.in_ch, 2, np, L.in_ch, nullptr, 0, 1.f);
+                    }
+                }
                 break;
             }
             case LayerSpec::RES: {
@@ -573,7 +588,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
             fprintf(stderr, "plan: %-44s %4dx%-4d Cin=%-3d C2=%-3d N=%-3d %s\n", name.c_str(), d.Hout, d.Wout, d.Cin, d.C2, d.n_valid, buf);
         }
         if (real) { if (int rc = prepare_conv(o.tc, d)) return rc; }
-        o.flops = 2.0 * d.Hout * d.Wout * (double)d.n_valid * ((double)d.ksize * d.ksize * d.Cin + ((d.x2 && !d.x2_identity) ? d.C2 : 0));
+        o.flops = 2.0 * d.Hout * d.Wout * (double)d.n_valid * ((double)(d.subpix ? 4 : d.ksize * d.ksize) * d.Cin + ((d.x2 && !d.x2_identity) ? d.C2 : 0));
         o.bytes = 2.0 * d.Hin * d.Win * d.Cin + (d.x2 ? 2.0 * d.Hout * d.Wout * d.C2 : 0.0) +   // Cin / C2 are concat totals
                   (d.residual ? 2.0 * d.Hout * d.Wout * d.n_valid : 0.0) +
                   (d.out_mode == 0 ? 2.0 : 4.0) * d.Hout * d.Wout * d.n_valid;
@@ -765,6 +780,27 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
             }
             case LayerSpec::UP: {
                 const int so = side * 2;
+                if (subpixel_up_enabled()) {
+                    // opt-in: four sub-pixel phases on the low-resolution tensor (pnpf_patchconv.cuh SUBPIX) instead of
+                    // upsample2x + a 3x3 conv on the 4x larger tensor
+                    ConvDesc d;
+                    d.x = h.p; d.Hin = d.Win = d.Hout = d.Wout = side; d.Cin = L.in_ch; d.x_pitch = L.in_ch;
+                    d.N_pad = round_n(L.out_ch); d.ksize = 3; d.stride = 1; d.subpix = 1;
+                    d.out_mode = 0; d.out_img_stride = (long long)so * so * L.out_ch; d.out_row_stride = L.out_ch; d.n_valid = L.out_ch;
+                    if (patchconv_eligible(d)) {
+                        Act y = new_h(L.out_ch, so, false);
+                        d.out = y.p; d.stats_out = y.stats;
+                        for (int ph = 0; ph < 4; ++ph) {
+                            d.sp_a = ph >> 1; d.sp_b = ph & 1;
+                            if (real) { d.w = wptr<bf16>(e, p + ".w_sp" + std::to_string(ph)); d.bias = wptr<float>(e, p + ".b"); }
+                            // the op that completes the tensor carries the layer's name (debug taps compare it with the oracle)
+                            const std::string nm = ph == 3 ? p : p + ".phase" + std::to_string(ph);
+                            if (int rc = add_conv(nm, d, ph == 3 ? y.p : nullptr, y.C, so)) return rc;
+                        }
+                        h = y;
+                        break;
+                    }
+                }
                 {
                     Op o;
                     o.kind = Op::UPSAMPLE; o.name = p + ".nearest2x"; o.up_src = h.p; o.up_side = side; o.up_C = L.in_ch; o.dst = t_up;

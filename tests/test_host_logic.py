@@ -112,6 +112,29 @@ def test_as_engine_operator_accepts_foreign_plugins():
         P.as_engine_operator(object())
 
 
+def test_subpixel_weight_fold_equals_nearest_upsample_plus_conv3x3():
+    """models.py:41-47 (Upsample = F.interpolate(scale 2, nearest) -> 3x3 conv) restated as four 2x2 convolutions on the
+    low-resolution tensor with the weights folded by the C ABI's host-side pnpf_fold_subpixel_weights (the opt-in
+    PNPF_SUBPIXEL_UP=1 plan): output pixel (2h+a, 2w+b) = sum_ij W_ab[i,j] * x[h-1+a+i, w-1+b+j]."""
+    import torch.nn.functional as F
+    from pnpflow_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    O, I, H, W = 6, 5, 7, 9
+    w = torch.randn(O, I, 3, 3, generator=g, dtype=torch.float32)
+    x = torch.randn(2, I, H, W, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w.double(), padding=1)
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for a in (0, 1):
+        for b in (0, 1):
+            f = torch.empty(O, I, 2, 2, dtype=torch.float32)
+            _lib.check(lib.pnpf_fold_subpixel_weights(w.contiguous().data_ptr(), O, I, a, b, f.data_ptr()))
+            y = F.conv2d(xp, f.double())                      # y[h', w'] = sum_ij f[i,j] xp[h'+i, w'+j], xp index = x index + 1
+            out[:, :, a::2, b::2] = y[:, :, a:a + H, b:b + W]
+    assert (out - ref).abs().max() < 1e-5
+
+
 def test_cpu_tensors_are_rejected_not_silently_computed():
     import pnpflow_b200 as P
     with pytest.raises(RuntimeError, match="no CPU fallback"):
