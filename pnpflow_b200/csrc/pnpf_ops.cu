@@ -122,11 +122,77 @@ bool patchconv_eligible(const ConvDesc& d) {
     PatchShape r;
     return patchconv_shape(d, r);
 }
+// Patch-streaming kernel with fused GroupNorm(+SiLU) / concat inputs (pnpf_patchgn.cuh).  Opt-in: PNPF_PATCH_GN=1 (every
+// width) or PNPF_PATCH_GN=256 (C_out = 256 only, where shared memory has headroom): written at the end of round 1, not yet
+// run on a GPU.
+static bool patchgn_shape(const ConvDesc& d, PatchShape& r) {
+    static const char* env = getenv("PNPF_PATCH_GN");
+    if (!env || !d.gn_gamma || d.subpix) return false;
+    if (atoi(env) > 1 && d.N_pad != atoi(env)) return false;
+    if (!d.allow_rowconv || d.ksize != 3 || d.stride != 1 || d.Wout != d.Win || d.Hout != d.Hin || d.Wout > 128) return false;
+    if (!(d.N_pad == 64 || d.N_pad == 128 || d.N_pad == 256) || d.c_base != 0 || d.out_mode != 0) return false;
+    const int Ca = d.Cin - d.Cb, C2a = d.C2 - d.C2b;
+    if (d.Cin % 64 || d.C2 % 64 || Ca % 64 || d.Cb % 64 || C2a % 64 || d.C2b % 64 || Ca <= 0 || d.Cin > 512) return false;
+    if (d.Cin % d.gn_groups) return false;
+    r.P = d.Wout + 2;
+    r.NR = (r.P - 1 + 127) / r.P + 1 + 2;
+    r.patch_bytes = (r.NR * r.P * 128 + 1023) / 1024 * 1024;
+    r.tiles_per_img = (d.Hout * r.P + 127) / 128;
+    const int b_bytes = d.N_pad * 128;
+    const int budget = PATCH_SMEM_MAX - 1024 - 512 - 4096;               // alignment slack, barriers, scale / shift table
+    r.na = 3;
+    while (r.na > 2 && budget - r.na * r.patch_bytes < 4 * b_bytes) --r.na;
+    r.nb = (budget - r.na * r.patch_bytes) / b_bytes;
+    if (r.nb > 12) r.nb = 12;
+    r.nb_pair = (budget - r.na * r.patch_bytes) / (b_bytes / 2);
+    if (r.nb_pair > 12) r.nb_pair = 12;
+    return r.nb >= 4;
+}
+bool patchgn_eligible(const ConvDesc& d) {
+    PatchShape r;
+    return patchgn_shape(d, r);
+}
+static int try_prepare_patchgn(TcOp& op, const ConvDesc& d) {
+    PatchShape sh;
+    if (!patchgn_shape(d, sh)) return -1;
+    PatchGnParams& q = op.gp;
+    memset(&q, 0, sizeof(q));
+    const int Ca = d.Cin - d.Cb, C2a = d.C2 - d.C2b;
+    q.H = d.Hout; q.W = d.Wout; q.P = sh.P; q.NR = sh.NR; q.n_img = d.B; q.tiles_per_img = sh.tiles_per_img;
+    q.kchunks = d.Cin / 64; q.kchunks2 = d.x2 ? d.C2 / 64 : 0;
+    q.kch_a = Ca / 64; q.kch2_a = d.x2 ? C2a / 64 : 0;
+    q.patch_bytes = sh.patch_bytes; q.na = sh.na; q.nb = sh.nb;
+    op.patch_nb_pair = sh.nb_pair;
+    PNPF_REQUIRE(d.gn_beta && d.gn_stats_a && (d.Cb == 0 || d.gn_stats_b), "fused GroupNorm needs beta and statistics");
+    q.gn_silu = d.gn_silu; q.gn_gs = d.Cin / d.gn_groups; q.gn_Ca = Ca; q.gn_Cb = d.Cb; q.gn_eps = d.gn_eps;
+    q.gn_gamma = d.gn_gamma; q.gn_beta = d.gn_beta; q.gn_st_a = d.gn_stats_a; q.gn_st_b = d.gn_stats_b;
+    fill_epi(q.epi, d);
+    op.kind = 3; op.BK = 64; op.BN = d.N_pad;
+    const long long Ktot = 9LL * d.Cin + (d.x2 ? d.C2 : 0);
+    if (int e = make_act_tmap(&op.tmA, d.x, Ca, d.x_pitch, d.Win, d.Hin, d.B, 64, sh.P, sh.NR, 1)) return e;
+    op.tmAb = op.tmA;
+    if (d.Cb) { if (int e = make_act_tmap(&op.tmAb, d.xb, d.Cb, d.xb_pitch, d.Win, d.Hin, d.B, 64, sh.P, sh.NR, 1)) return e; }
+    op.tmA2 = op.tmA;
+    op.tmA2b = op.tmA;
+    if (d.x2) {
+        if (int e = make_act_tmap(&op.tmA2, d.x2, C2a, d.x2_pitch, d.Wout, d.Hout, d.B, 64, sh.P, sh.NR, 1)) return e;
+        op.tmA2b = op.tmA2;
+        if (d.C2b) { if (int e = make_act_tmap(&op.tmA2b, d.x2b, d.C2b, d.x2b_pitch, d.Wout, d.Hout, d.B, 64, sh.P, sh.NR, 1)) return e; }
+    }
+    if (int e = make_b_tmap(&op.tmB, d.w, Ktot, Ktot, d.N_pad, 1, 0, 64, d.N_pad)) return e;
+    if (int e = make_b_tmap(&op.tmBh, d.w, Ktot, Ktot, d.N_pad, 1, 0, 64, d.N_pad / 2)) return e;
+    op.flops = 2.0 * d.B * d.Hout * d.Wout * (double)d.n_valid * (double)(Ktot - (d.x2_identity ? d.C2 : 0));
+    return 0;
+}
+
 void describe_conv_impl(const ConvDesc& d, char* buf, size_t n) {
     RowShape r;
     if (rowconv_shape(d, r))
         snprintf(buf, n, "rowconv<%d,%d,%d> nsplit=%d nslot=%d kch2=%d w=%dKB slot=%dKB stage=%dKB epi_warps=%d gn=%d", r.BK, r.BN, r.kch, r.nsplit,
                  r.nslot, r.kch2, r.w_bytes / 1024, r.slot_bytes / 1024, r.stage_bytes / 1024, r.n_epi, d.gn_gamma ? 1 : 0);
+    else if (PatchShape pg; patchgn_shape(d, pg))
+        snprintf(buf, n, "patchgn<%d> P=%d NR=%d patch=%dKB na=%d nb=%d tiles/img=%d kch=%d+%d gn=1", d.N_pad, pg.P, pg.NR, pg.patch_bytes / 1024, pg.na,
+                 pg.nb, pg.tiles_per_img, d.Cin / 64, d.C2 / 64);
     else if (PatchShape ps; patchconv_shape(d, ps))
         snprintf(buf, n, "patchconv<%d> P=%d NR=%d patch=%dKB na=%d nb=%d tiles/img=%d%s", d.N_pad, ps.P, ps.NR, ps.patch_bytes / 1024, ps.na, ps.nb,
                  ps.tiles_per_img, d.subpix ? " subpix" : "");
@@ -206,6 +272,10 @@ int prepare_conv(TcOp& op, const ConvDesc& d) {
     PNPF_REQUIRE(d.ksize == 1 || d.ksize == 3, "conv kernel size %d unsupported (1 or 3)", d.ksize);
     {
         const int rc = try_prepare_rowconv(op, d);
+        if (rc >= 0) return rc;
+    }
+    {
+        const int rc = try_prepare_patchgn(op, d);
         if (rc >= 0) return rc;
     }
     {
@@ -398,7 +468,61 @@ static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
     return 0;
 }
 
+template <int BN, bool PAIR>
+static int launch_patchgn_t(const TcOp& op, cudaStream_t stream) {
+    using Cfg = PatchGnCfg<BN, PAIR>;
+    PatchGnParams q = op.gp;
+    if (PAIR) q.nb = op.patch_nb_pair;
+    const int smem = q.na * q.patch_bytes + q.nb * Cfg::B_BYTES + Cfg::BAR_BYTES + Cfg::TAB_BYTES + 1024;
+    static bool attr_set = false;
+    static int max_clusters = 0;
+    if (!attr_set) {
+        PNPF_CHECK_CUDA(cudaFuncSetAttribute(patchgn_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, PATCH_SMEM_MAX));
+        if (PAIR) {                                   // same query as the plain patch kernel (one CTA per SM)
+            cudaLaunchConfig_t qc = {};
+            qc.gridDim = dim3(num_sms() & ~1);
+            qc.blockDim = dim3(Cfg::THREADS);
+            qc.dynamicSmemBytes = PATCH_SMEM_MAX;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa; qc.numAttrs = 1;
+            PNPF_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, patchgn_kernel<BN, PAIR>, &qc));
+            PNPF_REQUIRE(max_clusters >= 1, "no CTA pair of patchgn_kernel<%d> fits on this device", BN);
+        }
+        attr_set = true;
+    }
+    PNPF_REQUIRE(smem <= PATCH_SMEM_MAX, "patch (GroupNorm) conv shared memory %d exceeds the budget", smem);
+    const long long units = (long long)(q.n_img / (PAIR ? 2 : 1)) * q.tiles_per_img;
+    if (units < 1) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    if (PAIR) {
+        const int clusters = (int)(units < max_clusters ? units : max_clusters);
+        cfg.gridDim = dim3(2 * clusters);
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+    } else {
+        cfg.gridDim = dim3((unsigned)(units < num_sms() ? units : num_sms()));
+    }
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    PNPF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, patchgn_kernel<BN, PAIR>, op.tmA, op.tmAb, op.tmA2, op.tmA2b, PAIR ? op.tmBh : op.tmB, q));
+    return 0;
+}
+
 int launch_tc(const TcOp& op, cudaStream_t s) {
+    if (op.kind == 3) {
+        static const bool no_pair = getenv("PNPF_NO_PAIR") != nullptr;
+        const bool pair = !no_pair && op.gp.n_img % 2 == 0;
+        if (op.BN == 64) return pair ? launch_patchgn_t<64, true>(op, s) : launch_patchgn_t<64, false>(op, s);
+        if (op.BN == 128) return pair ? launch_patchgn_t<128, true>(op, s) : launch_patchgn_t<128, false>(op, s);
+        if (op.BN == 256) return pair ? launch_patchgn_t<256, true>(op, s) : launch_patchgn_t<256, false>(op, s);
+        set_error("no patchgn instantiation for BN=%d", op.BN);
+        return 2;
+    }
     if (op.kind == 2) {
         static const bool no_pair = getenv("PNPF_NO_PAIR") != nullptr;
         const bool pair = !no_pair && op.pp.n_img % 2 == 0;

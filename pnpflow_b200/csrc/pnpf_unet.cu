@@ -697,8 +697,9 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 }
                 d2.stats_out = y.stats;
                 d2.out = y.p; d2.out_mode = 0; d2.out_img_stride = px * L.out_ch; d2.out_row_stride = L.out_ch; d2.n_valid = L.out_ch;
-                bool fuse2 = rowconv_eligible(d2);
-                bool fuse1 = rowconv_eligible(d1);
+                // (patchgn_eligible: the opt-in fused-GroupNorm variant of the patch kernel, PNPF_PATCH_GN; false by default)
+                bool fuse2 = rowconv_eligible(d2) || patchgn_eligible(d2);
+                bool fuse1 = rowconv_eligible(d1) || patchgn_eligible(d1);
                 if (!fuse2 && L.skip_ch && sc) fuse1 = false;       // the unfused conv2 needs the raw concat copy made by norm1
                 if (!fuse1) {                                        // separate GroupNorm pass -> normalised (concatenated) operand
                     add_gn(p + ".norm1", src, side, p + ".norm1", 1, t_a1, (L.skip_ch && sc) ? t_xcat : nullptr);
