@@ -99,7 +99,8 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU arm (the oracle port of the reference algorithm) — the only place bench.py executes oracle/
+# Baseline legs (the oracle port of the reference algorithm): cpu_reference / torch_gpu_reference below are the ONLY places
+# bench.py executes oracle/, and only to time the reference next to the engine — the engine arm never touches it
 # ------------------------------------------------------------------------------------------------------------
 def cpu_reference(cfgname, steps, warmup):
     import oracle
