@@ -40,17 +40,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
-#ifdef PNPF_MBAR_HINT
-    // suspend-time hint (ns): the polling thread is parked by the hardware until the phase completes or the hint expires,
-    // instead of re-issuing try_wait every ~11 clocks and competing with the working warps of its scheduler for issue slots
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(PNPF_MBAR_HINT))
-        : "memory");
-#else
+    // (a suspendTimeHint operand does not change the SASS ptxas generates for sm_100a — SYNCS.PHASECHK.TRANS64.TRYWAIT returns
+    // after ~ 11 clocks either way: profiles/r01_ab_experiments.md)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -58,7 +49,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
-#endif
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
