@@ -423,16 +423,17 @@ static int launch_row_t(const TcOp& op, cudaStream_t stream) {
     return 0;
 }
 
-template <int BN, bool PAIR, bool SUBPIX = false>
+template <int BN, bool PAIR, bool SUBPIX = false, int TG = 1>
 static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
     using Cfg = PatchCfg<BN, PAIR>;
     PatchConvParams q = op.pp;
     if (PAIR) q.nb = op.patch_nb_pair;
-    const int smem = q.na * q.patch_bytes + q.nb * Cfg::B_BYTES + 512 + 1024;
+    q.nb /= TG;                                       // ring depth in slots of TG weight tiles (PNPF_PATCH_TG)
+    const int smem = q.na * q.patch_bytes + q.nb * TG * Cfg::B_BYTES + 512 + 1024;
     static bool attr_set = false;
     static int max_clusters = 0;
     if (!attr_set) {
-        PNPF_CHECK_CUDA(cudaFuncSetAttribute(patchconv_kernel<BN, PAIR, SUBPIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, PATCH_SMEM_MAX));
+        PNPF_CHECK_CUDA(cudaFuncSetAttribute(patchconv_kernel<BN, PAIR, SUBPIX, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, PATCH_SMEM_MAX));
         if (PAIR) {
             cudaLaunchConfig_t qc = {};
             qc.gridDim = dim3(num_sms() & ~1);
@@ -442,7 +443,7 @@ static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
             qa[0].id = cudaLaunchAttributeClusterDimension;
             qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
             qc.attrs = qa; qc.numAttrs = 1;
-            PNPF_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, patchconv_kernel<BN, PAIR, SUBPIX>, &qc));
+            PNPF_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, patchconv_kernel<BN, PAIR, SUBPIX, TG>, &qc));
             PNPF_REQUIRE(max_clusters >= 1, "no CTA pair of patchconv_kernel<%d> fits on this device", BN);
         }
         attr_set = true;
@@ -464,7 +465,7 @@ static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
     cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    PNPF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, patchconv_kernel<BN, PAIR, SUBPIX>, op.tmA, op.tmA2, PAIR ? op.tmBh : op.tmB, q));
+    PNPF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, patchconv_kernel<BN, PAIR, SUBPIX, TG>, op.tmA, op.tmA2, PAIR ? op.tmBh : op.tmB, q));
     return 0;
 }
 
@@ -530,6 +531,13 @@ int launch_tc(const TcOp& op, cudaStream_t s) {
             if (op.BN == 64) return pair ? launch_patch_t<64, true, true>(op, s) : launch_patch_t<64, false, true>(op, s);
             if (op.BN == 128) return pair ? launch_patch_t<128, true, true>(op, s) : launch_patch_t<128, false, true>(op, s);
             if (op.BN == 256) return pair ? launch_patch_t<256, true, true>(op, s) : launch_patch_t<256, false, true>(op, s);
+        }
+        // opt-in (PNPF_PATCH_TG=3): three taps per weight-ring slot -> one barrier wait + one commit per 12 MMAs; needs >= 2 slots
+        static const bool tg3 = getenv("PNPF_PATCH_TG") != nullptr && atoi(getenv("PNPF_PATCH_TG")) == 3;
+        if (tg3 && (pair ? op.patch_nb_pair : op.pp.nb) >= 6) {
+            if (op.BN == 64) return pair ? launch_patch_t<64, true, false, 3>(op, s) : launch_patch_t<64, false, false, 3>(op, s);
+            if (op.BN == 128) return pair ? launch_patch_t<128, true, false, 3>(op, s) : launch_patch_t<128, false, false, 3>(op, s);
+            if (op.BN == 256) return pair ? launch_patch_t<256, true, false, 3>(op, s) : launch_patch_t<256, false, false, 3>(op, s);
         }
         if (op.BN == 64) return pair ? launch_patch_t<64, true>(op, s) : launch_patch_t<64, false>(op, s);
         if (op.BN == 128) return pair ? launch_patch_t<128, true>(op, s) : launch_patch_t<128, false>(op, s);

@@ -21,6 +21,11 @@
 // 4 taps each replace one launch with 9 taps on a 4x larger tensor — 2.25x fewer FLOPs, and the upsampled tensor is never
 // materialised.  In the padded-linear space tap (i,j) is simply patch-row offset (a+i)*P + (b+j); the epilogue scatters the
 // tile to the stride-2 lattice of the high-resolution output.
+//
+// TG (opt-in, PNPF_PATCH_TG=3): taps per weight-ring slot.  The MMA issuer pays a barrier wait and a tcgen05.commit per weight
+// slot (~ 100 clocks), which is exposed when the four MMAs of a tap are short (N = 128: 4 x 64 clocks, measured ~ 90 per MMA;
+// N = 64: 4 x 32): with TG = 3 a slot holds the three taps (kh, 0..2) of a kernel row, so the issuer waits and commits once per
+// 12 MMAs.  Same arithmetic in the same order.
 #pragma once
 #include "pnpf_gemm.cuh"
 
@@ -53,7 +58,7 @@ struct PatchCfg {
     static_assert(BN == 64 || BN == 128 || BN == 256, "patch conv output widths");
 };
 
-template <int BN, bool PAIR, bool SUBPIX = false>
+template <int BN, bool PAIR, bool SUBPIX = false, int TG = 1>
 __global__ void __launch_bounds__(PatchCfg<BN, PAIR>::THREADS, 1)
 patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ PatchConvParams p) {
@@ -62,7 +67,7 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;                                    // [na] patches
     uint8_t* b_ring = smem + p.na * p.patch_bytes;             // [nb] weight tiles
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + p.nb * Cfg::B_BYTES);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + p.nb * (TG * Cfg::B_BYTES));      // nb slots of TG weight tiles
     uint64_t* a_empty = a_full + Cfg::MAX_A;
     uint64_t* b_full = a_empty + Cfg::MAX_A;
     uint64_t* b_empty = b_full + Cfg::MAX_B;
@@ -147,24 +152,51 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int u = unit0; u < total_units; u += unit_step) {
             for (int c = 0; c < nch; ++c) {
                 const int ntap = c < p.kchunks ? (SUBPIX ? 4 : 9) : 1;
-                for (int t = 0; t < ntap; ++t) {
-                    PNPF_TIMED_WAIT(&b_empty[slot], phase ^ 1, c_wait);
-                    uint8_t* dst = b_ring + slot * Cfg::B_BYTES;
-                    if (elect_one_sync()) {
-                        // packed K order (pack_conv_weight): (kh, kw, cin) for the 3x3 part, then the 1x1 source channels
-                        const int tap = SUBPIX ? t : (t + tap_rot) % 9;      // SUBPIX: packed K order (i, j, cin), 4 taps
-                        const int k0 = c < p.kchunks ? (tap * p.kchunks + c) * 64 : (9 * p.kchunks + (c - p.kchunks)) * 64;
-                        if constexpr (PAIR) {
-                            const uint32_t fb = mapa_u32(smem_u32(&b_full[slot]), 0);
-                            if (rank == 0) mbar_arrive_expect_tx(&b_full[slot], 2 * Cfg::B_BYTES);
-                            tma_load_3d_pair(dst, &tmB, fb, k0, static_cast<int>(rank) * Cfg::B_ROWS, 0);
-                        } else {
-                            mbar_arrive_expect_tx(&b_full[slot], Cfg::B_BYTES);
-                            tma_load_3d(dst, &tmB, &b_full[slot], k0, 0, 0);
+                if constexpr (TG == 1) {
+                    for (int t = 0; t < ntap; ++t) {
+                        PNPF_TIMED_WAIT(&b_empty[slot], phase ^ 1, c_wait);
+                        uint8_t* dst = b_ring + slot * Cfg::B_BYTES;
+                        if (elect_one_sync()) {
+                            // packed K order (pack_conv_weight): (kh, kw, cin) for the 3x3 part, then the 1x1 source channels
+                            const int tap = SUBPIX ? t : (t + tap_rot) % 9;      // SUBPIX: packed K order (i, j, cin), 4 taps
+                            const int k0 = c < p.kchunks ? (tap * p.kchunks + c) * 64 : (9 * p.kchunks + (c - p.kchunks)) * 64;
+                            if constexpr (PAIR) {
+                                const uint32_t fb = mapa_u32(smem_u32(&b_full[slot]), 0);
+                                if (rank == 0) mbar_arrive_expect_tx(&b_full[slot], 2 * Cfg::B_BYTES);
+                                tma_load_3d_pair(dst, &tmB, fb, k0, static_cast<int>(rank) * Cfg::B_ROWS, 0);
+                            } else {
+                                mbar_arrive_expect_tx(&b_full[slot], Cfg::B_BYTES);
+                                tma_load_3d(dst, &tmB, &b_full[slot], k0, 0, 0);
+                            }
                         }
+                        __syncwarp();
+                        if (++slot == p.nb) { slot = 0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    if (++slot == p.nb) { slot = 0; phase ^= 1; }
+                } else {
+                    static_assert(TG == 1 || !SUBPIX, "tap groups are for the 3x3 form");
+                    for (int t0 = 0; t0 < ntap; t0 += TG) {
+                        const int ng = min(TG, ntap - t0);           // the three taps of a kernel row, or the single 1x1 tap
+                        PNPF_TIMED_WAIT(&b_empty[slot], phase ^ 1, c_wait);
+                        uint8_t* dst = b_ring + slot * (TG * Cfg::B_BYTES);
+                        if (elect_one_sync()) {
+                            if constexpr (PAIR) {
+                                const uint32_t fb = mapa_u32(smem_u32(&b_full[slot]), 0);
+                                if (rank == 0) mbar_arrive_expect_tx(&b_full[slot], 2 * ng * Cfg::B_BYTES);
+                                for (int j = 0; j < ng; ++j) {
+                                    const int k0 = c < p.kchunks ? ((t0 + j) * p.kchunks + c) * 64 : (9 * p.kchunks + (c - p.kchunks)) * 64;
+                                    tma_load_3d_pair(dst + j * Cfg::B_BYTES, &tmB, fb, k0, static_cast<int>(rank) * Cfg::B_ROWS, 0);
+                                }
+                            } else {
+                                mbar_arrive_expect_tx(&b_full[slot], ng * Cfg::B_BYTES);
+                                for (int j = 0; j < ng; ++j) {
+                                    const int k0 = c < p.kchunks ? ((t0 + j) * p.kchunks + c) * 64 : (9 * p.kchunks + (c - p.kchunks)) * 64;
+                                    tma_load_3d(dst + j * Cfg::B_BYTES, &tmB, &b_full[slot], k0, 0, 0);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (++slot == p.nb) { slot = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -192,38 +224,73 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_fence_after();
                     const uint32_t pa = smem_u32(a_ring + aslot * p.patch_bytes);
                     const int ntap = c < p.kchunks ? (SUBPIX ? 4 : 9) : 1;
-                    for (int t = 0; t < ntap; ++t) {
-                        PNPF_TIMED_WAIT(&b_full[bslot], bphase, c_bfull);
-                        tc_fence_after();
-                        int kh, kw;
-                        if constexpr (SUBPIX) {
-                            kh = p.sp_a + (t >> 1);
-                            kw = p.sp_b + (t & 1);
-                        } else {
-                            const int tap = ntap == 9 ? (t + tap_rot) % 9 : 4;
-                            kh = tap / 3;
-                            kw = tap - 3 * kh;
-                        }
-                        const uint64_t adesc = make_smem_desc<128>(pa + static_cast<uint32_t>((kh * p.P + kw + a_shift) * 128));
-                        const uint64_t bdesc = make_smem_desc<128>(smem_u32(b_ring + bslot * Cfg::B_BYTES));
-                        if (elect_one_sync()) {
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
-                                else umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
-                            }
-                            if constexpr (PAIR) {
-                                umma_commit_pair(&b_empty[bslot]);
-                                if (t == ntap - 1) umma_commit_pair(&a_empty[aslot]);
-                                if (t == ntap - 1 && c == nch - 1) umma_commit_pair(&tfull_bar[acc]);
+                    if constexpr (TG == 1) {
+                        for (int t = 0; t < ntap; ++t) {
+                            PNPF_TIMED_WAIT(&b_full[bslot], bphase, c_bfull);
+                            tc_fence_after();
+                            int kh, kw;
+                            if constexpr (SUBPIX) {
+                                kh = p.sp_a + (t >> 1);
+                                kw = p.sp_b + (t & 1);
                             } else {
-                                umma_commit(&b_empty[bslot]);
-                                if (t == ntap - 1) umma_commit(&a_empty[aslot]);
-                                if (t == ntap - 1 && c == nch - 1) umma_commit(&tfull_bar[acc]);
+                                const int tap = ntap == 9 ? (t + tap_rot) % 9 : 4;
+                                kh = tap / 3;
+                                kw = tap - 3 * kh;
                             }
+                            const uint64_t adesc = make_smem_desc<128>(pa + static_cast<uint32_t>((kh * p.P + kw + a_shift) * 128));
+                            const uint64_t bdesc = make_smem_desc<128>(smem_u32(b_ring + bslot * Cfg::B_BYTES));
+                            if (elect_one_sync()) {
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
+                                    else umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
+                                }
+                                if constexpr (PAIR) {
+                                    umma_commit_pair(&b_empty[bslot]);
+                                    if (t == ntap - 1) umma_commit_pair(&a_empty[aslot]);
+                                    if (t == ntap - 1 && c == nch - 1) umma_commit_pair(&tfull_bar[acc]);
+                                } else {
+                                    umma_commit(&b_empty[bslot]);
+                                    if (t == ntap - 1) umma_commit(&a_empty[aslot]);
+                                    if (t == ntap - 1 && c == nch - 1) umma_commit(&tfull_bar[acc]);
+                                }
+                            }
+                            __syncwarp();
+                            if (++bslot == p.nb) { bslot = 0; bphase ^= 1; }
                         }
-                        __syncwarp();
-                        if (++bslot == p.nb) { bslot = 0; bphase ^= 1; }
+                    } else {
+                        for (int t0 = 0; t0 < ntap; t0 += TG) {
+                            const int ng = min(TG, ntap - t0);
+                            PNPF_TIMED_WAIT(&b_full[bslot], bphase, c_bfull);
+                            tc_fence_after();
+                            const uint32_t pb = smem_u32(b_ring + bslot * (TG * Cfg::B_BYTES));
+                            if (elect_one_sync()) {
+                                for (int j = 0; j < ng; ++j) {
+                                    const int t = t0 + j;
+                                    const int tap = ntap == 9 ? t : 4;
+                                    const int kh = tap / 3, kw = tap - 3 * kh;
+                                    const uint64_t adesc = make_smem_desc<128>(pa + static_cast<uint32_t>((kh * p.P + kw + a_shift) * 128));
+                                    const uint64_t bdesc = make_smem_desc<128>(pb + static_cast<uint32_t>(j * Cfg::B_BYTES));
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk) {
+                                        if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
+                                        else umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
+                                    }
+                                }
+                                const bool last = t0 + ng == ntap;
+                                if constexpr (PAIR) {
+                                    umma_commit_pair(&b_empty[bslot]);
+                                    if (last) umma_commit_pair(&a_empty[aslot]);
+                                    if (last && c == nch - 1) umma_commit_pair(&tfull_bar[acc]);
+                                } else {
+                                    umma_commit(&b_empty[bslot]);
+                                    if (last) umma_commit(&a_empty[aslot]);
+                                    if (last && c == nch - 1) umma_commit(&tfull_bar[acc]);
+                                }
+                            }
+                            __syncwarp();
+                            if (++bslot == p.nb) { bslot = 0; bphase ^= 1; }
+                        }
                     }
                     if (++aslot == p.na) { aslot = 0; aphase ^= 1; }
                 }
