@@ -469,16 +469,17 @@ static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
     return 0;
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, int TG = 1>
 static int launch_patchgn_t(const TcOp& op, cudaStream_t stream) {
     using Cfg = PatchGnCfg<BN, PAIR>;
     PatchGnParams q = op.gp;
     if (PAIR) q.nb = op.patch_nb_pair;
-    const int smem = q.na * q.patch_bytes + q.nb * Cfg::B_BYTES + Cfg::BAR_BYTES + Cfg::TAB_BYTES + 1024;
+    q.nb /= TG;                                       // ring depth in slots of TG weight tiles (PNPF_PATCH_TG)
+    const int smem = q.na * q.patch_bytes + q.nb * TG * Cfg::B_BYTES + Cfg::BAR_BYTES + Cfg::TAB_BYTES + 1024;
     static bool attr_set = false;
     static int max_clusters = 0;
     if (!attr_set) {
-        PNPF_CHECK_CUDA(cudaFuncSetAttribute(patchgn_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, PATCH_SMEM_MAX));
+        PNPF_CHECK_CUDA(cudaFuncSetAttribute(patchgn_kernel<BN, PAIR, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, PATCH_SMEM_MAX));
         if (PAIR) {                                   // same query as the plain patch kernel (one CTA per SM)
             cudaLaunchConfig_t qc = {};
             qc.gridDim = dim3(num_sms() & ~1);
@@ -488,7 +489,7 @@ static int launch_patchgn_t(const TcOp& op, cudaStream_t stream) {
             qa[0].id = cudaLaunchAttributeClusterDimension;
             qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
             qc.attrs = qa; qc.numAttrs = 1;
-            PNPF_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, patchgn_kernel<BN, PAIR>, &qc));
+            PNPF_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, patchgn_kernel<BN, PAIR, TG>, &qc));
             PNPF_REQUIRE(max_clusters >= 1, "no CTA pair of patchgn_kernel<%d> fits on this device", BN);
         }
         attr_set = true;
@@ -510,7 +511,7 @@ static int launch_patchgn_t(const TcOp& op, cudaStream_t stream) {
     cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    PNPF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, patchgn_kernel<BN, PAIR>, op.tmA, op.tmAb, op.tmA2, op.tmA2b, PAIR ? op.tmBh : op.tmB, q));
+    PNPF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, patchgn_kernel<BN, PAIR, TG>, op.tmA, op.tmAb, op.tmA2, op.tmA2b, PAIR ? op.tmBh : op.tmB, q));
     return 0;
 }
 
@@ -518,6 +519,12 @@ int launch_tc(const TcOp& op, cudaStream_t s) {
     if (op.kind == 3) {
         static const bool no_pair = getenv("PNPF_NO_PAIR") != nullptr;
         const bool pair = !no_pair && op.gp.n_img % 2 == 0;
+        static const bool tg3 = getenv("PNPF_PATCH_TG") != nullptr && atoi(getenv("PNPF_PATCH_TG")) == 3;
+        if (tg3 && (pair ? op.patch_nb_pair : op.gp.nb) >= 6) {
+            if (op.BN == 64) return pair ? launch_patchgn_t<64, true, 3>(op, s) : launch_patchgn_t<64, false, 3>(op, s);
+            if (op.BN == 128) return pair ? launch_patchgn_t<128, true, 3>(op, s) : launch_patchgn_t<128, false, 3>(op, s);
+            if (op.BN == 256) return pair ? launch_patchgn_t<256, true, 3>(op, s) : launch_patchgn_t<256, false, 3>(op, s);
+        }
         if (op.BN == 64) return pair ? launch_patchgn_t<64, true>(op, s) : launch_patchgn_t<64, false>(op, s);
         if (op.BN == 128) return pair ? launch_patchgn_t<128, true>(op, s) : launch_patchgn_t<128, false>(op, s);
         if (op.BN == 256) return pair ? launch_patchgn_t<256, true>(op, s) : launch_patchgn_t<256, false>(op, s);

@@ -52,7 +52,7 @@ struct PatchGnCfg {
     static_assert(BN == 64 || BN == 128 || BN == 256, "patch conv output widths");
 };
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, int TG = 1>      // TG: taps per weight-ring slot (1, or 3 = a kernel row: see pnpf_patchconv.cuh)
 __global__ void __launch_bounds__(PatchGnCfg<BN, PAIR>::THREADS, 1)
 patchgn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAb,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA2b,
@@ -62,7 +62,7 @@ patchgn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;                                    // [na] patches
     uint8_t* b_ring = smem + p.na * p.patch_bytes;             // [nb] weight tiles
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + p.nb * Cfg::B_BYTES);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + p.nb * (TG * Cfg::B_BYTES));      // nb slots of TG weight tiles
     uint64_t* a_empty = a_full + Cfg::MAX_A;
     uint64_t* a_ready = a_empty + Cfg::MAX_A;
     uint64_t* b_full = a_ready + Cfg::MAX_A;
@@ -148,19 +148,25 @@ patchgn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int u = unit0; u < total_units; u += unit_step) {
             for (int c = 0; c < nch; ++c) {
                 const int ntap = c < p.kchunks ? 9 : 1;
-                for (int t = 0; t < ntap; ++t) {
+                for (int t0 = 0; t0 < ntap; t0 += TG) {
+                    const int ng = min(TG, ntap - t0);               // TG = 3: the three taps of a kernel row share a slot
                     mbar_wait(&b_empty[slot], phase ^ 1);
-                    uint8_t* dst = b_ring + slot * Cfg::B_BYTES;
+                    uint8_t* dst = b_ring + slot * (TG * Cfg::B_BYTES);
                     if (elect_one_sync()) {
-                        // packed K order (pack_conv_weight): (kh, kw, cin) for the 3x3 part, then the 1x1 source channels
-                        const int k0 = c < p.kchunks ? (t * p.kchunks + c) * 64 : (9 * p.kchunks + (c - p.kchunks)) * 64;
                         if constexpr (PAIR) {
-                            const uint32_t fb = mapa_u32(smem_u32(&b_full[slot]), 0);
-                            if (rank == 0) mbar_arrive_expect_tx(&b_full[slot], 2 * Cfg::B_BYTES);
-                            tma_load_3d_pair(dst, &tmB, fb, k0, static_cast<int>(rank) * Cfg::B_ROWS, 0);
+                            if (rank == 0) mbar_arrive_expect_tx(&b_full[slot], 2 * ng * Cfg::B_BYTES);
                         } else {
-                            mbar_arrive_expect_tx(&b_full[slot], Cfg::B_BYTES);
-                            tma_load_3d(dst, &tmB, &b_full[slot], k0, 0, 0);
+                            mbar_arrive_expect_tx(&b_full[slot], ng * Cfg::B_BYTES);
+                        }
+                        for (int j = 0; j < ng; ++j) {
+                            // packed K order (pack_conv_weight): (kh, kw, cin) for the 3x3 part, then the 1x1 source channels
+                            const int k0 = c < p.kchunks ? ((t0 + j) * p.kchunks + c) * 64 : (9 * p.kchunks + (c - p.kchunks)) * 64;
+                            if constexpr (PAIR) {
+                                const uint32_t fb = mapa_u32(smem_u32(&b_full[slot]), 0);
+                                tma_load_3d_pair(dst + j * Cfg::B_BYTES, &tmB, fb, k0, static_cast<int>(rank) * Cfg::B_ROWS, 0);
+                            } else {
+                                tma_load_3d(dst + j * Cfg::B_BYTES, &tmB, &b_full[slot], k0, 0, 0);
+                            }
                         }
                     }
                     __syncwarp();
@@ -189,27 +195,33 @@ patchgn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc_fence_after();
                     const uint32_t pa = smem_u32(a_ring + aslot * p.patch_bytes);
                     const int ntap = c < p.kchunks ? 9 : 1;
-                    for (int t = 0; t < ntap; ++t) {
+                    for (int t0 = 0; t0 < ntap; t0 += TG) {
+                        const int ng = min(TG, ntap - t0);
                         mbar_wait(&b_full[bslot], bphase);
                         tc_fence_after();
-                        const int tap = ntap == 9 ? t : 4;
-                        const int kh = tap / 3, kw = tap - 3 * kh;
-                        const uint64_t adesc = make_smem_desc<128>(pa + static_cast<uint32_t>((kh * p.P + kw + a_shift) * 128));
-                        const uint64_t bdesc = make_smem_desc<128>(smem_u32(b_ring + bslot * Cfg::B_BYTES));
+                        const uint32_t pb = smem_u32(b_ring + bslot * (TG * Cfg::B_BYTES));
                         if (elect_one_sync()) {
+                            for (int j = 0; j < ng; ++j) {
+                                const int t = t0 + j;
+                                const int tap = ntap == 9 ? t : 4;
+                                const int kh = tap / 3, kw = tap - 3 * kh;
+                                const uint64_t adesc = make_smem_desc<128>(pa + static_cast<uint32_t>((kh * p.P + kw + a_shift) * 128));
+                                const uint64_t bdesc = make_smem_desc<128>(pb + static_cast<uint32_t>(j * Cfg::B_BYTES));
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
-                                else umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
+                                    else umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
+                                }
                             }
+                            const bool last = t0 + ng == ntap;
                             if constexpr (PAIR) {
                                 umma_commit_pair(&b_empty[bslot]);
-                                if (t == ntap - 1) umma_commit_pair(&a_empty[aslot]);
-                                if (t == ntap - 1 && c == nch - 1) umma_commit_pair(&tfull_bar[acc]);
+                                if (last) umma_commit_pair(&a_empty[aslot]);
+                                if (last && c == nch - 1) umma_commit_pair(&tfull_bar[acc]);
                             } else {
                                 umma_commit(&b_empty[bslot]);
-                                if (t == ntap - 1) umma_commit(&a_empty[aslot]);
-                                if (t == ntap - 1 && c == nch - 1) umma_commit(&tfull_bar[acc]);
+                                if (last) umma_commit(&a_empty[aslot]);
+                                if (last && c == nch - 1) umma_commit(&tfull_bar[acc]);
                             }
                         }
                         __syncwarp();
