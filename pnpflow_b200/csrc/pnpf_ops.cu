@@ -83,7 +83,10 @@ static bool rowconv_shape(const ConvDesc& d, RowShape& r) {
         const int stage = staged ? n_epi_warps * 32 * 64 : 0;
         int nslot = ((dual ? ROWCONV_DUAL_SMEM - 2048 - 1024 : ROWCONV_SMEM_BUDGET) - w_bytes - stage) / r.slot_bytes;
         if (nslot > (dual ? 6 : 8)) nslot = dual ? 6 : 8;
-        if (nslot >= (nsplit == 1 ? 4 : 3)) {
+        // (opt-in experiment PNPF_ROW_MINSLOT=3: accept three row slots for the unsplit layout, which keeps the level-1 conv2 +
+        // shortcut layers on N = 192 MMAs with one read of every row instead of two half-width CTAs reading every row twice)
+        static const int min_slots = getenv("PNPF_ROW_MINSLOT") ? atoi(getenv("PNPF_ROW_MINSLOT")) : 4;
+        if (nslot >= (nsplit == 1 ? (min_slots >= 2 ? min_slots : 4) : 3)) {
             r.BN = BN; r.nsplit = nsplit; r.w_bytes = w_bytes; r.nslot = nslot; r.stage_bytes = stage; r.n_epi = n_epi;
             return true;
         }

@@ -13,8 +13,10 @@ PNPF_PATCH_TG=3 run python -m pytest tests/test_gpu_layers.py tests/test_gpu_une
 # fused GroupNorm / concat inputs in the patch kernel
 PNPF_PATCH_GN=1 PNPF_TEST_PATCH_GN=1 run python -m pytest tests/test_gpu_zz_patchgn.py -m gpu -q -x
 PNPF_PATCH_GN=1 PNPF_PATCH_TG=3 PNPF_TEST_PATCH_GN=1 run python -m pytest tests/test_gpu_zz_patchgn.py -m gpu -q -x
+# three row slots for the unsplit row-kernel layout (host-side choice only: same kernel)
+PNPF_ROW_MINSLOT=3 run python -m pytest tests/test_gpu_unet.py -m gpu -q -x
 # same-box A/B (only meaningful for the paths that passed above)
 echo "=== A/B"
-AB_ROUNDS=2 timeout 400 python tools/ab_env.py "base:" "subpix:PNPF_SUBPIXEL_UP=1" "tg3:PNPF_PATCH_TG=3" "gn256:PNPF_PATCH_GN=256" "gn:PNPF_PATCH_GN=1" \
+AB_ROUNDS=2 timeout 400 python tools/ab_env.py "base:" "minslot3:PNPF_ROW_MINSLOT=3" "subpix:PNPF_SUBPIXEL_UP=1" "tg3:PNPF_PATCH_TG=3" "gn256:PNPF_PATCH_GN=256" "gn:PNPF_PATCH_GN=1" \
     "gn+tg3:PNPF_PATCH_GN=1,PNPF_PATCH_TG=3" "tg3+subpix:PNPF_PATCH_TG=3,PNPF_SUBPIXEL_UP=1" \
     "all256:PNPF_PATCH_TG=3,PNPF_SUBPIXEL_UP=1,PNPF_PATCH_GN=256" "all:PNPF_PATCH_TG=3,PNPF_SUBPIXEL_UP=1,PNPF_PATCH_GN=1" 2>&1 | grep -v Warning | tail -24
