@@ -36,6 +36,8 @@ CONFIGS = {
     "cfg3": dict(net="celeba128", problem="gaussian_deblurring_FFT", b_per_gpu=32, T=100, S=5, sigma=0.05, alpha=0.01),
     "cfg4": dict(net="afhq256", problem="superresolution", b_per_gpu=16, T=100, S=5, sigma=0.05, alpha=0.3),
     "cfg5": dict(net="afhq256", problem="random_inpainting", b_per_gpu=32, T=200, S=5, sigma=0.01, alpha=0.01),
+    # S is not stated for cfg2-4 -> the reference default S=5 is the headline, S=1 (demo notebook) reported next to it
+    "cfg4s1": dict(net="afhq256", problem="superresolution", b_per_gpu=16, T=100, S=1, sigma=0.05, alpha=0.3),
 }
 METRIC = "restored images/sec at 100 PnP steps, 256x256x3"
 UNIT = "images/s"
@@ -91,11 +93,71 @@ class ClockSampler(threading.Thread):
 
 
 def peaks():
+    """Roofline denominators: burst bf16 for a kernel timed alone (per-op CUDA events), sustained bf16 for the whole step."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(tflops=d.get("bf16_tflops_sustained", d.get("bf16_tflops")), hbm=d.get("hbm_gbs"), src="measured (MEASURED_PEAKS.json, sustained bf16)")
-    return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+        burst = d.get("bf16_tflops")
+        return dict(burst=burst, sustained=d.get("bf16_tflops_sustained", burst), hbm=d.get("hbm_gbs"),
+                    src="measured (MEASURED_PEAKS.json: bf16_tflops burst for per-kernel numbers, bf16_tflops_sustained for the whole step, hbm_gbs)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+def kernel_family(impl):
+    """'rowconv<32,32,1> nsplit=..' -> ('rowconv', 'rowconv<32,32,1>'): kernel FUNCTION and template instantiation."""
+    inst = impl.split(">")[0] + ">" if "<" in impl else impl.split(" ")[0]
+    return inst.split("<")[0], inst
+
+
+def ncu_traffic(kernel_prefix):
+    """DRAM bytes per launch of a kernel from the newest committed `ncu --set full` summary (tools/summarize_profiles.py)."""
+    for name in ("r02_kernel_dram_bytes.json", "r01_kernel_dram_bytes.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(tp):
+            continue
+        try:
+            ks = json.load(open(tp))["kernels"]
+        except Exception:
+            continue
+        hits = [v for k, v in ks.items() if k.startswith(kernel_prefix) and v.get("dram_bytes_per_launch_mean")]
+        if hits:
+            n = sum(h.get("launches", 1) for h in hits)
+            return sum(h["dram_bytes_per_launch_mean"] * h.get("launches", 1) for h in hits) / n, name
+    return None, None
+
+
+def time_hbm_kernels(sess, x, y, pk, K=10):
+    """The per-pixel kernels of one PnP step timed ALONE with CUDA events, L2 flushed (a 256 MB write)
+    before every launch; achieved = algorithmic bytes / time against the measured copy bandwidth."""
+    from pnpflow_b200 import _lib
+    lib = _lib.load()
+    S, n = sess.S, sess.n
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=x.device)
+    sp = _lib.stream_ptr
+
+    def timed(fn):
+        tot = 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(K):
+            flush.fill_(1)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / K
+    opname = type(sess.op).__name__
+    sf = getattr(sess.op, "sf", 1)
+    by_datafit = {"Superresolution": (8 + 4.0 / (sf * sf)) * n, "GaussianDeblurring": 2 * 12.0 * n}.get(opname, 12.0 * n)
+    sess.eps.normal_()
+    out = []
+    for name, fn, by in (
+            ("datafit_step[" + opname + "]", lambda: sess.op.datafit_step(x, y, 0.5, out=sess.z), by_datafit),
+            ("interp", lambda: _lib.check(lib.pnpf_interp(sess.z.data_ptr(), sess.eps.data_ptr(), 0.3, sess.zt.data_ptr(), n, S, sp())), (4.0 + 8.0 * S) * n),
+            ("push_accum", lambda: _lib.check(lib.pnpf_push_accum(sess.zt.data_ptr(), sess.v.data_ptr(), 0.3, S, sess.xbuf[0].data_ptr(), n, sp())), (8.0 * S + 4.0) * n)):
+        ms = timed(fn)
+        tr, src = ncu_traffic({"datafit_step": "blur" if opname == "GaussianDeblurring" else "datafit_diag"}.get(name.split("[")[0], name))
+        out.append({"kernel": name, "ms": ms, "algorithmic_bytes": by, "achieved": by / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": by / (ms * 1e-3) / 1e9 / pk["hbm"], "traffic": tr, "traffic_source": src})
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -194,9 +256,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS))
+    ap.add_argument("--weights", default="recipe", choices=["recipe", "untouched"],
+                    help="recipe: SURVEY §8d re-drawn init_scale=0 layers; untouched: the literal random init (gain 1e-10 there)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-shard-check", action="store_true")
     a = ap.parse_args()
     K, W = a.steps, max(a.warmup, 3 if a.impl == "engine" else 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -205,6 +270,7 @@ def main():
     c = CONFIGS[a.config]
     cfg_desc = {"workload": f"{a.config}: {c['net']} {c['problem']} T={c['T']} S={c['S']} {c['b_per_gpu']} images/GPU",
                 "global_batch": c["b_per_gpu"] * max(world, a.gpus if world == 1 else world), "parallelism": f"batch-sharded dp{world}",
+                "weights": a.weights,
                 "l2": "per-step working set (activations of the S*B U-Net batch, GBs) >> 126 MB L2; no explicit flush"}
 
     if a.impl == "reference":
@@ -231,12 +297,15 @@ def main():
     net = synth.NETS[c["net"]]
     side, B, S, T = net["input_height"], c["b_per_gpu"], c["S"], c["T"]
     Btot = B * world
-    sd = synth.random_state_dict(net, seed=0)
+    if a.weights == "untouched":
+        sd = synth.random_state_dict(net, seed=0, inner_gain=1e-10, end_gain=1e-10)     # models.py:84,137,212-216,432
+    else:
+        sd = synth.random_state_dict(net, seed=0)
     eng = P.UNetEngine(net, sd, device=dev, max_batch=S * B)
     op_full = make_operator(P, c["problem"], side)
     lo, hi = sharding.shard_bounds(Btot, world, rank)
     op = sharding.shard_operator(op_full, lo, hi, Btot)
-    # measurements: rank 0 synthesises the full batch on its GPU and scatters the shards over NCCL (outside the timed region)
+    # measurements: rank 0 synthesises the full batch on its GPU and scatters the shards over NCCL (outside the step loop)
     if rank == 0:
         clean = synth.synthetic_clean(Btot, 3, side, 1234 + 4).to(dev)
         y_full = op_full.H(clean)
@@ -246,28 +315,54 @@ def main():
     else:
         y_full = None
         y_shape = None
-    if world > 1:
-        obj = [y_shape]
-        dist.broadcast_object_list(obj, src=0)
-        y_shape = obj[0]
-        t_sc0 = time.perf_counter()
-        y = sharding.scatter_batch(y_full, y_shape, torch.float32, dev)
-        torch.cuda.synchronize()
-        scatter_ms = (time.perf_counter() - t_sc0) * 1e3
-    else:
-        y, scatter_ms = y_full, 0.0
-    sess = P.PnPFlowSession(eng, op, tuple(y.shape), steps_pnp=T, lr_pnp=1.0, alpha=c["alpha"], num_samples=S, device=dev)
-    torch.manual_seed(1)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        if world > 1:
+            tv = torch.tensor([v], device=dev, dtype=torch.float64)
+            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+            return float(tv.item())
+        return v
+
+    scatter_ms = scatter_first_ms = 0.0
+    if world > 1:
+        obj = [y_shape]
+        dist.broadcast_object_list(obj, src=0)
+        y_shape = obj[0]
+        # first scatter = lazy NCCL communicator / channel setup (hundreds of ms, once per process); the steady-state
+        # scatter a long-running job pays per batch is timed on the second call, on the device, max over ranks
+        t_sc0 = time.perf_counter()
+        y = sharding.scatter_batch(y_full, y_shape, torch.float32, dev)
+        torch.cuda.synchronize()
+        scatter_first_ms = (time.perf_counter() - t_sc0) * 1e3
+        sharding.gather_batch(torch.zeros((hi - lo, 3, side, side), device=dev), Btot)       # warms the all-gather path too
+        barrier()
+        es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es0.record()
+        y = sharding.scatter_batch(y_full, y_shape, torch.float32, dev)
+        es1.record()
+        torch.cuda.synchronize()
+        scatter_ms = max_over_ranks(es0.elapsed_time(es1))
+    else:
+        y = y_full
+    sess = P.PnPFlowSession(eng, op, tuple(y.shape), steps_pnp=T, lr_pnp=1.0, alpha=c["alpha"], num_samples=S, device=dev)
+    full_shape = (Btot, 3, side, side)
+
+    def noise_stream(seed):
+        """The reference's noise: torch.randn_like of the FULL batch per draw (pnp_flow.py:48).  One rank: the session draws
+        it itself (noise_it=None); sharded: every rank draws the full-batch tensor from the same seed and keeps its slice."""
+        torch.manual_seed(seed)
+        return iter(sharding.FullBatchNoise(full_shape, lo, hi, dev)) if world > 1 else None
+
     # ---------------- device-resident timing (value) ----------------
+    nz = noise_stream(1)
     x = sess.initial_state(y)
     for i in range(W):
-        x = sess.step(x, y, i)
+        x = sess.step(x, y, i, nz)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -275,15 +370,11 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        x = sess.step(x, y, W + i)
+        x = sess.step(x, y, W + i, nz)
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None
-    if world > 1:
-        tms = torch.tensor([ms], device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
     ms_per_step = ms / K
     value = Btot / (T * ms_per_step / 1e3)
     finite = bool(torch.isfinite(x).all())
@@ -295,30 +386,54 @@ def main():
     xe = sess.initial_state(y)
     for i in range(3):
         y_dev.copy_(y_host, non_blocking=True)
-        xe = sess.step(xe, y_dev, i)
+        xe = sess.step(xe, y_dev, i, nz)
         x_host.copy_(xe, non_blocking=True)
     barrier()
     e0.record()
     for i in range(K):
         y_dev.copy_(y_host, non_blocking=True)          # H2D of the step's input (pinned)
-        xe = sess.step(xe, y_dev, 3 + i)
+        xe = sess.step(xe, y_dev, 3 + i, nz)
         x_host.copy_(xe, non_blocking=True)             # D2H of the step's result
     e1.record()
     barrier()
-    ms_e = e0.elapsed_time(e1)
-    if world > 1:
-        tms = torch.tensor([ms_e], device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms_e = float(tms.item())
+    ms_e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = Btot / (T * (ms_e / K) / 1e3)
+    gather_ms = 0.0
     if world > 1:
-        t_g0 = time.perf_counter()
+        barrier()
+        e0.record()
         full = sharding.gather_batch(x, Btot)
+        e1.record()
         torch.cuda.synchronize()
-        gather_ms = (time.perf_counter() - t_g0) * 1e3
+        gather_ms = max_over_ranks(e0.elapsed_time(e1))
         assert full.shape[0] == Btot
-    else:
-        gather_ms = 0.0
+    # a whole batch through the job: scatter + T steps (host buffers) + gather
+    e2e_batch_value = Btot / ((T * (ms_e / K) + scatter_ms + gather_ms) / 1e3)
+
+    # ---------------- sharded == unsharded (N > 1): 2 steps from the same seed, all ranks vs rank 0 alone ----------------
+    shard_check = None
+    if world > 1 and not a.no_shard_check:
+        nz = noise_stream(77)
+        xs = sess.initial_state(y)
+        for i in range(2):
+            xs = sess.step(xs, y, 50 + i, nz)
+        full = sharding.gather_batch(xs, Btot)
+        barrier()
+        if rank == 0:
+            try:
+                sess1 = P.PnPFlowSession(eng, op_full, y_shape, steps_pnp=T, lr_pnp=1.0, alpha=c["alpha"], num_samples=S, device=dev)
+                torch.manual_seed(77)
+                x1 = sess1.initial_state(y_full)
+                for i in range(2):
+                    x1 = sess1.step(x1, y_full, 50 + i)              # world-1 semantics: randn_like of the full batch
+                d = (x1 - full).abs().max().item()
+                shard_check = {"what": "2 PnP steps, seed 77: gathered sharded result vs the same full batch run unsharded on rank 0",
+                               "max_abs_diff": d, "equal_within_1e-3": bool(d < 1e-3),
+                               "checksum_sharded": full.double().sum().item(), "checksum_unsharded": x1.double().sum().item()}
+                del sess1
+            except Exception as ex:
+                shard_check = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -337,69 +452,73 @@ def main():
     torch.cuda.synchronize()
     unet_replay_ms = e0.elapsed_time(e1) / 5
 
-    # ---------------- rooflines from per-op CUDA events of one U-Net evaluation (pnpf_profile_forward) ----------------
-    # Every op has algorithmic FLOPs and algorithmic HBM bytes (each operand read once, each output written once), so its
-    # roof is the slower of FLOPs / measured bf16 peak and bytes / measured copy bandwidth.  `roofline` proper is the
-    # DOMINANT kernel = the template instantiation with the largest share of the evaluation; the other kernels and the
-    # tensor-core aggregate (the north star's "fraction of the conv-GEMM roofline") are listed next to it.
+    # ---------------- rooflines ----------------
+    # Per-op CUDA events of one U-Net evaluation (pnpf_profile_forward).  Every op has algorithmic FLOPs and algorithmic HBM
+    # bytes (each operand read once, each output written once); its roof is the slower of FLOPs / BURST bf16 peak (a kernel timed
+    # alone) and bytes / measured copy bandwidth.  Kernels are grouped by kernel FUNCTION (rowconv / patchconv / conv_gemm /
+    # gn_apply ...); the per-instantiation list is kept under `instantiations`.  The headline `frac` is the WHOLE-STEP conv-GEMM
+    # fraction (the north star's metric): images/s x T x S x F_conv / sustained bf16 peak.
     prof = eng.profile(S * B)
     pk = peaks()
-    pk_fl, pk_by = pk["tflops"] * 1e12, pk["hbm"] * 1e9
+    pk_fl, pk_by = pk["burst"] * 1e12, pk["hbm"] * 1e9
 
-    def kernel_of(o):
-        impl = o.get("impl", "?")
-        return impl.split(">")[0] + ">" if "<" in impl else impl.split(" ")[0]
-
-    fams = {}
-    for o in prof:
-        f = fams.setdefault(kernel_of(o), dict(launches=0, ms=0.0, flops=0.0, bytes=0.0, roof_ms=0.0, tensor_roof_ms=0.0, hbm_roof_ms=0.0))
-        f["launches"] += 1; f["ms"] += o["ms"]; f["flops"] += o["flops"]; f["bytes"] += o["bytes"]
-        t_fl, t_by = o["flops"] / pk_fl * 1e3, o["bytes"] / pk_by * 1e3
-        f["roof_ms"] += max(t_fl, t_by); f["tensor_roof_ms"] += t_fl; f["hbm_roof_ms"] += t_by
-    total_ms = sum(f["ms"] for f in fams.values())
-    kernels = []
-    for name, f in sorted(fams.items(), key=lambda kv: -kv[1]["ms"]):
-        if f["ms"] <= 0:
-            continue
-        bound = "tensor" if f["tensor_roof_ms"] >= f["hbm_roof_ms"] else "hbm"
-        kernels.append({"kernel": name, "launches": f["launches"], "ms": f["ms"], "share": f["ms"] / total_ms, "bound": bound,
-                        "tflops": f["flops"] / (f["ms"] * 1e-3) / 1e12, "gbs": f["bytes"] / (f["ms"] * 1e-3) / 1e9,
-                        "frac_of_roof": f["roof_ms"] / f["ms"]})
+    def group(keyfn):
+        fams = {}
+        for o in prof:
+            f = fams.setdefault(keyfn(o), dict(launches=0, ms=0.0, flops=0.0, bytes=0.0, roof_ms=0.0, tensor_roof_ms=0.0, hbm_roof_ms=0.0))
+            f["launches"] += 1; f["ms"] += o["ms"]; f["flops"] += o["flops"]; f["bytes"] += o["bytes"]
+            t_fl, t_by = o["flops"] / pk_fl * 1e3, o["bytes"] / pk_by * 1e3
+            f["roof_ms"] += max(t_fl, t_by); f["tensor_roof_ms"] += t_fl; f["hbm_roof_ms"] += t_by
+        tot = sum(f["ms"] for f in fams.values())
+        rows = []
+        for name, f in sorted(fams.items(), key=lambda kv: -kv[1]["ms"]):
+            if f["ms"] <= 0:
+                continue
+            bound = "tensor" if f["tensor_roof_ms"] >= f["hbm_roof_ms"] else "hbm"
+            rows.append({"kernel": name, "launches": f["launches"], "ms": f["ms"], "share": f["ms"] / tot, "bound": bound,
+                         "tflops": f["flops"] / (f["ms"] * 1e-3) / 1e12, "gbs": f["bytes"] / (f["ms"] * 1e-3) / 1e9,
+                         "frac_of_tensor_burst": f["tensor_roof_ms"] / f["ms"], "frac_of_hbm": f["hbm_roof_ms"] / f["ms"],
+                         "frac_of_roof": f["roof_ms"] / f["ms"], "flops": f["flops"], "bytes": f["bytes"]})
+        return rows, tot
+    kernels, total_ms = group(lambda o: kernel_family(o.get("impl", "?"))[0])
+    insts, _ = group(lambda o: kernel_family(o.get("impl", "?"))[1])
     dom = kernels[0]
-    domf = fams[dom["kernel"]]
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (tools/summarize_profiles.py), per launch
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_kernel_dram_bytes.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp))["kernels"].get(dom["kernel"], {}).get("dram_bytes_per_launch_mean")
-        except Exception:
-            traffic = None
+    traffic, traffic_src = ncu_traffic(dom["kernel"])
     tc = [o for o in prof if o["kind"] == "tc"]
     simt = [o for o in prof if o["kind"] == "simt"]
     tc_ms, tc_fl = sum(o["ms"] for o in tc), sum(o["flops"] for o in tc)
     simt_ms, simt_by = sum(o["ms"] for o in simt), sum(o["bytes"] for o in simt)
-    ach = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    if dom["bound"] == "hbm":
-        r_ach, r_peak, r_unit = domf["bytes"] / domf["launches"] / (domf["ms"] / domf["launches"] * 1e-3) / 1e9, pk["hbm"], "GB/s"
-        per_launch = domf["bytes"] / domf["launches"]
-    else:
-        r_ach, r_peak, r_unit = domf["flops"] / domf["launches"] / (domf["ms"] / domf["launches"] * 1e-3) / 1e12, pk["tflops"], "TFLOP/s"
-        per_launch = domf["flops"] / domf["launches"]
-    roofline = {"bound": dom["bound"], "kernel": dom["kernel"], "achieved": r_ach, "peak": r_peak, "unit": r_unit,
-                "frac": r_ach / r_peak if r_peak else None, "traffic": traffic, "peak_source": pk["src"],
-                "launches": dom["launches"], "avg_launch_ms": domf["ms"] / domf["launches"], "algorithmic_per_launch": per_launch,
-                "algorithmic_bytes_per_launch": domf["bytes"] / domf["launches"],
-                "share_of_unet_eval": dom["share"],
-                "kernels": kernels,
-                "step_frac_of_roof": sum(f["roof_ms"] for f in fams.values()) / total_ms,
-                "tensor_aggregate": {"kernel": "all tensor-core launches of one U-Net evaluation (rowconv + patchconv + conv_gemm)",
-                                     "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"] if pk["tflops"] else None,
-                                     "launches": len(tc), "flops_per_eval_batch": tc_fl, "tc_ms_per_eval": tc_ms,
+    # whole step: executed tensor-core FLOPs of the engine plan (sub-pixel up convs execute 2.25x fewer MACs than the
+    # reference's upsample + 3x3 form) and the reference's algorithmic conv FLOPs (F_conv)
+    F_CONV_REF = {"afhq256": 188.37e9, "celeba128": 48.84e9}[c["net"]]
+    evals_per_s = value * T * S / world
+    ws_exec = evals_per_s * eng.flops_per_image / 1e12
+    ws_ref = evals_per_s * F_CONV_REF / 1e12
+    roofline = {"bound": "tensor", "kernel": "whole PnP step (all launches), conv-GEMM FLOPs of the reference U-Net",
+                "achieved": ws_ref, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": ws_ref / pk["sustained"],
+                "frac_executed_flops": ws_exec / pk["sustained"], "achieved_executed": ws_exec,
+                "flops_per_eval_reference": F_CONV_REF, "flops_per_eval_executed": eng.flops_per_image,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["src"],
+                "dominant_kernel": {"kernel": dom["kernel"], "launches": dom["launches"], "share_of_unet_eval": dom["share"], "bound": dom["bound"],
+                                    "achieved": dom["tflops"] if dom["bound"] == "tensor" else dom["gbs"],
+                                    "peak": pk["burst"] if dom["bound"] == "tensor" else pk["hbm"],
+                                    "unit": "TFLOP/s" if dom["bound"] == "tensor" else "GB/s",
+                                    "frac": dom["frac_of_tensor_burst"] if dom["bound"] == "tensor" else dom["frac_of_hbm"],
+                                    "frac_of_tensor_burst": dom["frac_of_tensor_burst"], "frac_of_hbm": dom["frac_of_hbm"],
+                                    "avg_launch_ms": dom["ms"] / dom["launches"],
+                                    "algorithmic_flops_per_launch": dom["flops"] / dom["launches"],
+                                    "algorithmic_bytes_per_launch": dom["bytes"] / dom["launches"],
+                                    "traffic_dram_bytes_per_launch_ncu": traffic},
+                "kernels": kernels, "instantiations": insts,
+                "tensor_aggregate": {"kernel": "all tensor-core launches of one U-Net evaluation, per-op events, vs BURST peak",
+                                     "achieved": tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else None, "peak": pk["burst"], "unit": "TFLOP/s",
+                                     "frac": tc_fl / (tc_ms * 1e-3) / 1e12 / pk["burst"] if tc_ms > 0 else None,
+                                     "launches": len(tc), "tc_ms_per_eval": tc_ms,
                                      "tc_share_of_eval": tc_ms / (tc_ms + simt_ms) if tc_ms + simt_ms > 0 else None},
                 "simt": {"achieved_gbs": simt_by / (simt_ms * 1e-3) / 1e9 if simt_ms > 0 else None, "peak_gbs": pk["hbm"],
                          "ms_per_eval": simt_ms, "algorithmic_bytes": simt_by},
-                "whole_step_conv_gemm_frac": (value * T * S * eng.flops_per_image / world) / (pk["tflops"] * 1e12) if pk["tflops"] else None}
+                "hbm_kernels": time_hbm_kernels(sess, x, y, pk),
+                "whole_step_conv_gemm_frac": ws_ref / pk["sustained"]}
 
     cpu = None
     if not a.no_cpu_baseline and world == 1:          # reported baseline: rank 0 at N=1 only
@@ -418,9 +537,13 @@ def main():
             "impl": "engine", "config": cfg_desc, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": y_host.numel() * 4, "d2h_bytes_per_step": x_host.numel() * 4,
                     "ms_per_step": ms_e / K},
+            "e2e_batch": {"value": e2e_batch_value, "unit": UNIT,
+                          "what": "one whole batch through the job: NCCL scatter of y + T steps with host buffers + NCCL gather of x"},
             "gpu_launches": K * sess.launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "torch_gpu_baseline": tgpu,
             "finite": finite, "unet_flops_per_image": eng.flops_per_image, "unet_launches_per_eval": eng.num_launches,
-            "unet_graph_replay_ms": unet_replay_ms, "scatter_ms": scatter_ms, "gather_ms": gather_ms, "workspace_gb": eng.workspace_bytes / 2 ** 30}
+            "unet_graph_replay_ms": unet_replay_ms, "scatter_ms": scatter_ms, "gather_ms": gather_ms,
+            "scatter_first_call_ms": scatter_first_ms, "noise": "torch Philox, full-batch randn per draw sliced per rank" if world > 1 else
+            "torch Philox randn_like per draw", "shard_check": shard_check, "workspace_gb": eng.workspace_bytes / 2 ** 30}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

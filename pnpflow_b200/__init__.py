@@ -12,7 +12,7 @@ importing this package never imports ``oracle`` and there is no CPU / PyTorch fa
 from .degradations import (BoxInpainting, Degradation, Denoising, GaussianDeblurring, PaintbrushInpainting,  # noqa: F401
                            RandomInpainting, Superresolution, as_engine_operator)
 from .engine import UNetEngine  # noqa: F401
-from .method import PNP_FLOW, PnPFlowSession, gamma_schedule, psnr, restore  # noqa: F401
+from .method import PNP_FLOW, PnPFlowSession, gamma_schedule, psnr, restore, step_time  # noqa: F401
 
 __all__ = ["PNP_FLOW", "PnPFlowSession", "restore", "UNetEngine", "Degradation", "Denoising", "BoxInpainting", "RandomInpainting",
-           "PaintbrushInpainting", "GaussianDeblurring", "Superresolution", "as_engine_operator", "gamma_schedule", "psnr"]
+           "PaintbrushInpainting", "GaussianDeblurring", "Superresolution", "as_engine_operator", "gamma_schedule", "psnr", "step_time"]

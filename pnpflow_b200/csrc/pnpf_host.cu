@@ -21,13 +21,33 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err.c_str(); }
 
+static std::mutex g_dev_mutex;
+static int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < DeviceCache::MAX_DEV) ? dev : 0;
+}
+bool DeviceCache::lookup(int* value) {
+    const int dev = current_device();
+    std::lock_guard<std::mutex> g(g_dev_mutex);
+    if (!set_[dev]) return false;
+    *value = val_[dev];
+    return true;
+}
+void DeviceCache::store(int value) {
+    const int dev = current_device();
+    std::lock_guard<std::mutex> g(g_dev_mutex);
+    val_[dev] = value;
+    set_[dev] = true;
+}
+
 int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    static DeviceCache cache;
+    int n = 0;
+    if (!cache.lookup(&n)) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, current_device());
         if (n <= 0) n = 148;
+        cache.store(n);
     }
     return n;
 }
@@ -92,9 +112,9 @@ template <int BK, int BN, bool PAIR>
 static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const GemmParams& p,
                     cudaStream_t stream) {
     using Cfg = GemmCfg<BK, BN, PAIR>;
-    static bool attr_set = false;
-    static int max_clusters = 0;
-    if (!attr_set) {
+    static DeviceCache cache;
+    int max_clusters = 0;
+    if (!cache.lookup(&max_clusters)) {
         PNPF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BK, BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES));
         if (PAIR) {                                       // how many CTA pairs (one per TPC) can be resident at once
@@ -109,7 +129,7 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUten
             PNPF_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, conv_gemm_kernel<BK, BN, PAIR>, &qc));
             PNPF_REQUIRE(max_clusters >= 1, "no CTA pair of conv_gemm_kernel<%d,%d> fits on this device", BK, BN);
         }
-        attr_set = true;
+        cache.store(max_clusters);
     }
     const long long tiles = (long long)p.n_img * p.tiles_h * p.tiles_w * p.n_tiles_n;
     if (tiles < 1) return 0;

@@ -34,7 +34,19 @@ const char* get_error();
         }                                  \
     } while (0)
 
-int num_sms();
+int num_sms();                      // of the CURRENT device (cached per device)
+
+// Kernel attributes (dynamic shared-memory opt-in) and occupancy answers are PER DEVICE: every launcher keeps one of these as a
+// function-local static and initialises it the first time it runs on a device.  lookup()/store() are guarded, a racing double
+// initialisation is harmless (the attribute calls are idempotent).
+struct DeviceCache {
+    static constexpr int MAX_DEV = 64;
+    bool lookup(int* value);        // false: not initialised for the current device yet
+    void store(int value);
+private:
+    int val_[MAX_DEV] = {};
+    bool set_[MAX_DEV] = {};
+};
 
 // ---- tensor maps ----
 // Activation map: bf16 NHWC buffer viewed as 4-D (C, W, H, B); `pitch` = channel pitch of the buffer in elements

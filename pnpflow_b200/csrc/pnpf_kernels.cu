@@ -453,10 +453,11 @@ static int launch_blur(const OpDesc& op, const float* in, const float* aux, floa
     PNPF_REQUIRE(op.taps && op.ksize % 2 == 1 && op.ksize <= H && op.ksize <= W, "blur kernel size %d vs image %dx%d", op.ksize, H, W);
     const int R = (op.ksize - 1) / 2, HT = BLUR_TILE + 2 * R;
     const size_t smem = ((size_t)HT * HT + (size_t)HT * BLUR_TILE + op.ksize) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static DeviceCache cache;
+    int dummy = 0;
+    if (!cache.lookup(&dummy)) {
         PNPF_CHECK_CUDA(cudaFuncSetAttribute(blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr = true;
+        cache.store(1);
     }
     PNPF_REQUIRE(smem <= 160 * 1024, "blur kernel too large for shared memory");
     dim3 grid((W + BLUR_TILE - 1) / BLUR_TILE, (H + BLUR_TILE - 1) / BLUR_TILE, planes);
@@ -514,6 +515,48 @@ __global__ void datafit_diag_kernel(OpDesc op, const float* __restrict__ x, cons
     z[i] = out;
 }
 
+// 16-byte version (W % 4 == 0): a thread owns four consecutive pixels of one (b, c) plane row; grid.y = plane, so all index
+// arithmetic is 32-bit.  Same separately rounded operations per element as the scalar kernel (bit-identical results).
+__global__ void datafit_diag_vec4_kernel(OpDesc op, const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ z,
+                                         float gamma, int laplace, int C, int H, int W) {
+    const int W4 = W >> 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;            // vector index inside the plane
+    if (idx >= H * W4) return;
+    const int plane = blockIdx.y;
+    const int h = idx / W4, w = (idx - h * W4) << 2;
+    const long long base = ((long long)plane * H + h) * W + w;
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + base));
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, out[4] = {xv.x, xv.y, xv.z, xv.w};
+    if (op.kind == 3) {
+        if ((h % op.sf) == 0) {
+            const float* yrow = y + ((long long)plane * (H / op.sf) + h / op.sf) * (W / op.sf);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (((w + e) % op.sf) == 0)
+                    out[e] = __fsub_rn(xs[e], __fmul_rn(gamma, datafit_residual(xs[e], __ldg(yrow + (w + e) / op.sf), laplace)));
+        }
+    } else {
+        const float4 yv = __ldg(reinterpret_cast<const float4*>(y + base));
+        const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
+        bool keep[4] = {true, true, true, true};
+        if (op.kind == 1) {
+            const int d = H / 2;
+            const bool hin = (h >= d - op.half_size) && (h < d + op.half_size);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) keep[e] = !(hin && (w + e >= d - op.half_size) && (w + e < d + op.half_size));
+        } else if (op.kind == 2) {
+            const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(op.mask + ((long long)(plane / C) * H + h) * W + w));
+            keep[0] = m.x != 0; keep[1] = m.y != 0; keep[2] = m.z != 0; keep[3] = m.w != 0;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (keep[e]) out[e] = __fsub_rn(xs[e], __fmul_rn(gamma, datafit_residual(xs[e], ys[e], laplace)));
+    }
+    *reinterpret_cast<float4*>(z + base) = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 int launch_datafit(const OpDesc& op, const float* x, const float* y, float* z, float gamma, int laplace, int B, int C, int H, int W,
                    cudaStream_t st) {
     const long long n = (long long)B * C * H * W;
@@ -525,36 +568,93 @@ int launch_datafit(const OpDesc& op, const float* x, const float* y, float* z, f
     PNPF_REQUIRE(op.kind >= 0 && op.kind <= 3, "unknown operator kind %d", op.kind);
     PNPF_REQUIRE(op.kind != 2 || op.mask, "mask operator without a device mask");
     PNPF_REQUIRE(op.kind != 3 || (op.sf >= 1 && H % op.sf == 0 && W % op.sf == 0), "SR factor %d vs %dx%d", op.sf, H, W);
-    datafit_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, x, y, z, gamma, laplace, C, H, W, n);
+    const bool vec = (W % 4 == 0) && aligned16(x) && aligned16(z) && (op.kind == 3 || aligned16(y)) &&
+                     (op.kind != 2 || (reinterpret_cast<uintptr_t>(op.mask) & 3) == 0) && (long long)B * C <= 65535;
+    if (vec) {
+        dim3 grid((unsigned)((H * (W / 4) + 255) / 256), (unsigned)(B * C));
+        datafit_diag_vec4_kernel<<<grid, 256, 0, st>>>(op, x, y, z, gamma, laplace, C, H, W);
+    } else {
+        datafit_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, x, y, z, gamma, laplace, C, H, W, n);
+    }
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-// zt[s] = t*z + eps[s]*(1-t): three separately rounded ops like the eager reference (pnp_flow.py:48)
+// zt[s] = t*z + eps[s]*(1-t): three separately rounded ops like the eager reference (pnp_flow.py:48).
+// grid.y = draw s (no 64-bit modulo); the 16-byte version handles n % 4 == 0, the scalar one everything else.
 __global__ void interp_kernel(const float* __restrict__ z, const float* __restrict__ eps, float t, float omt,
-                              float* __restrict__ zt, long long n, long long total) {
+                              float* __restrict__ zt, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < total) zt[i] = __fadd_rn(__fmul_rn(t, __ldg(z + i % n)), __fmul_rn(eps[i], omt));
+    const long long o = (long long)blockIdx.y * n + i;
+    if (i < n) zt[o] = __fadd_rn(__fmul_rn(t, __ldg(z + i)), __fmul_rn(eps[o], omt));
+}
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {       // read-once data: do not allocate in L1
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__global__ void interp_vec4_kernel(const float* __restrict__ z, const float* __restrict__ eps, float t, float omt,
+                                   float* __restrict__ zt, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const long long o = ((long long)blockIdx.y * n4 + i) * 4;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(z) + i);      // z is re-read by every draw: keep it cached
+    const float4 e = ldg_stream_f4(eps + o);
+    float4 r;
+    r.x = __fadd_rn(__fmul_rn(t, a.x), __fmul_rn(e.x, omt));
+    r.y = __fadd_rn(__fmul_rn(t, a.y), __fmul_rn(e.y, omt));
+    r.z = __fadd_rn(__fmul_rn(t, a.z), __fmul_rn(e.z, omt));
+    r.w = __fadd_rn(__fmul_rn(t, a.w), __fmul_rn(e.w, omt));
+    *reinterpret_cast<float4*>(zt + o) = r;
 }
 int launch_interp(const float* z, const float* eps, float t, float* zt, long long n, int S, cudaStream_t st) {
-    const long long total = n * S;
-    interp_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(z, eps, t, 1.0f - t, zt, n, total);
+    PNPF_REQUIRE(S >= 1 && S <= 65535, "num_samples %d", S);
+    if (n % 4 == 0 && aligned16(z) && aligned16(eps) && aligned16(zt)) {
+        const long long n4 = n / 4;
+        dim3 grid((unsigned)((n4 + 255) / 256), (unsigned)S);
+        interp_vec4_kernel<<<grid, 256, 0, st>>>(z, eps, t, 1.0f - t, zt, n4);
+    } else {
+        dim3 grid((unsigned)((n + 255) / 256), (unsigned)S);
+        interp_kernel<<<grid, 256, 0, st>>>(z, eps, t, 1.0f - t, zt, n);
+    }
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-// x_new = (sum_s (zt_s + (1-t) v_s)) * (1/S), summed in draw order with separately rounded ops (pnp_flow.py:114-121)
-__global__ void push_accum_kernel(const float* __restrict__ zt, const float* __restrict__ v, float omt, int S, float invS,
+// x_new = (sum_s (zt_s + (1-t) v_s)) / S, summed in draw order with separately rounded ops and a true division
+// (pnp_flow.py:114-121: x_new += ...; x_new /= num_samples)
+__global__ void push_accum_kernel(const float* __restrict__ zt, const float* __restrict__ v, float omt, int S, float fS,
                                   float* __restrict__ x_new, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float acc = 0.f;
     for (int s = 0; s < S; ++s) acc = __fadd_rn(acc, __fadd_rn(zt[s * n + i], __fmul_rn(omt, v[s * n + i])));
-    x_new[i] = __fmul_rn(acc, invS);
+    x_new[i] = __fdiv_rn(acc, fS);
+}
+__global__ void push_accum_vec4_kernel(const float* __restrict__ zt, const float* __restrict__ v, float omt, int S, float fS,
+                                       float* __restrict__ x_new, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 5
+    for (int s = 0; s < S; ++s) {
+        const float4 a = ldg_stream_f4(zt + ((long long)s * n4 + i) * 4);
+        const float4 b = ldg_stream_f4(v + ((long long)s * n4 + i) * 4);
+        acc.x = __fadd_rn(acc.x, __fadd_rn(a.x, __fmul_rn(omt, b.x)));
+        acc.y = __fadd_rn(acc.y, __fadd_rn(a.y, __fmul_rn(omt, b.y)));
+        acc.z = __fadd_rn(acc.z, __fadd_rn(a.z, __fmul_rn(omt, b.z)));
+        acc.w = __fadd_rn(acc.w, __fadd_rn(a.w, __fmul_rn(omt, b.w)));
+    }
+    *reinterpret_cast<float4*>(x_new + i * 4) = make_float4(__fdiv_rn(acc.x, fS), __fdiv_rn(acc.y, fS), __fdiv_rn(acc.z, fS), __fdiv_rn(acc.w, fS));
 }
 int launch_push_accum(const float* zt, const float* v, float t, int S, float* x_new, long long n, cudaStream_t st) {
     PNPF_REQUIRE(S >= 1, "num_samples %d", S);
-    push_accum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(zt, v, 1.0f - t, S, 1.0f / (float)S, x_new, n);
+    if (n % 4 == 0 && aligned16(zt) && aligned16(v) && aligned16(x_new)) {
+        const long long n4 = n / 4;
+        push_accum_vec4_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(zt, v, 1.0f - t, S, (float)S, x_new, n4);
+    } else {
+        push_accum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(zt, v, 1.0f - t, S, (float)S, x_new, n);
+    }
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -39,7 +39,6 @@ static void fill_epi(EpiParams& e, const ConvDesc& d) {
 // Shared memory of the row kernel: 227 KB per CTA on sm_100 minus barriers/tables (RowCfg::BAR_BYTES) and alignment slack.
 constexpr int ROWCONV_SMEM_MAX = 227 * 1024;
 constexpr int ROWCONV_SMEM_BUDGET = ROWCONV_SMEM_MAX - 2048 - 1024;
-constexpr int ROWCONV_DUAL_SMEM = 110 * 1024;        // two CTAs per SM: 2 x (110 KB + 1 KB reserved) < 228 KB
 int rowconv_max_smem() { return ROWCONV_SMEM_MAX; }
 
 // Row-streaming kernel: shape analysis shared by rowconv_eligible() and the preparation.
@@ -71,22 +70,18 @@ static bool rowconv_shape(const ConvDesc& d, RowShape& r) {
         const int w_bytes = 3 * r.kch * (3 * BN * rowb) + r.kch2 * w_tile;
         // bf16 NHWC outputs with full 32-channel blocks are transposed through per-warp staging tiles (RowCfg::STAGE_BYTES)
         const bool staged = d.out_mode == 0 && BN >= 32 && d.n_valid == d.N_pad && d.out_col_stride == 1;
-        // Warp-role configuration (RowCfg): WIDE (n_epi = 12: 8 epilogue + 8 transform warps) for the fused-GroupNorm layers;
-        // DUAL (n_epi = 4: two half-sized CTAs per SM) is an opt-in experiment.  Both accumulate the output statistics in the
-        // staged store, so they need it (the only unstaged outputs without statistics are fp32 NCHW).
-        static const bool no_wide = getenv("PNPF_NO_WIDE") != nullptr;    // A/B switches (tools/ab_env.py)
-        static const bool want_dual = getenv("PNPF_ROW_DUAL") != nullptr;
-        const bool dual = want_dual && nsplit == 1 && r.kch == 1 && BN <= 32 && (staged || d.out_mode == 2);
-        const bool wide = !dual && !no_wide && staged && d.gn_gamma != nullptr;
-        const int n_epi = dual ? 4 : (wide ? 12 : 8);
-        const int n_epi_warps = dual ? 4 : 8;
-        const int stage = staged ? n_epi_warps * 32 * 64 : 0;
-        int nslot = ((dual ? ROWCONV_DUAL_SMEM - 2048 - 1024 : ROWCONV_SMEM_BUDGET) - w_bytes - stage) / r.slot_bytes;
-        if (nslot > (dual ? 6 : 8)) nslot = dual ? 6 : 8;
-        // (opt-in experiment PNPF_ROW_MINSLOT=3: accept three row slots for the unsplit layout, which keeps the level-1 conv2 +
-        // shortcut layers on N = 192 MMAs with one read of every row instead of two half-width CTAs reading every row twice)
-        static const int min_slots = getenv("PNPF_ROW_MINSLOT") ? atoi(getenv("PNPF_ROW_MINSLOT")) : 4;
-        if (nslot >= (nsplit == 1 ? (min_slots >= 2 ? min_slots : 4) : 3)) {
+        // Warp-role configuration (RowCfg): WIDE (n_epi = 12: 8 epilogue + 8 transform warps) for the fused-GroupNorm layers.
+        // It accumulates the output statistics in the staged store, so it needs it (the only unstaged outputs without
+        // statistics are fp32 NCHW).
+        static const bool no_wide = getenv("PNPF_NO_WIDE") != nullptr;    // A/B switch (tools/ab_env.py)
+        const bool wide = !no_wide && staged && d.gn_gamma != nullptr;
+        const int n_epi = wide ? 12 : 8;
+        const int stage = staged ? 8 * 32 * 64 : 0;
+        int nslot = (ROWCONV_SMEM_BUDGET - w_bytes - stage) / r.slot_bytes;
+        if (nslot > 8) nslot = 8;
+        // three row slots are enough for either layout: the unsplit one keeps the level-1 conv2 + shortcut layers on N = 192
+        // MMAs with one read of every row instead of two half-width CTAs reading every row twice (r02 A/B: equal or faster)
+        if (nslot >= 3) {
             r.BN = BN; r.nsplit = nsplit; r.w_bytes = w_bytes; r.nslot = nslot; r.stage_bytes = stage; r.n_epi = n_epi;
             return true;
         }
@@ -125,77 +120,11 @@ bool patchconv_eligible(const ConvDesc& d) {
     PatchShape r;
     return patchconv_shape(d, r);
 }
-// Patch-streaming kernel with fused GroupNorm(+SiLU) / concat inputs (pnpf_patchgn.cuh).  Opt-in: PNPF_PATCH_GN=1 (every
-// width) or PNPF_PATCH_GN=256 (C_out = 256 only, where shared memory has headroom): written at the end of round 1, not yet
-// run on a GPU.
-static bool patchgn_shape(const ConvDesc& d, PatchShape& r) {
-    static const char* env = getenv("PNPF_PATCH_GN");
-    if (!env || !d.gn_gamma || d.subpix) return false;
-    if (atoi(env) > 1 && d.N_pad != atoi(env)) return false;
-    if (!d.allow_rowconv || d.ksize != 3 || d.stride != 1 || d.Wout != d.Win || d.Hout != d.Hin || d.Wout > 128) return false;
-    if (!(d.N_pad == 64 || d.N_pad == 128 || d.N_pad == 256) || d.c_base != 0 || d.out_mode != 0) return false;
-    const int Ca = d.Cin - d.Cb, C2a = d.C2 - d.C2b;
-    if (d.Cin % 64 || d.C2 % 64 || Ca % 64 || d.Cb % 64 || C2a % 64 || d.C2b % 64 || Ca <= 0 || d.Cin > 512) return false;
-    if (d.Cin % d.gn_groups) return false;
-    r.P = d.Wout + 2;
-    r.NR = (r.P - 1 + 127) / r.P + 1 + 2;
-    r.patch_bytes = (r.NR * r.P * 128 + 1023) / 1024 * 1024;
-    r.tiles_per_img = (d.Hout * r.P + 127) / 128;
-    const int b_bytes = d.N_pad * 128;
-    const int budget = PATCH_SMEM_MAX - 1024 - 512 - 4096;               // alignment slack, barriers, scale / shift table
-    r.na = 3;
-    while (r.na > 2 && budget - r.na * r.patch_bytes < 4 * b_bytes) --r.na;
-    r.nb = (budget - r.na * r.patch_bytes) / b_bytes;
-    if (r.nb > 12) r.nb = 12;
-    r.nb_pair = (budget - r.na * r.patch_bytes) / (b_bytes / 2);
-    if (r.nb_pair > 12) r.nb_pair = 12;
-    return r.nb >= 4;
-}
-bool patchgn_eligible(const ConvDesc& d) {
-    PatchShape r;
-    return patchgn_shape(d, r);
-}
-static int try_prepare_patchgn(TcOp& op, const ConvDesc& d) {
-    PatchShape sh;
-    if (!patchgn_shape(d, sh)) return -1;
-    PatchGnParams& q = op.gp;
-    memset(&q, 0, sizeof(q));
-    const int Ca = d.Cin - d.Cb, C2a = d.C2 - d.C2b;
-    q.H = d.Hout; q.W = d.Wout; q.P = sh.P; q.NR = sh.NR; q.n_img = d.B; q.tiles_per_img = sh.tiles_per_img;
-    q.kchunks = d.Cin / 64; q.kchunks2 = d.x2 ? d.C2 / 64 : 0;
-    q.kch_a = Ca / 64; q.kch2_a = d.x2 ? C2a / 64 : 0;
-    q.patch_bytes = sh.patch_bytes; q.na = sh.na; q.nb = sh.nb;
-    op.patch_nb_pair = sh.nb_pair;
-    PNPF_REQUIRE(d.gn_beta && d.gn_stats_a && (d.Cb == 0 || d.gn_stats_b), "fused GroupNorm needs beta and statistics");
-    q.gn_silu = d.gn_silu; q.gn_gs = d.Cin / d.gn_groups; q.gn_Ca = Ca; q.gn_Cb = d.Cb; q.gn_eps = d.gn_eps;
-    q.gn_gamma = d.gn_gamma; q.gn_beta = d.gn_beta; q.gn_st_a = d.gn_stats_a; q.gn_st_b = d.gn_stats_b;
-    fill_epi(q.epi, d);
-    op.kind = 3; op.BK = 64; op.BN = d.N_pad;
-    const long long Ktot = 9LL * d.Cin + (d.x2 ? d.C2 : 0);
-    if (int e = make_act_tmap(&op.tmA, d.x, Ca, d.x_pitch, d.Win, d.Hin, d.B, 64, sh.P, sh.NR, 1)) return e;
-    op.tmAb = op.tmA;
-    if (d.Cb) { if (int e = make_act_tmap(&op.tmAb, d.xb, d.Cb, d.xb_pitch, d.Win, d.Hin, d.B, 64, sh.P, sh.NR, 1)) return e; }
-    op.tmA2 = op.tmA;
-    op.tmA2b = op.tmA;
-    if (d.x2) {
-        if (int e = make_act_tmap(&op.tmA2, d.x2, C2a, d.x2_pitch, d.Wout, d.Hout, d.B, 64, sh.P, sh.NR, 1)) return e;
-        op.tmA2b = op.tmA2;
-        if (d.C2b) { if (int e = make_act_tmap(&op.tmA2b, d.x2b, d.C2b, d.x2b_pitch, d.Wout, d.Hout, d.B, 64, sh.P, sh.NR, 1)) return e; }
-    }
-    if (int e = make_b_tmap(&op.tmB, d.w, Ktot, Ktot, d.N_pad, 1, 0, 64, d.N_pad)) return e;
-    if (int e = make_b_tmap(&op.tmBh, d.w, Ktot, Ktot, d.N_pad, 1, 0, 64, d.N_pad / 2)) return e;
-    op.flops = 2.0 * d.B * d.Hout * d.Wout * (double)d.n_valid * (double)(Ktot - (d.x2_identity ? d.C2 : 0));
-    return 0;
-}
-
 void describe_conv_impl(const ConvDesc& d, char* buf, size_t n) {
     RowShape r;
     if (rowconv_shape(d, r))
         snprintf(buf, n, "rowconv<%d,%d,%d> nsplit=%d nslot=%d kch2=%d w=%dKB slot=%dKB stage=%dKB epi_warps=%d gn=%d", r.BK, r.BN, r.kch, r.nsplit,
                  r.nslot, r.kch2, r.w_bytes / 1024, r.slot_bytes / 1024, r.stage_bytes / 1024, r.n_epi, d.gn_gamma ? 1 : 0);
-    else if (PatchShape pg; patchgn_shape(d, pg))
-        snprintf(buf, n, "patchgn<%d> P=%d NR=%d patch=%dKB na=%d nb=%d tiles/img=%d kch=%d+%d gn=1", d.N_pad, pg.P, pg.NR, pg.patch_bytes / 1024, pg.na,
-                 pg.nb, pg.tiles_per_img, d.Cin / 64, d.C2 / 64);
     else if (PatchShape ps; patchconv_shape(d, ps))
         snprintf(buf, n, "patchconv<%d> P=%d NR=%d patch=%dKB na=%d nb=%d tiles/img=%d%s", d.N_pad, ps.P, ps.NR, ps.patch_bytes / 1024, ps.na, ps.nb,
                  ps.tiles_per_img, d.subpix ? " subpix" : "");
@@ -216,8 +145,8 @@ static int try_prepare_rowconv(TcOp& op, const ConvDesc& d) {
     r.staged_store = sh.stage_bytes > 0;
     op.n_epi = sh.n_epi;
     static const bool no_mma2 = getenv("PNPF_NO_MMA2") != nullptr;       // A/B switch (tools/ab_env.py)
-    r.mma2 = (sh.n_epi != 4 && !no_mma2 && d.Hout >= 2) ? 1 : 0;         // second MMA-issuing warp (RowCfg::NMMA)
-    PNPF_REQUIRE(sh.n_epi == 8 || r.staged_store || !d.stats_out, "row conv (DUAL / WIDE): output statistics need the staged store");
+    r.mma2 = (!no_mma2 && d.Hout >= 2) ? 1 : 0;         // second MMA-issuing warp (RowCfg::NMMA)
+    PNPF_REQUIRE(sh.n_epi == 8 || r.staged_store || !d.stats_out, "row conv (WIDE): output statistics need the staged store");
     PNPF_REQUIRE((long long)d.B * r.strips * d.Hout < (1LL << 31) / 256, "row conv: batch * rows too large for 32-bit row indices");
     r.kchunks = sh.kch; r.kchunks2 = sh.kch2; r.nslot = sh.nslot; r.slot_bytes = sh.slot_bytes;
     r.kch_a = sh.kch_a; r.kch2_a = sh.kch2_a;
@@ -275,10 +204,6 @@ int prepare_conv(TcOp& op, const ConvDesc& d) {
     PNPF_REQUIRE(d.ksize == 1 || d.ksize == 3, "conv kernel size %d unsupported (1 or 3)", d.ksize);
     {
         const int rc = try_prepare_rowconv(op, d);
-        if (rc >= 0) return rc;
-    }
-    {
-        const int rc = try_prepare_patchgn(op, d);
         if (rc >= 0) return rc;
     }
     {
@@ -386,35 +311,14 @@ static int launch_row_t(const TcOp& op, cudaStream_t stream) {
     const RowConvParams& r = op.rp;
     const int smem = 3 * r.kchunks * Cfg::W_STACK + r.kchunks2 * Cfg::W_TILE + r.nslot * r.slot_bytes + (r.staged_store ? Cfg::STAGE_BYTES : 0) +
                      Cfg::BAR_BYTES + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PNPF_CHECK_CUDA(cudaFuncSetAttribute(rowconv_kernel<BK, BN, KCH, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::DUAL ? ROWCONV_DUAL_SMEM : rowconv_max_smem()));
-        if (Cfg::DUAL)
-            PNPF_CHECK_CUDA(cudaFuncSetAttribute(rowconv_kernel<BK, BN, KCH, NEW>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                 cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
+    static DeviceCache cache;
+    int dummy = 0;
+    if (!cache.lookup(&dummy)) {
+        PNPF_CHECK_CUDA(cudaFuncSetAttribute(rowconv_kernel<BK, BN, KCH, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowconv_max_smem()));
+        cache.store(1);
     }
-    PNPF_REQUIRE(smem <= (Cfg::DUAL ? ROWCONV_DUAL_SMEM : rowconv_max_smem()), "row conv shared memory %d exceeds the budget", smem);
-    // CTAs resident per SM: 1, or 2 for the DUAL configuration (each allocates Cfg::TMEM_COLS <= 512 / ctas_per_sm columns, so
-    // co-resident CTAs can never starve each other's tcgen05.alloc)
-    int ctas_per_sm = 1;
-    if (Cfg::DUAL) {
-        // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for EVERY kernel that contains tcgen05.alloc, whatever its
-        // resources, while the hardware does co-schedule such CTAs (tools/probes/tmem_occupancy_probe.cu: 2 x 148 CTAs with
-        // 256 columns each all run pairwise on one SM).  So the residency is computed here: shared memory (+ 1 KB reserved per
-        // CTA) against 228 KB, and registers per SM sub-partition (its 16 K registers hold ceil(warps / 4) warps of each CTA).
-        static int fit = -1;
-        if (fit < 0) {
-            cudaFuncAttributes fa;
-            PNPF_CHECK_CUDA(cudaFuncGetAttributes(&fa, rowconv_kernel<BK, BN, KCH, NEW>));
-            const int warps_pp = (Cfg::THREADS / 32 + 3) / 4;
-            fit = (2 * (ROWCONV_DUAL_SMEM + 1024) <= 228 * 1024 && 2 * warps_pp * 32 * fa.numRegs <= 16384 && 2 * Cfg::TMEM_COLS <= 512) ? 2 : 1;
-            if (getenv("PNPF_PLAN_DUMP"))
-                fprintf(stderr, "[pnpf] rowconv<%d,%d,%d> DUAL: %d registers, %d TMEM columns -> %d CTAs/SM\n", BK, BN, KCH, fa.numRegs, Cfg::TMEM_COLS, fit);
-        }
-        ctas_per_sm = fit;
-    }
+    PNPF_REQUIRE(smem <= rowconv_max_smem(), "row conv shared memory %d exceeds the budget", smem);
+    const int ctas_per_sm = 1;      // (a two-CTA-per-SM variant was measured slower in round 1: profiles/r01_ab_experiments.md)
     // one CTA group (nsplit CTAs) per contiguous range of the flattened row space; at least 8 rows per range
     const long long rows = (long long)r.n_img * r.strips * r.H;
     long long groups = (long long)num_sms() * ctas_per_sm / r.nsplit;
@@ -431,11 +335,11 @@ static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
     using Cfg = PatchCfg<BN, PAIR>;
     PatchConvParams q = op.pp;
     if (PAIR) q.nb = op.patch_nb_pair;
-    q.nb /= TG;                                       // ring depth in slots of TG weight tiles (PNPF_PATCH_TG)
+    q.nb /= TG;                                       // ring depth in slots of TG weight tiles
     const int smem = q.na * q.patch_bytes + q.nb * TG * Cfg::B_BYTES + 512 + 1024;
-    static bool attr_set = false;
-    static int max_clusters = 0;
-    if (!attr_set) {
+    static DeviceCache cache;
+    int max_clusters = 0;
+    if (!cache.lookup(&max_clusters)) {
         PNPF_CHECK_CUDA(cudaFuncSetAttribute(patchconv_kernel<BN, PAIR, SUBPIX, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, PATCH_SMEM_MAX));
         if (PAIR) {
             cudaLaunchConfig_t qc = {};
@@ -449,7 +353,7 @@ static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
             PNPF_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, patchconv_kernel<BN, PAIR, SUBPIX, TG>, &qc));
             PNPF_REQUIRE(max_clusters >= 1, "no CTA pair of patchconv_kernel<%d> fits on this device", BN);
         }
-        attr_set = true;
+        cache.store(max_clusters);
     }
     PNPF_REQUIRE(smem <= PATCH_SMEM_MAX, "patch conv shared memory %d exceeds the budget", smem);
     const long long units = (long long)(q.n_img / (PAIR ? 2 : 1)) * q.tiles_per_img;
@@ -472,68 +376,7 @@ static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
     return 0;
 }
 
-template <int BN, bool PAIR, int TG = 1>
-static int launch_patchgn_t(const TcOp& op, cudaStream_t stream) {
-    using Cfg = PatchGnCfg<BN, PAIR>;
-    PatchGnParams q = op.gp;
-    if (PAIR) q.nb = op.patch_nb_pair;
-    q.nb /= TG;                                       // ring depth in slots of TG weight tiles (PNPF_PATCH_TG)
-    const int smem = q.na * q.patch_bytes + q.nb * TG * Cfg::B_BYTES + Cfg::BAR_BYTES + Cfg::TAB_BYTES + 1024;
-    static bool attr_set = false;
-    static int max_clusters = 0;
-    if (!attr_set) {
-        PNPF_CHECK_CUDA(cudaFuncSetAttribute(patchgn_kernel<BN, PAIR, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, PATCH_SMEM_MAX));
-        if (PAIR) {                                   // same query as the plain patch kernel (one CTA per SM)
-            cudaLaunchConfig_t qc = {};
-            qc.gridDim = dim3(num_sms() & ~1);
-            qc.blockDim = dim3(Cfg::THREADS);
-            qc.dynamicSmemBytes = PATCH_SMEM_MAX;
-            cudaLaunchAttribute qa[1];
-            qa[0].id = cudaLaunchAttributeClusterDimension;
-            qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-            qc.attrs = qa; qc.numAttrs = 1;
-            PNPF_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, patchgn_kernel<BN, PAIR, TG>, &qc));
-            PNPF_REQUIRE(max_clusters >= 1, "no CTA pair of patchgn_kernel<%d> fits on this device", BN);
-        }
-        attr_set = true;
-    }
-    PNPF_REQUIRE(smem <= PATCH_SMEM_MAX, "patch (GroupNorm) conv shared memory %d exceeds the budget", smem);
-    const long long units = (long long)(q.n_img / (PAIR ? 2 : 1)) * q.tiles_per_img;
-    if (units < 1) return 0;
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute at[1];
-    if (PAIR) {
-        const int clusters = (int)(units < max_clusters ? units : max_clusters);
-        cfg.gridDim = dim3(2 * clusters);
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-    } else {
-        cfg.gridDim = dim3((unsigned)(units < num_sms() ? units : num_sms()));
-    }
-    cfg.blockDim = dim3(Cfg::THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    PNPF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, patchgn_kernel<BN, PAIR, TG>, op.tmA, op.tmAb, op.tmA2, op.tmA2b, PAIR ? op.tmBh : op.tmB, q));
-    return 0;
-}
-
 int launch_tc(const TcOp& op, cudaStream_t s) {
-    if (op.kind == 3) {
-        static const bool no_pair = getenv("PNPF_NO_PAIR") != nullptr;
-        const bool pair = !no_pair && op.gp.n_img % 2 == 0;
-        static const bool tg3 = getenv("PNPF_PATCH_TG") != nullptr && atoi(getenv("PNPF_PATCH_TG")) == 3;
-        if (tg3 && (pair ? op.patch_nb_pair : op.gp.nb) >= 6) {
-            if (op.BN == 64) return pair ? launch_patchgn_t<64, true, 3>(op, s) : launch_patchgn_t<64, false, 3>(op, s);
-            if (op.BN == 128) return pair ? launch_patchgn_t<128, true, 3>(op, s) : launch_patchgn_t<128, false, 3>(op, s);
-            if (op.BN == 256) return pair ? launch_patchgn_t<256, true, 3>(op, s) : launch_patchgn_t<256, false, 3>(op, s);
-        }
-        if (op.BN == 64) return pair ? launch_patchgn_t<64, true>(op, s) : launch_patchgn_t<64, false>(op, s);
-        if (op.BN == 128) return pair ? launch_patchgn_t<128, true>(op, s) : launch_patchgn_t<128, false>(op, s);
-        if (op.BN == 256) return pair ? launch_patchgn_t<256, true>(op, s) : launch_patchgn_t<256, false>(op, s);
-        set_error("no patchgn instantiation for BN=%d", op.BN);
-        return 2;
-    }
     if (op.kind == 2) {
         static const bool no_pair = getenv("PNPF_NO_PAIR") != nullptr;
         const bool pair = !no_pair && op.pp.n_img % 2 == 0;
@@ -542,9 +385,10 @@ int launch_tc(const TcOp& op, cudaStream_t s) {
             if (op.BN == 128) return pair ? launch_patch_t<128, true, true>(op, s) : launch_patch_t<128, false, true>(op, s);
             if (op.BN == 256) return pair ? launch_patch_t<256, true, true>(op, s) : launch_patch_t<256, false, true>(op, s);
         }
-        // opt-in (PNPF_PATCH_TG=3): three taps per weight-ring slot -> one barrier wait + one commit per 12 MMAs; needs >= 2 slots
-        static const bool tg3 = getenv("PNPF_PATCH_TG") != nullptr && atoi(getenv("PNPF_PATCH_TG")) == 3;
-        if (tg3 && (pair ? op.patch_nb_pair : op.pp.nb) >= 6) {
+        // three taps (one kernel row) per weight-ring slot: the issuer waits and commits once per 12 MMAs instead of once per 4
+        // (same arithmetic in the same order; r02 A/B: profiles/r02_optin_validation.log).  Needs >= 2 slots of 3 tiles.
+        static const bool tg1 = getenv("PNPF_PATCH_TG1") != nullptr;        // A/B switch (tools/ab_env.py)
+        if (!tg1 && (pair ? op.patch_nb_pair : op.pp.nb) >= 6) {
             if (op.BN == 64) return pair ? launch_patch_t<64, true, false, 3>(op, s) : launch_patch_t<64, false, false, 3>(op, s);
             if (op.BN == 128) return pair ? launch_patch_t<128, true, false, 3>(op, s) : launch_patch_t<128, false, false, 3>(op, s);
             if (op.BN == 256) return pair ? launch_patch_t<256, true, false, 3>(op, s) : launch_patch_t<256, false, false, 3>(op, s);
@@ -562,10 +406,6 @@ int launch_tc(const TcOp& op, cudaStream_t s) {
         if (op.rp.kchunks == 2) return launch_row_t<bk, bn, 2, ne>(op, s);                \
         if (op.rp.kchunks == 3) return launch_row_t<bk, bn, 3, ne>(op, s);                \
     }
-#define PNPF_RDUAL(bk, bn) \
-    if (op.BK == bk && op.BN == bn && op.n_epi == 4 && op.rp.kchunks == 1) return launch_row_t<bk, bn, 1, 4>(op, s);
-        PNPF_RDUAL(32, 16) PNPF_RDUAL(32, 32) PNPF_RDUAL(64, 16) PNPF_RDUAL(64, 32)
-#undef PNPF_RDUAL
         PNPF_RCASE(32, 32, 12) PNPF_RCASE(32, 64, 12) PNPF_RCASE(64, 32, 12) PNPF_RCASE(64, 64, 12)
         PNPF_RCASE(32, 16, 8) PNPF_RCASE(32, 32, 8) PNPF_RCASE(32, 64, 8) PNPF_RCASE(64, 16, 8) PNPF_RCASE(64, 32, 8) PNPF_RCASE(64, 64, 8)
 #undef PNPF_RCASE

@@ -3,7 +3,6 @@
 #include "pnpf_host.h"
 #include "pnpf_rowconv.cuh"
 #include "pnpf_patchconv.cuh"
-#include "pnpf_patchgn.cuh"
 
 namespace pnpf {
 
@@ -16,10 +15,9 @@ struct TcOp {               // a prepared conv_gemm launch
     GemmParams p;
     RowConvParams rp;       // kind == 1: row-streaming conv (pnpf_rowconv.cuh)
     PatchConvParams pp;     // kind == 2: patch-streaming conv (pnpf_patchconv.cuh)
-    PatchGnParams gp;       // kind == 3: patch-streaming conv with fused GroupNorm / concat inputs (pnpf_patchgn.cuh, opt-in)
     int patch_nb_pair = 0;  // weight-ring depth of the CTA-pair launch (half tiles)
     int patch_subpix = 0;   // patch conv computes one phase of a sub-pixel (nearest x2 + 3x3) convolution
-    int kind = 0;           // 0: conv_gemm_kernel, 1: rowconv_kernel, 2: patchconv_kernel, 3: patchgn_kernel
+    int kind = 0;           // 0: conv_gemm_kernel, 1: rowconv_kernel, 2: patchconv_kernel
     int BK = 0, BN = 0;
     int n_epi = 8;          // row conv: epilogue warps (RowCfg::NEW), the other worker warps run the GroupNorm transform
     double flops = 0;       // algorithmic 2*M*N*K (for reporting)
@@ -76,7 +74,6 @@ struct ConvDesc {
 int prepare_conv(TcOp& op, const ConvDesc& d);
 bool rowconv_eligible(const ConvDesc& d);     // would prepare_conv pick the row-streaming kernel?
 bool patchconv_eligible(const ConvDesc& d);   // ... the patch-streaming kernel (3x3 stride 1, W <= 128, C_out 64 / 128 / 256)?
-bool patchgn_eligible(const ConvDesc& d);     // ... its fused-GroupNorm / concat-input variant (opt-in: PNPF_PATCH_GN)?
 int rowconv_max_smem();
 void describe_conv_impl(const ConvDesc& d, char* buf, size_t n);   // which kernel prepare_conv would pick (PNPF_PLAN_DUMP)
 

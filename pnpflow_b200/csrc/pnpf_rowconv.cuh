@@ -71,19 +71,16 @@ struct RowCfg {
     //   12 : WIDE = 8 epilogue + 8 transform warps, 96 registers — for the fused-GroupNorm layers, where the 4-warp transform
     //        (one latency chain per scheduler: ld.shared -> unpack -> fma -> tanh -> pack -> st.shared, issuing 26 % of the time)
     //        is as slow as the MMA issuer
-    //   4  : DUAL = two CTAs per SM, each 4 epilogue + 4 transform warps, 256 TMEM columns, 80 registers (experiment: measured
-    //        slower, opt-in with PNPF_ROW_DUAL=1; profiles/r01_ab_experiments.md)
-    static constexpr bool DUAL = NEW_ == 4;
+    // (a two-CTA-per-SM configuration with 4 + 4 worker warps was measured slower in round 1 and removed:
+    //  profiles/r01_ab_experiments.md)
     static constexpr bool WIDE = NEW_ == 12;
-    static constexpr int MIN_CTAS = DUAL ? 2 : 1;
     // Below 128 registers the per-thread GroupNorm statistics of the output (2 x 32 accumulators) would spill, so they are
     // accumulated in the READ phase of the staged store instead (a lane sees 8 channels of 4 pixels per row: 16 accumulators), on
-    // the bf16 values that are actually stored — exactly the tensor the next GroupNorm normalises.  The host selects these
-    // configurations only together with the staged store.
-    static constexpr bool STAGED_STATS = DUAL || WIDE;
-    static constexpr int TMEM_BUDGET = DUAL ? 256 : 512;
-    static constexpr int NACC = (TMEM_BUDGET / BN) > 16 ? 16 : (TMEM_BUDGET / BN);
-    static constexpr int TMEM_COLS = NACC * BN;              // 256 (BN=16 or DUAL) or 512
+    // the bf16 values that are actually stored — exactly the tensor the next GroupNorm normalises.  The host selects this
+    // configuration only together with the staged store.
+    static constexpr bool STAGED_STATS = WIDE;
+    static constexpr int NACC = (512 / BN) > 16 ? 16 : (512 / BN);
+    static constexpr int TMEM_COLS = NACC * BN;              // 256 (BN = 16) or 512
     static constexpr int MAX_SLOTS = 8;
     // Worker warps besides the producer and the MMA issuer: NEW epilogue warps (sets of 4, one warp per TMEM lane quarter) and
     // 4 GroupNorm-transform warps.  Both are per-warp LATENCY chains (barrier wait, tcgen05.ld/st round trips or ld/st.shared +
@@ -105,13 +102,11 @@ struct RowCfg {
     // barrier waits, commits and bookkeeping of one row (~ 600 of the ~ 1000 clocks a single issuer spends per row: the limit of
     // the 32 -> 32 layers once the transform has 8 warps) with the MMA issue of the next.  RowConvParams::mma2 = 0 leaves the
     // second warp idle (A/B switch).
-    static constexpr int NMMA = DUAL ? 1 : 2;
+    static constexpr int NMMA = 2;
     static constexpr int THREADS = 64 + (NEW + NTW) * 32 + (NMMA - 1) * 32;
-    // Register budget: the register file is split over the four SM sub-partitions (16 K registers each) and the 10 warps of a
-    // DUAL CTA land 3/3/2/2 on them, so two co-resident CTAs need 6 warps x 32 x regs <= 16384 -> 80 registers per thread
-    // (a bound of 96, which 2 x 320 threads would suggest, leaves ONE CTA per SM).  Declaring 384 threads makes ptxas pick 80.
-    // WIDE: 18 warps are allocated as 5 per sub-partition -> 5 x 32 x regs <= 16384 -> 96 registers (= the bound of 640 threads).
-    static constexpr int BOUND_THREADS = DUAL ? 384 : (WIDE ? 640 : THREADS);
+    // Register budget of WIDE: the register file is split over the four SM sub-partitions (16 K registers each); 18 warps are
+    // allocated as 5 per sub-partition -> 5 x 32 x regs <= 16384 -> 96 registers (= the bound of 640 threads).
+    static constexpr int BOUND_THREADS = WIDE ? 640 : THREADS;
     static constexpr int CPT = BN > 32 ? 32 : BN;            // columns per epilogue thread
     static constexpr int BAR_BYTES = 2048;                   // barriers + tmem slot | bias staging (2 x 64 floats) | GN scale/shift (2 x 128)
     static_assert(BN == 16 || BN == 32 || BN == 64, "row conv is for thin outputs");
@@ -166,7 +161,7 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
 }
 
 template <int BK, int BN, int KCH, int NEW_>
-__global__ void __launch_bounds__(RowCfg<BK, BN, NEW_>::BOUND_THREADS, RowCfg<BK, BN, NEW_>::MIN_CTAS)
+__global__ void __launch_bounds__(RowCfg<BK, BN, NEW_>::BOUND_THREADS, 1)
 rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAb,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA2b,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ RowConvParams p) {

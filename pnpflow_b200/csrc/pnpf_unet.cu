@@ -98,10 +98,11 @@ struct pnpf_engine {
 // ------------------------------------------------------------------------------------------------
 // plan construction
 // ------------------------------------------------------------------------------------------------
-// opt-in (PNPF_SUBPIXEL_UP=1): the three nearest-x2 + 3x3 convs run as four sub-pixel phases on the low-resolution tensor
+// The nearest-x2 + 3x3 convs (models.py:41-47) run as four sub-pixel phases (folded 2x2 kernels) on the LOW-resolution tensor
+// whenever the patch kernel takes the shape: 2.25x fewer MACs and no materialised upsampled tensor.
 static bool subpixel_up_enabled() {
-    static const bool on = getenv("PNPF_SUBPIXEL_UP") != nullptr;
-    return on;
+    static const bool off = getenv("PNPF_NO_SUBPIXEL") != nullptr;       // A/B switch (tools/ab_env.py)
+    return !off;
 }
 
 static bool has_attn(const pnpf_unet_config& c, int side) {
@@ -697,9 +698,8 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 }
                 d2.stats_out = y.stats;
                 d2.out = y.p; d2.out_mode = 0; d2.out_img_stride = px * L.out_ch; d2.out_row_stride = L.out_ch; d2.n_valid = L.out_ch;
-                // (patchgn_eligible: the opt-in fused-GroupNorm variant of the patch kernel, PNPF_PATCH_GN; false by default)
-                bool fuse2 = rowconv_eligible(d2) || patchgn_eligible(d2);
-                bool fuse1 = rowconv_eligible(d1) || patchgn_eligible(d1);
+                bool fuse2 = rowconv_eligible(d2);
+                bool fuse1 = rowconv_eligible(d1);
                 if (!fuse2 && L.skip_ch && sc) fuse1 = false;       // the unfused conv2 needs the raw concat copy made by norm1
                 if (!fuse1) {                                        // separate GroupNorm pass -> normalised (concatenated) operand
                     add_gn(p + ".norm1", src, side, p + ".norm1", 1, t_a1, (L.skip_ch && sc) ? t_xcat : nullptr);
@@ -782,7 +782,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
             case LayerSpec::UP: {
                 const int so = side * 2;
                 if (subpixel_up_enabled()) {
-                    // opt-in: four sub-pixel phases on the low-resolution tensor (pnpf_patchconv.cuh SUBPIX) instead of
+                    // four sub-pixel phases on the low-resolution tensor (pnpf_patchconv.cuh SUBPIX) instead of
                     // upsample2x + a 3x3 conv on the 4x larger tensor
                     ConvDesc d;
                     d.x = h.p; d.Hin = d.Win = d.Hout = d.Wout = side; d.Cin = L.in_ch; d.x_pitch = L.in_ch;
@@ -912,6 +912,7 @@ static int run_ops(pnpf_engine* e, const float* x, const float* t, float* v, int
                 TcOp tc = o.tc;
                 tc.p.n_img = batch;
                 tc.rp.n_img = batch;
+                tc.pp.n_img = batch;            // launch_tc re-derives the CTA-pair decision from it
                 if (i == e->end_op) {
                     PNPF_REQUIRE(v != nullptr, "null output pointer");
                     tc.p.epi.out = v;

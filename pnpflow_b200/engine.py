@@ -72,6 +72,8 @@ class UNetEngine:
             _lib.check(self.lib.pnpf_load_weight(self._h, k.encode(), w.data_ptr(), shape, w.dim()))
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pnpf_finalize_weights(self._h))
+        # the old weight arena is gone: graphs captured before this point must not be replayed any more
+        self._weights_gen = getattr(self, "_weights_gen", 0) + 1
         self._graphs = {}
         if getattr(self, "_ws", None) is not None:
             mb, self.max_batch = self.max_batch, 0
@@ -79,6 +81,9 @@ class UNetEngine:
 
     # ------------------------------------------------------------------ workspace
     def ensure_batch(self, batch: int):
+        """Grow the workspace to hold ``batch`` images.  Graphs captured on the previous workspace stay valid: each one keeps
+        its workspace tensor alive (``graphed`` stores it next to the graph) and has the old plan's pointers baked in, so a
+        live PnPFlowSession is not disturbed; only NEW ``graphed()`` calls capture against the new workspace."""
         if batch <= self.max_batch:
             return
         with torch.cuda.device(self.device):
@@ -86,7 +91,6 @@ class UNetEngine:
             if need == 0:
                 _lib.check(1)
             self._graphs = {}
-            self._ws = None
             self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
             base = (self._ws.data_ptr() + 1023) // 1024 * 1024
             _lib.check(self.lib.pnpf_bind_workspace(self._h, base, need, batch))
@@ -132,7 +136,14 @@ class UNetEngine:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._launch(xb, tb, vb, batch)
-        self._graphs[batch] = (xb, tb, vb, g.replay)
+        ws, gen = self._ws, self._weights_gen     # the graph's kernels point into THIS workspace and weight arena
+
+        def replay(_g=g, _ws=ws, _gen=gen):
+            if _gen != self._weights_gen:
+                raise RuntimeError("stale CUDA graph: the engine's weights were reloaded after this graph was captured; "
+                                   "call UNetEngine.graphed() (or create a new PnPFlowSession) again")
+            _g.replay()
+        self._graphs[batch] = (xb, tb, vb, replay)
         return self._graphs[batch]
 
     # ------------------------------------------------------------------ introspection / debug

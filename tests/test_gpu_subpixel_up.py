@@ -1,19 +1,13 @@
-"""Opt-in GPU parity of the sub-pixel form of Upsample (models.py:41-47: nearest x2 + 3x3 conv as four 2x2-tap phases of the
-patch-streaming kernel on the low-resolution tensor).  The path is NOT on by default (PNPF_SUBPIXEL_UP=1 enables it in the
-U-Net plan) and was written after this round's GPU budget was spent, so these tests only run with PNPF_TEST_SUBPIXEL=1:
-
-    PNPF_TEST_SUBPIXEL=1 python -m pytest tests/test_gpu_zz_subpixel_up.py -m gpu -q
-"""
-import os
-
+"""GPU parity of the sub-pixel form of Upsample (models.py:41-47: nearest x2 + 3x3 conv as four 2x2-tap phases of the
+patch-streaming kernel on the low-resolution tensor) — the default plan since round 2 (PNPF_NO_SUBPIXEL=1 is the A/B switch
+back to upsample2x + 3x3 conv)."""
 import pytest
 import torch
 import torch.nn.functional as F
 
 import oracle
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("PNPF_TEST_SUBPIXEL"), reason="opt-in: unverified path (set PNPF_TEST_SUBPIXEL=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("B,H,Cin,Cout", [(2, 32, 256, 256), (2, 64, 128, 128), (2, 128, 64, 64), (3, 32, 128, 64)])
@@ -32,8 +26,7 @@ def test_upconv2x_layer_vs_torch(B, H, Cin, Cout):
     assert rel < 8e-3, rel          # bf16 output rounding + bf16 rounding of the folded (summed) weights
 
 
-def test_unet_with_subpixel_up_matches_oracle(monkeypatch):
-    monkeypatch.setenv("PNPF_SUBPIXEL_UP", "1")      # read once per process by the library: run this file in its own process
+def test_unet_with_subpixel_up_matches_oracle():
     from pnpflow_b200 import UNetEngine
     cfg = oracle.AFHQ_256
     sd = oracle.init_state_dict(cfg, seed=0)

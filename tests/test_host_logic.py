@@ -93,6 +93,17 @@ def test_gamma_schedule_matches_reference_arithmetic():
             assert abs(got - ref) <= 2e-6 * max(1.0, abs(ref)), (style, it)
 
 
+def test_step_time_is_bit_identical_to_the_reference_tensor_arithmetic():
+    """pnp_flow.py:107-108: t1 = torch.ones(B) * delta * iteration (fp32 tensor x python scalars).  r01 computed
+    fp32(double(delta * it)), which differs by 1 ulp on ~30 % of the steps."""
+    import pnpflow_b200 as P
+    for T in (20, 100, 200, 7):
+        delta = 1 / T
+        for it in range(T):
+            ref = float((torch.ones(1) * delta * it)[0])
+            assert P.step_time(delta, it) == ref, (T, it)
+
+
 def test_as_engine_operator_accepts_foreign_plugins():
     import pnpflow_b200 as P
     from pnpflow_b200.degradations import _PythonOperator
