@@ -11,15 +11,17 @@ from pnpflow_b200 import synth
 net = synth.NETS["afhq256"]; B = int(sys.argv[2])
 eng = P.UNetEngine(net, synth.random_state_dict(net), max_batch=B)
 x = torch.randn(B, 3, 256, 256, device="cuda"); t = torch.full((B,), 0.5, device="cuda")
-for _ in range(3): v = eng.forward(x, t)
+xb, tb, v, replay = eng.graphed(B)          # CUDA-graph replay = what PnPFlowSession.step runs
+xb.copy_(x); tb.copy_(t)
+for _ in range(3): replay()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ts = []
 for rep in range(5):
     e0.record()
-    for _ in range(5): eng.forward(x, t)
+    for _ in range(5): replay()
     e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) / 5)
-print("%%-28s B=%%d min %%.3f  med %%.3f ms/eval  (%%.3f ms/img) checksum %%.6e" %% (sys.argv[1], B, min(ts), sorted(ts)[2], min(ts) / B, v.double().abs().mean().item()), flush=True)
+print("%%-28s B=%%d min %%.3f  med %%.3f ms/eval  (%%.3f ms/img) launches %%d checksum %%.6e" %% (sys.argv[1], B, min(ts), sorted(ts)[2], min(ts) / B, eng.num_launches, v.double().abs().mean().item()), flush=True)
 ''' % ROOT
 batch = os.environ.get("AB_BATCH", "80")
 for rnd in range(int(os.environ.get("AB_ROUNDS", "2"))):

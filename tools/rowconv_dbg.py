@@ -7,6 +7,7 @@ os.environ["PNPF_ROWCONV_DBG"] = "1"
 from pnpflow_b200 import _lib
 lib = _lib.load()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 80
+ONLY_GN = len(sys.argv) > 2 and sys.argv[2] == "gn"
 
 
 def timed(fn):
@@ -18,7 +19,7 @@ def timed(fn):
 
 
 print("=== plain convs: B H W Cin Cout C2 res", flush=True)
-for (H, W, Cin, Cout, C2, res) in ((256, 256, 32, 32, 0, 0), (256, 256, 32, 32, 0, 1), (256, 256, 32, 32, 32, 0), (256, 256, 64, 32, 0, 0),
+for (H, W, Cin, Cout, C2, res) in () if ONLY_GN else ((256, 256, 32, 32, 0, 0), (256, 256, 32, 32, 0, 1), (256, 256, 32, 32, 32, 0), (256, 256, 64, 32, 0, 0),
                                    (128, 128, 64, 64, 0, 0), (128, 128, 64, 64, 0, 1), (128, 128, 64, 64, 64, 0), (128, 128, 128, 64, 0, 0),
                                    (128, 128, 64, 64, 128, 0),
                                    (64, 64, 128, 128, 0, 0), (64, 64, 128, 128, 0, 1), (64, 64, 256, 128, 0, 0), (64, 64, 128, 128, 256, 0),
