@@ -98,16 +98,19 @@ enum {
     PNPF_OP_BOX = 1,      /* BoxInpainting        degradations.py:23-32, utils.py:327-336 */
     PNPF_OP_MASK = 2,     /* Random/Paintbrush    degradations.py:35-52 (cached uint8 keep-mask [B,H,W]) */
     PNPF_OP_SR = 3,       /* Superresolution      degradations.py:92-127 mode None */
-    PNPF_OP_BLUR = 4      /* GaussianDeblurring   degradations.py:55-89 (separable circular Gaussian) */
+    PNPF_OP_BLUR = 4,     /* GaussianDeblurring   degradations.py:55-89 (separable circular Gaussian) */
+    PNPF_OP_SR_BICUBIC = 5 /* Superresolution(mode='bicubic')  degradations.py:97-109,117-127 + utils.py:365-396 (separable circular
+                              4*sf-tap bicubic filter + decimation; adjoint = zero-fill + correlation) */
 };
 typedef struct {
     int kind;
     int half_size;        /* BOX: half_size_mask */
     const uint8_t* mask;  /* MASK: device [B,H,W] keep mask (1 = observed) */
-    int sf;               /* SR: scale factor */
-    const float* taps;    /* BLUR: device 1-D normalised Gaussian, ksize taps (kernel = outer(taps,taps)) */
-    int ksize;            /* BLUR: 61 */
-    float* scratch;       /* BLUR: device scratch, B*C*H*W floats */
+    int sf;               /* SR, SR_BICUBIC: scale factor */
+    const float* taps;    /* BLUR: device 1-D normalised Gaussian, ksize taps (kernel = outer(taps,taps));
+                             SR_BICUBIC: device 1-D normalised bicubic weights, ksize = 4*sf taps */
+    int ksize;            /* BLUR: 61; SR_BICUBIC: 4*sf */
+    float* scratch;       /* BLUR: device scratch, B*C*H*W floats; SR_BICUBIC: B*C*(H/sf)*(W/sf) floats */
 } pnpf_operator;
 
 /* y = A x.                       Degradation.H      (degradations.py)      x [B,C,H,W] -> y [B,C,Hy,Wy] */
@@ -127,6 +130,27 @@ int pnpf_interp(const float* z, const float* eps, float t, float* zt, long long 
 /* x_new = (sum_{s<S} (zt_s + (1-t) v_s)) / S        pnp_flow.py:50-52,114-121.
  * zt, v: [S][n] contiguous (draw-major), x_new: [n]. Summation order s = 0..S-1 like the reference. */
 int pnpf_push_accum(const float* zt, const float* v, float t, int S, float* x_new, long long n, void* stream);
+
+/* ONE whole PnP-Flow iteration (pnp_flow.py:107-121) on the S*B Monte-Carlo batch, for hosts that do not want to sequence
+ * the four calls above themselves:
+ *     z    = x - gamma * A^T(Ax - y)            (laplace != 0: A^T(2*heaviside(Ax - y, 0) - 1))       :39-45,111-112
+ *     zt_s = t z + (1-t) eps_s,  s < S          eps: [S][B,C,H,W] noise the caller drew (torch Philox for seed parity)   :47-48
+ *     v_s  = v_theta(zt_s, t)                   one U-Net evaluation at batch S*B (workspace bound for >= S*B)           :19-21
+ *     x_new = (sum_s (zt_s + (1-t) v_s)) / S                                                                              :50-52,114-121
+ * t = fp32(fp32(1/steps) * it) and gamma = lr_pnp * g(t) are computed by the host (pnp_flow.py:29-37,107-108).
+ * Caller-owned scratch: z [B,C,H,W], zt and v [S*B,C,H,W], t_dev [S*B]; x_new [B,C,H,W] (may alias x: x is last read by the first kernel).  Asynchronous on
+ * `stream`, CUDA-graph capturable, no allocation. */
+int pnpf_step(pnpf_engine* e, const pnpf_operator* op, int laplace, const float* x, const float* y, const float* eps, float t,
+              float gamma, int S, int B, int C, int H, int W, float* z, float* zt, float* t_dev, float* v, float* x_new,
+              void* stream);
+
+/* Forward-only sibling that shares the U-Net engine: one fixed-grid Euler step of the flow-matching ODE
+ *     x_next = x + dt * v_theta(x, t0)
+ * as FLOW_MATCHING.generate_samples(integration_method="euler") drives it through torchdiffeq's fixed-grid solver
+ * (pnpflow/train_flow_matching.py:170-198, cnf.forward :252-262).  t_dev [B] and v [B,C,H,W] are caller-owned scratch;
+ * x_next may alias x.  Asynchronous on `stream`, graph capturable. */
+int pnpf_euler_step(pnpf_engine* e, const float* x, float t0, float dt, int B, int C, int H, int W, float* t_dev, float* v,
+                    float* x_next, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Layer-level entry points (parity tests of the individual kernels; same kernels the plan uses)

@@ -15,3 +15,4 @@ from .unet import UNetConfig, unet_layer_spec, unet_forward, init_state_dict, CE
 from .operators import (Denoising, BoxInpainting, RandomInpainting, PaintbrushInpainting,  # noqa: F401
                         GaussianDeblurring, Superresolution, make_degradation, PROBLEMS)
 from .loop import pnp_flow_restore, learning_rate, psnr  # noqa: F401
+from .sampler import euler_sample  # noqa: F401,E402

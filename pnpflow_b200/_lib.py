@@ -26,7 +26,7 @@ class OperatorC(C.Structure):
                 ("taps", C.c_void_p), ("ksize", C.c_int), ("scratch", C.c_void_p)]
 
 
-OP_IDENTITY, OP_BOX, OP_MASK, OP_SR, OP_BLUR = range(5)
+OP_IDENTITY, OP_BOX, OP_MASK, OP_SR, OP_BLUR, OP_SR_BICUBIC = range(6)
 
 # name -> (restype, argtypes); must list every symbol include/pnpflow_b200.h declares (tests check this)
 _VP, _I, _LL, _F, _SZ = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
@@ -58,6 +58,8 @@ SYMBOLS = {
     "pnpf_datafit_step_laplace": (_I, [C.POINTER(OperatorC), _VP, _VP, _VP, _F, _I, _I, _I, _I, _VP]),
     "pnpf_interp": (_I, [_VP, _VP, _F, _VP, _LL, _I, _VP]),
     "pnpf_push_accum": (_I, [_VP, _VP, _F, _I, _VP, _LL, _VP]),
+    "pnpf_euler_step": (_I, [_VP, _VP, _F, _F, _I, _I, _I, _I, _VP, _VP, _VP, _VP]),
+    "pnpf_step": (_I, [_VP, C.POINTER(OperatorC), _I, _VP, _VP, _VP, _F, _F, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "pnpf_conv2d_nhwc": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _I, _VP]),
     "pnpf_gn_conv2d_nhwc": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _I, _I, _VP, _I, _VP]),
     "pnpf_gemm_nt": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),

@@ -364,6 +364,10 @@ int launch_upsample2x(const bf16* src, int B, int H, int W, int C, bf16* dst, cu
 // =================================================================================================
 // PnP-Flow per-pixel kernels
 // =================================================================================================
+__device__ __forceinline__ int floor_div(int a, int b) {      // b > 0
+    const int q = a / b;
+    return (a % b != 0 && a < 0) ? q - 1 : q;
+}
 __device__ __forceinline__ bool keep_pixel(const OpDesc& op, int b, int h, int w, int H, int W) {
     if (op.kind == 1) {                               // box: zero the square [d-hs, d+hs)^2, d = H//2 (utils.py:331-335)
         const int d = H / 2;
@@ -466,6 +470,83 @@ static int launch_blur(const OpDesc& op, const float* in, const float* aux, floa
     return 0;
 }
 
+// ---- Superresolution(mode='bicubic') (degradations.py:97-109,117-127; utils.py:365-396) -------------------------------------
+// The reference filters with the 4 sf x 4 sf bicubic kernel through the FFT (circular, the filter image rolled by -(K-1)//2 =
+// -K/2), then decimates; the adjoint zero-fills and correlates.  The kernel is separable, k = outer(g, g) with g = w / sum(w),
+// so both directions are direct sums here:
+//   H:      y[i, j]  = sum_{m1, m2} g[m1] g[m2] x[(sf i + K/2 - m1) mod H, (sf j + K/2 - m2) mod W]      K^2 MACs per LOW-res pixel
+//   H_adj:  u[n1,n2] = sum_{i, j}   g[sf i - n1 + K/2] g[sf j - n2 + K/2] r[i mod Hs, j mod Ws]          (K/sf)^2 = 16 MACs per pixel
+// mode 0: out = Hx ; 1: out = Hx - aux ; 3: out = sign(Hx - aux)   (aux = y, low resolution)
+__global__ void sr_bicubic_down_kernel(const float* __restrict__ x, const float* __restrict__ aux, float* __restrict__ out,
+                                       const float* __restrict__ taps, int K, int sf, int H, int W, int mode) {
+    extern __shared__ float g[];
+    for (int i = threadIdx.x; i < K; i += blockDim.x) g[i] = taps[i];
+    __syncthreads();
+    const int Hs = H / sf, Ws = W / sf;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;            // low-resolution pixel inside the plane
+    if (idx >= Hs * Ws) return;
+    const long long plane = blockIdx.y;
+    const int i = idx / Ws, j = idx - i * Ws;
+    const float* src = x + plane * H * W;
+    const int o = K / 2;
+    float acc = 0.f;
+    for (int m1 = 0; m1 < K; ++m1) {
+        int hh = (sf * i + o - m1) % H; if (hh < 0) hh += H;
+        const float* row = src + (long long)hh * W;
+        float racc = 0.f;
+        for (int m2 = 0; m2 < K; ++m2) {
+            int ww = (sf * j + o - m2) % W; if (ww < 0) ww += W;
+            racc = fmaf(g[m2], __ldg(row + ww), racc);
+        }
+        acc = fmaf(g[m1], racc, acc);
+    }
+    const long long oi = plane * Hs * Ws + idx;
+    if (mode == 1) acc = acc - aux[oi];
+    else if (mode == 3) acc = (acc - aux[oi] > 0.f) ? 1.f : -1.f;     // laplace: 2*heaviside(Hx - y, 0) - 1 (pnp_flow.py:43)
+    out[oi] = acc;
+}
+// mode 0: out = H^T r ; 2: out = aux - gamma * H^T r   (aux = x, full resolution)
+__global__ void sr_bicubic_up_kernel(const float* __restrict__ r, const float* __restrict__ aux, float* __restrict__ out,
+                                     const float* __restrict__ taps, int K, int sf, int H, int W, int mode, float gamma) {
+    extern __shared__ float g[];
+    for (int i = threadIdx.x; i < K; i += blockDim.x) g[i] = taps[i];
+    __syncthreads();
+    const int Hs = H / sf, Ws = W / sf;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;            // full-resolution pixel inside the plane
+    if (idx >= H * W) return;
+    const long long plane = blockIdx.y;
+    const int n1 = idx / W, n2 = idx - n1 * W;
+    const float* src = r + plane * Hs * Ws;
+    const int o = K / 2;
+    // low-resolution rows i with 0 <= sf i - n1 + o < K  (i may be negative or >= Hs: circular)
+    const int i0 = -floor_div(o - n1, sf), j0 = -floor_div(o - n2, sf);      // ceil((n - o) / sf)
+    float acc = 0.f;
+    for (int i = i0; sf * i - n1 + o < K; ++i) {
+        int ii = i % Hs; if (ii < 0) ii += Hs;
+        const float* row = src + (long long)ii * Ws;
+        float racc = 0.f;
+        for (int j = j0; sf * j - n2 + o < K; ++j) {
+            int jj = j % Ws; if (jj < 0) jj += Ws;
+            racc = fmaf(g[sf * j - n2 + o], __ldg(row + jj), racc);
+        }
+        acc = fmaf(g[sf * i - n1 + o], racc, acc);
+    }
+    const long long oi = plane * H * W + idx;
+    out[oi] = mode == 2 ? __fsub_rn(aux[oi], __fmul_rn(gamma, acc)) : acc;
+}
+static int launch_sr_bicubic(const OpDesc& op, bool up, const float* in, const float* aux, float* out, int planes, int H, int W, int mode,
+                             float gamma, cudaStream_t st) {
+    PNPF_REQUIRE(op.taps && op.sf >= 1 && op.ksize == 4 * op.sf && H % op.sf == 0 && W % op.sf == 0 && op.ksize <= H / 1 && op.ksize <= W,
+                 "bicubic SR: factor %d, %d taps vs image %dx%d", op.sf, op.ksize, H, W);
+    PNPF_REQUIRE(planes <= 65535, "bicubic SR: too many planes (%d)", planes);
+    const int n = up ? H * W : (H / op.sf) * (W / op.sf);
+    dim3 grid((n + 255) / 256, planes);
+    if (up) sr_bicubic_up_kernel<<<grid, 256, op.ksize * sizeof(float), st>>>(in, aux, out, op.taps, op.ksize, op.sf, H, W, mode, gamma);
+    else sr_bicubic_down_kernel<<<grid, 256, op.ksize * sizeof(float), st>>>(in, aux, out, op.taps, op.ksize, op.sf, H, W, mode);
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_apply_H(const OpDesc& op, const float* x, float* y, int B, int C, int H, int W, bool adjoint, cudaStream_t st) {
     const long long n = (long long)B * C * H * W;
     if (op.kind == 3) {
@@ -478,6 +559,8 @@ int launch_apply_H(const OpDesc& op, const float* x, float* y, int B, int C, int
         }
     } else if (op.kind == 4) {
         return launch_blur(op, x, nullptr, y, B * C, H, W, 0, 0.f, st);
+    } else if (op.kind == 5) {
+        return launch_sr_bicubic(op, adjoint, x, nullptr, y, B * C, H, W, 0, 0.f, st);
     } else {
         PNPF_REQUIRE(op.kind != 2 || op.mask, "mask operator without a device mask");
         apply_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, x, y, C, H, W, n);
@@ -565,6 +648,11 @@ int launch_datafit(const OpDesc& op, const float* x, const float* y, float* z, f
         if (int e = launch_blur(op, x, y, op.scratch, B * C, H, W, laplace ? 3 : 1, 0.f, st)) return e;   // r = Gx - y (or its sign)
         return launch_blur(op, op.scratch, x, z, B * C, H, W, 2, gamma, st);                 // z = x - gamma G r
     }
+    if (op.kind == 5) {
+        PNPF_REQUIRE(op.scratch, "bicubic SR data-fidelity step needs pnpf_operator.scratch (B*C*H*W/sf^2 floats)");
+        if (int e = launch_sr_bicubic(op, false, x, y, op.scratch, B * C, H, W, laplace ? 3 : 1, 0.f, st)) return e;   // r = Hx - y (or its sign)
+        return launch_sr_bicubic(op, true, op.scratch, x, z, B * C, H, W, 2, gamma, st);                               // z = x - gamma H^T r
+    }
     PNPF_REQUIRE(op.kind >= 0 && op.kind <= 3, "unknown operator kind %d", op.kind);
     PNPF_REQUIRE(op.kind != 2 || op.mask, "mask operator without a device mask");
     PNPF_REQUIRE(op.kind != 3 || (op.sf >= 1 && H % op.sf == 0 && W % op.sf == 0), "SR factor %d vs %dx%d", op.sf, H, W);
@@ -621,17 +709,20 @@ int launch_interp(const float* z, const float* eps, float t, float* zt, long lon
     return 0;
 }
 
-// x_new = (sum_s (zt_s + (1-t) v_s)) / S, summed in draw order with separately rounded ops and a true division
-// (pnp_flow.py:114-121: x_new += ...; x_new /= num_samples)
-__global__ void push_accum_kernel(const float* __restrict__ zt, const float* __restrict__ v, float omt, int S, float fS,
+// x_new = (sum_s (zt_s + (1-t) v_s)) / S, summed in draw order with separately rounded ops (pnp_flow.py:114-121: x_new += ...;
+// x_new /= num_samples).  The final "/= S" is a MULTIPLICATION by fp32(1/S): that is what the reference's GPU path executes —
+// ATen's CUDA true-divide kernel turns division by a CPU scalar into `a * (1 / b)` (BinaryDivTrueKernel.cu), only the CPU kernel
+// divides.  Verified on the B200: with __fdiv_rn the result differs from eager torch-CUDA in the last bit, with the reciprocal it
+// is torch.equal (tests/test_gpu_pnp.py).
+__global__ void push_accum_kernel(const float* __restrict__ zt, const float* __restrict__ v, float omt, int S, float invS,
                                   float* __restrict__ x_new, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float acc = 0.f;
     for (int s = 0; s < S; ++s) acc = __fadd_rn(acc, __fadd_rn(zt[s * n + i], __fmul_rn(omt, v[s * n + i])));
-    x_new[i] = __fdiv_rn(acc, fS);
+    x_new[i] = __fmul_rn(acc, invS);
 }
-__global__ void push_accum_vec4_kernel(const float* __restrict__ zt, const float* __restrict__ v, float omt, int S, float fS,
+__global__ void push_accum_vec4_kernel(const float* __restrict__ zt, const float* __restrict__ v, float omt, int S, float invS,
                                        float* __restrict__ x_new, long long n4) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
@@ -645,16 +736,35 @@ __global__ void push_accum_vec4_kernel(const float* __restrict__ zt, const float
         acc.z = __fadd_rn(acc.z, __fadd_rn(a.z, __fmul_rn(omt, b.z)));
         acc.w = __fadd_rn(acc.w, __fadd_rn(a.w, __fmul_rn(omt, b.w)));
     }
-    *reinterpret_cast<float4*>(x_new + i * 4) = make_float4(__fdiv_rn(acc.x, fS), __fdiv_rn(acc.y, fS), __fdiv_rn(acc.z, fS), __fdiv_rn(acc.w, fS));
+    *reinterpret_cast<float4*>(x_new + i * 4) = make_float4(__fmul_rn(acc.x, invS), __fmul_rn(acc.y, invS), __fmul_rn(acc.z, invS), __fmul_rn(acc.w, invS));
 }
 int launch_push_accum(const float* zt, const float* v, float t, int S, float* x_new, long long n, cudaStream_t st) {
     PNPF_REQUIRE(S >= 1, "num_samples %d", S);
     if (n % 4 == 0 && aligned16(zt) && aligned16(v) && aligned16(x_new)) {
         const long long n4 = n / 4;
-        push_accum_vec4_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(zt, v, 1.0f - t, S, (float)S, x_new, n4);
+        push_accum_vec4_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(zt, v, 1.0f - t, S, 1.0f / (float)S, x_new, n4);
     } else {
-        push_accum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(zt, v, 1.0f - t, S, (float)S, x_new, n);
+        push_accum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(zt, v, 1.0f - t, S, 1.0f / (float)S, x_new, n);
     }
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// out = x + a * v with separately rounded product and sum (one fixed-grid Euler step  y1 = y0 + dt * f(t0, y0))
+__global__ void axpy_kernel(const float* __restrict__ x, const float* __restrict__ v, float a, float* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __fadd_rn(x[i], __fmul_rn(a, v[i]));
+}
+__global__ void axpy_vec4_kernel(const float* __restrict__ x, const float* __restrict__ v, float a, float* __restrict__ out, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 p = ldg_stream_f4(x + i * 4), q = ldg_stream_f4(v + i * 4);
+    *reinterpret_cast<float4*>(out + i * 4) = make_float4(__fadd_rn(p.x, __fmul_rn(a, q.x)), __fadd_rn(p.y, __fmul_rn(a, q.y)),
+                                                          __fadd_rn(p.z, __fmul_rn(a, q.z)), __fadd_rn(p.w, __fmul_rn(a, q.w)));
+}
+int launch_axpy(const float* x, const float* v, float a, float* out, long long n, cudaStream_t st) {
+    if (n % 4 == 0 && aligned16(x) && aligned16(v) && aligned16(out)) axpy_vec4_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(x, v, a, out, n / 4);
+    else axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, v, a, out, n);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -53,5 +53,7 @@ int launch_datafit(const OpDesc& op, const float* x, const float* y, float* z, f
 // zt[s][i] = t*z[i] + (1-t)*eps[s][i]
 int launch_interp(const float* z, const float* eps, float t, float* zt, long long n, int S, cudaStream_t st);
 int launch_push_accum(const float* zt, const float* v, float t, int S, float* x_new, long long n, cudaStream_t st);
+// out = x + a * v (fixed-grid Euler step of the flow-matching sampler)
+int launch_axpy(const float* x, const float* v, float a, float* out, long long n, cudaStream_t st);
 
 }  // namespace pnpf

@@ -59,14 +59,15 @@ def psnr(rec: torch.Tensor, clean: torch.Tensor) -> torch.Tensor:
 def restore(engine: UNetEngine, y: torch.Tensor, degradation, sigma_noise: float, *, steps_pnp: int = 100,
             lr_pnp: float = 1.0, alpha: float = 1.0, gamma_style: str = 'alpha_1_minus_t', num_samples: int = 5,
             noise_type: str = 'gaussian', noise: Optional[Iterable[torch.Tensor]] = None,
-            trace: Optional[Callable[[int, torch.Tensor], None]] = None, use_cuda_graph: bool = True) -> torch.Tensor:
+            trace: Optional[Callable[[int, torch.Tensor], None]] = None, use_cuda_graph: bool = True,
+            whole_step_call: bool = False) -> torch.Tensor:
     """The T-step PnP-Flow loop for one batch of measurements ``y`` (CUDA fp32); returns the restored x.
 
     Mirrors pnp_flow.py:93,102-121.  ``noise``: optional iterable of eps tensors [B,C,H,W], one per (step, draw).
     """
     sess = PnPFlowSession(engine, degradation, tuple(y.shape), steps_pnp=steps_pnp, lr_pnp=lr_pnp, alpha=alpha,
                           gamma_style=gamma_style, num_samples=num_samples, noise_type=noise_type,
-                          use_cuda_graph=use_cuda_graph, device=y.device)
+                          use_cuda_graph=use_cuda_graph, device=y.device, whole_step_call=whole_step_call)
     return sess.run(y, noise=noise, trace=trace)
 
 
@@ -77,7 +78,8 @@ class PnPFlowSession:
     draws, one interpolation kernel, one U-Net evaluation on the S*B batch, one push+average kernel."""
 
     def __init__(self, engine: UNetEngine, degradation, y_shape, *, steps_pnp=100, lr_pnp=1.0, alpha=1.0,
-                 gamma_style='alpha_1_minus_t', num_samples=5, noise_type='gaussian', use_cuda_graph=True, device="cuda"):
+                 gamma_style='alpha_1_minus_t', num_samples=5, noise_type='gaussian', use_cuda_graph=True, device="cuda",
+                 whole_step_call=False):
         if noise_type not in ('gaussian', 'laplace'):
             raise ValueError('Noise type not supported')                     # pnp_flow.py:45,68,87
         self.noise_type = noise_type
@@ -93,6 +95,11 @@ class PnPFlowSession:
         Hh = Ww = engine.cfg["input_height"]
         self.shape = (B, Cc, Hh, Ww)
         self.n = B * Cc * Hh * Ww
+        # whole_step_call: run every iteration through the single C entry point pnpf_step (what a non-Python host would call)
+        # instead of sequencing data-fit / interpolate / U-Net graph replay / push from here; eager launches, same kernels
+        self.whole_step_call = bool(whole_step_call) and hasattr(self.op, "descriptor") and type(self.op).__name__ != "_PythonOperator"
+        if self.whole_step_call:
+            use_cuda_graph = False
         self.use_cuda_graph = use_cuda_graph
         with torch.cuda.device(self.dev):
             self.z = torch.empty(self.shape, device=self.dev)
@@ -130,6 +137,17 @@ class PnPFlowSession:
         t = step_time(self.delta, it)                                        # :107-108
         gamma = gamma_schedule(self.lr_pnp, t, self.gamma_style, self.alpha)
         with torch.no_grad(), torch.cuda.device(self.dev):
+            if self.whole_step_call:
+                for s in range(S):
+                    self.eps[s].copy_(next(noise_it) if noise_it is not None else torch.randn_like(self.z))
+                B, Cc, Hh, Ww = self.shape
+                opd, _keep = self.op.descriptor(B, Cc, Hh, Ww, self.dev)
+                x_new = self.xbuf[self._flip]
+                self._flip ^= 1
+                _lib.check(self.lib.pnpf_step(self.engine._h, C.byref(opd), 1 if self.noise_type == 'laplace' else 0, x.data_ptr(),
+                                              y.data_ptr(), self.eps.data_ptr(), t, gamma, S, B, Cc, Hh, Ww, self.z.data_ptr(),
+                                              self.zt.data_ptr(), self.tb.data_ptr(), self.v.data_ptr(), x_new.data_ptr(), sp()))
+                return x_new
             self.op.datafit_step(x, y, gamma, out=self.z, noise_type=self.noise_type)
             for s in range(S):
                 if noise_it is not None:

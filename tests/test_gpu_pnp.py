@@ -75,7 +75,7 @@ def test_datafit_interp_push_vs_oracle():
     for s in range(S):
         acc += zt[s] + (1 - tb) * v[s]
     acc /= S
-    assert torch.equal(out, acc)                  # draw-order sum and a true division (pnp_flow.py:114-121): bit-exact
+    assert torch.equal(out, acc)                  # draw-order sum; '/= S' as torch-CUDA executes it (a * (1/S)): bit-exact
 
 
 @pytest.mark.parametrize("problem,alpha", [("box", 0.5), ("random", 0.01), ("sr2", 0.3), ("blur", 0.01), ("paintbrush", 0.5), ("denoising", 0.8)])
@@ -149,3 +149,48 @@ def test_method_plugin_surface():
     args.noise_type = 'poisson'
     with pytest.raises(ValueError, match='Noise type not supported'):
         m.solve_ip(loader, P.BoxInpainting(10), 0.05)
+
+
+def test_whole_step_c_entry_equals_sequenced_calls():
+    """pnpf_step (one C call per PnP iteration: data-fit, interpolate, U-Net at batch S*B, push+average) against the
+    session's own sequence of the four calls, for a diagonal operator, blur (scratch) and SR, both noise models."""
+    import pnpflow_b200 as P
+    cfg = oracle.UNetConfig(3, 64, 32, (1, 2), 1, (16,))
+    sd = oracle.init_state_dict(cfg, seed=2)
+    eng = P.UNetEngine(cfg, sd, max_batch=6)
+    g = torch.Generator().manual_seed(3)
+    clean = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    T, S = 4, 3
+    noise = [torch.randn(2, 3, 64, 64, generator=g).cuda() for _ in range(T * S)]
+    for name in ("random", "blur", "sr2"):
+        eng_op, orc_op = _ops()[name]
+        y = oracle.loop.synthesize_measurement(clean, orc_op.H, 0.05, 0).float().cuda()
+        for nt in ("gaussian", "laplace"):
+            a = P.restore(eng, y, eng_op, 0.05, steps_pnp=T, num_samples=S, alpha=0.5, noise=noise, noise_type=nt)
+            b = P.restore(eng, y, eng_op, 0.05, steps_pnp=T, num_samples=S, alpha=0.5, noise=noise, noise_type=nt, whole_step_call=True)
+            assert torch.isfinite(b).all()
+            assert ((a - b).norm() / a.norm()).item() < 2e-3, (name, nt)      # same kernels; GroupNorm statistics atomics reorder
+
+
+def test_euler_sampler_vs_oracle():
+    """generate_samples (train_flow_matching.py:170-198 with torchdiffeq's fixed-grid Euler restated in
+    oracle/sampler.py): same latent, 10 grid points, engine vs fp32 oracle."""
+    import pnpflow_b200 as P
+    cfg = oracle.UNetConfig(3, 64, 32, (1, 2), 1, (16,))
+    sd = oracle.init_state_dict(cfg, seed=2, end_gain=1.0)
+    g = torch.Generator().manual_seed(8)
+    x0 = torch.randn(5, 3, 64, 64, generator=g)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = oracle.euler_sample(lambda a, b: oracle.unet_forward(sd, cfg, a, b), x0, integration_steps=10)
+    eng = P.UNetEngine(cfg, sd, max_batch=3)
+    out = P.generate_samples(eng, n_samples=5, batch_size=3, integration_steps=10, x0=x0.cuda()).cpu()       # batches 3 + 2 (:176-181)
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert (ref - x0).norm() / x0.norm() > 0.05            # the flow moved the latent: the comparison is not vacuous
+    assert ((out - ref).norm() / ref.norm()).item() < 3e-2
+    torch.manual_seed(4)
+    a = P.generate_samples(eng, n_samples=2, integration_steps=3)
+    torch.manual_seed(4)
+    b = oracle.euler_sample(lambda u, t: oracle.unet_forward({k: v.cuda() for k, v in sd.items()}, cfg, u, t),
+                            torch.randn(2, 3, 64, 64, device="cuda"), integration_steps=3)
+    assert ((a - b).norm() / b.norm()).item() < 3e-2       # seeded path: the same torch.randn latent as :187-188

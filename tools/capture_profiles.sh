@@ -3,7 +3,7 @@
 # tensor-core kernels and gn_apply.  The raw metric pages are exported to CSV ON THE BOX and the .ncu-rep files deleted unless
 # KEEP_REP=1 (gpurun copies back at most 64 MiB; a capture with --import-source is ~17 MB).  Outputs land in gpurun_out/;
 # tools/summarize_profiles.py turns them into profiles/<tag>_*.json.
-TAG=${1:-r01}
+TAG=${1:-r02}
 SRC=${KEEP_REP:+--import-source on}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv --log-file gpurun_out/${TAG}_launches.csv \
@@ -20,4 +20,8 @@ cap rowconv_l1up rowconv 26 2
 cap patchconv_l2 patchconv 1 2
 cap patchconv_l3 patchconv 13 2
 cap gn_apply gn_apply 2 2
+# per-pixel PnP kernels (data-fidelity step of the BASELINE operators, interpolate, push + average): tools/ncu_pnp.py
+ncu --set full --clock-control none -k regex:"datafit|interp|push_accum|blur|sr_bicubic" -o gpurun_out/${TAG}_pnp_pixel -f python tools/ncu_pnp.py > gpurun_out/${TAG}_ncu_pnp_pixel.log 2>&1
+ncu -i gpurun_out/${TAG}_pnp_pixel.ncu-rep --page raw --csv > gpurun_out/${TAG}_pnp_pixel.raw.csv 2>/dev/null
+[ -z "$KEEP_REP" ] && rm -f gpurun_out/${TAG}_pnp_pixel.ncu-rep
 ls -la gpurun_out/ | head -30

@@ -78,7 +78,8 @@ if dram:
     json.dump(dict(source=f"{tag}_*_ncu.json (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                    kernels={k: dict(dram_bytes_per_launch=v, dram_bytes_per_launch_mean=sum(v) / len(v)) for k, v in dram.items()}),
               open(os.path.join(P, f"{tag}_kernel_dram_bytes.json"), "w"), indent=1)
-for src, dst in (("unet_profile_afhq256_b80.json", f"{tag}_unet_ops_afhq256_b80.json"), ("parity_report.json", f"{tag}_parity_report.json"),
-                 ("rate_probe3.json", f"{tag}_umma_rate_probe.json"), ("offset_probe.json", f"{tag}_umma_row_offset_probe.json")):
-    if os.path.exists(os.path.join(G, src)):
-        json.dump(json.load(open(os.path.join(G, src))), open(os.path.join(P, dst), "w"), indent=0)
+# parity numbers written by tests/test_gpu_parity_baseline.py during the same gpurun call (fresh file only: gpurun_out is scratch)
+for src, dst in (("parity_baseline.json", f"{tag}_parity_baseline.json"),):
+    sp = os.path.join(G, src)
+    if os.path.exists(sp) and "--with-parity" in sys.argv:
+        json.dump(json.load(open(sp)), open(os.path.join(P, dst), "w"), indent=1)
