@@ -180,6 +180,12 @@ int pnpf_upconv2x_nhwc(const void* x, int B, int H, int W, int Cin, const float*
                        void* out, void* stream);
 /* out[b] = A[b] (M x K) * Bm[b]^T (N x K), bf16 row-major operands, fp32 (out_f32=1) or bf16 output. Synchronous. */
 int pnpf_gemm_nt(const void* A, const void* Bm, void* out, int batch, int M, int N, int K, int out_f32, void* stream);
+/* Fused attention core of the 16x16 attention blocks (models.py:145-162 after the q/k/v projections):
+ * out = residual + softmax(q k^T) v Wo^T + bias, one kernel, logits and probabilities stay on chip (pnpf_attn.cuh).
+ * qk: device bf16 [B,L,2C] (q already scaled by C^-1/2 | k); vT: device bf16 [B,C,L]; host_wo: HOST fp32 [C,C] (proj_out, OI);
+ * host_bias: HOST fp32 [C] or NULL; residual: device bf16 [B,L,C] or NULL; out: device bf16 [B,L,C].  L = C = 256.  Synchronous. */
+int pnpf_attn_core_nhwc(const void* qk, const void* vT, const float* host_wo, const float* host_bias, const void* residual, void* out,
+                        int B, int L, int C, void* stream);
 
 #ifdef __cplusplus
 }

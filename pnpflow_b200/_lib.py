@@ -63,6 +63,7 @@ SYMBOLS = {
     "pnpf_conv2d_nhwc": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _I, _VP]),
     "pnpf_gn_conv2d_nhwc": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _I, _I, _VP, _I, _VP]),
     "pnpf_gemm_nt": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "pnpf_attn_core_nhwc": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "pnpf_fold_subpixel_weights": (_I, [_VP, _I, _I, _I, _I, _VP]),
     "pnpf_upconv2x_nhwc": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP]),
 }

@@ -222,3 +222,35 @@ extern "C" int pnpf_gn_conv2d_nhwc(const void* xa, int Ca, const void* xb, int C
     PNPF_CHECK_CUDA(e);
     return 0;
 }
+
+// Fused attention core on device tensors (parity test of pnpf_attn.cuh): qk bf16 [B][L][2C] (q scaled | k), vT bf16 [B][C][L],
+// host_wo fp32 [C][C] (proj_out weight, OI), host_bias fp32 [C] or NULL, residual bf16 [B][L][C] or NULL -> out bf16 [B][L][C].
+extern "C" int pnpf_attn_core_nhwc(const void* qk, const void* vT, const float* host_wo, const float* host_bias, const void* residual, void* out,
+                                   int B, int L, int C, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PNPF_REQUIRE(qk && vT && host_wo && out, "null pointer");
+    PNPF_REQUIRE(attn_core_eligible(L, C), "fused attention core handles L = 256 tokens, C = 256 channels (got %d, %d)", L, C);
+    std::vector<bf16> wp((size_t)C * C);
+    pack_conv_weight(wp.data(), host_wo, C, C, 1, C, C, nullptr, 0, 1.0f);
+    std::vector<float> bp(C, 0.f);
+    if (host_bias)
+        for (int i = 0; i < C; ++i) bp[i] = host_bias[i];
+    bf16* dw = nullptr;
+    float* db = nullptr;
+    PNPF_CHECK_CUDA(cudaMalloc(&dw, wp.size() * sizeof(bf16)));
+    PNPF_CHECK_CUDA(cudaMalloc(&db, bp.size() * sizeof(float)));
+    PNPF_CHECK_CUDA(cudaMemcpyAsync(dw, wp.data(), wp.size() * sizeof(bf16), cudaMemcpyHostToDevice, s));
+    PNPF_CHECK_CUDA(cudaMemcpyAsync(db, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    AttnDesc d;
+    d.qk = static_cast<const bf16*>(qk); d.vT = static_cast<const bf16*>(vT); d.w = dw; d.bias = db;
+    d.residual = static_cast<const bf16*>(residual); d.out = static_cast<bf16*>(out); d.B = B; d.L = L; d.C = C;
+    AttnOp op;
+    int rc = prepare_attn(op, d);
+    if (!rc) rc = launch_attn(op, B, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(dw);
+    cudaFree(db);
+    if (rc) return rc;
+    PNPF_CHECK_CUDA(e);
+    return 0;
+}

@@ -415,6 +415,46 @@ int launch_tc(const TcOp& op, cudaStream_t s) {
     return launch_conv_gemm(op.BK, op.BN, op.tmA, op.tmA2, op.tmB, op.tmBh, op.p, s);
 }
 
+// ---- fused attention core ---------------------------------------------------------------------------------------------------
+bool attn_core_eligible(int L, int C) {
+    static const bool off = getenv("PNPF_NO_FUSED_ATTN") != nullptr;     // A/B switch (tools/ab_env.py)
+    return !off && L == AttnCfg::L && C == AttnCfg::C;
+}
+int prepare_attn(AttnOp& op, const AttnDesc& d) {
+    PNPF_REQUIRE(d.L == AttnCfg::L && d.C == AttnCfg::C, "fused attention core is built for L = %d tokens, C = %d channels (got %d, %d)", AttnCfg::L,
+                 AttnCfg::C, d.L, d.C);
+    PNPF_REQUIRE(d.qk && d.vT && d.w && d.out, "fused attention: null operand");
+    memset(&op.p, 0, sizeof(op.p));
+    op.p.n_img = d.B; op.p.L = d.L; op.p.C = d.C;
+    EpiParams& e = op.p.epi;
+    e.out = d.out; e.out_mode = 0; e.out_img_stride = (long long)d.L * d.C; e.out_row_stride = d.C; e.out_col_stride = 1; e.n_valid = d.C;
+    e.bias = d.bias;
+    e.residual = d.residual; e.res_img_stride = (long long)d.L * d.C; e.res_row_stride = d.C;
+    e.stats = d.stats_out;
+    if (int rc = make_act_tmap(&op.tmQ, d.qk, d.C, 2LL * d.C, d.L, 1, d.B, 64, 128, 1, 1)) return rc;
+    if (int rc = make_b_tmap(&op.tmK, d.qk + d.C, d.C, 2LL * d.C, d.L, d.B, (long long)d.L * 2 * d.C, 64, 256)) return rc;
+    if (int rc = make_b_tmap(&op.tmV, d.vT, d.L, d.L, d.C, d.B, (long long)d.C * d.L, 64, 256)) return rc;
+    if (int rc = make_b_tmap(&op.tmW, d.w, d.C, d.C, d.C, 1, 0, 64, 256)) return rc;
+    op.flops = (double)d.B * (2.0 * d.L * d.L * d.C * 2 + 2.0 * d.L * d.C * d.C);
+    return 0;
+}
+int launch_attn(const AttnOp& op, int n_img, cudaStream_t s) {
+    static DeviceCache cache;
+    int dummy = 0;
+    if (!cache.lookup(&dummy)) {
+        PNPF_CHECK_CUDA(cudaFuncSetAttribute(attn_core_kernel<AttnCfg::L, AttnCfg::C>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg::SMEM_BYTES));
+        cache.store(1);
+    }
+    AttnParams q = op.p;
+    q.n_img = n_img;
+    const int units = n_img * (AttnCfg::L / 128);
+    if (units < 1) return 0;
+    const int grid = units < num_sms() ? units : num_sms();
+    attn_core_kernel<AttnCfg::L, AttnCfg::C><<<grid, AttnCfg::THREADS, AttnCfg::SMEM_BYTES, s>>>(op.tmQ, op.tmK, op.tmV, op.tmW, q);
+    PNPF_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static inline bf16 f2bf(float f) { return __float2bfloat16_rn(f); }
 
 void pack_conv_weight(bf16* dst, const float* w, int O, int Cin, int ks, int N_pad, int Cin_pad, const float* w2, int C2,

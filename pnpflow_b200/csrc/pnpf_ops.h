@@ -3,6 +3,7 @@
 #include "pnpf_host.h"
 #include "pnpf_rowconv.cuh"
 #include "pnpf_patchconv.cuh"
+#include "pnpf_attn.cuh"
 
 namespace pnpf {
 
@@ -94,6 +95,26 @@ struct GemmDesc {           // out[b][m][n] = sum_k A[b|0][m][k] * Bm[b|0][n][k]
 };
 int prepare_gemm(TcOp& op, const GemmDesc& d);
 int launch_tc(const TcOp& op, cudaStream_t s);
+
+// ------------------------------------------------------------------ fused attention core (pnpf_attn.cuh)
+struct AttnOp {
+    CUtensorMap tmQ, tmK, tmV, tmW;
+    AttnParams p;
+    double flops = 0;
+};
+struct AttnDesc {
+    const bf16* qk = nullptr;       // [B][L][2C]: q (scaled) | k
+    const bf16* vT = nullptr;       // [B][C][L]
+    const bf16* w = nullptr;        // packed projection weights [N_pad = C][C]
+    const float* bias = nullptr;    // [C]
+    const bf16* residual = nullptr; // [B][L][C]
+    bf16* out = nullptr;            // [B][L][C]
+    double* stats_out = nullptr;    // optional [B][C][2]
+    int B = 0, L = 0, C = 0;
+};
+bool attn_core_eligible(int L, int C);
+int prepare_attn(AttnOp& op, const AttnDesc& d);
+int launch_attn(const AttnOp& op, int n_img, cudaStream_t s);
 
 // host-side weight repack: OIHW fp32 (reference layout) -> [N_pad][k*k*Cin_pad + C2] bf16, K ordered (kh, kw, cin),
 // optionally followed by the 1x1 shortcut weights w2 [O][C2]; rows >= O and channels >= Cin are zero.

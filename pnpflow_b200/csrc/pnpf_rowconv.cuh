@@ -154,11 +154,6 @@ __device__ __forceinline__ void bar_sync_set(int set) {
     if (set == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
     else asm volatile("bar.sync 2, 128;" ::: "memory");
 }
-// one lane polls, the warp follows
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
-    if (lane == 0) mbar_wait(bar, parity);
-    __syncwarp();
-}
 
 template <int BK, int BN, int KCH, int NEW_>
 __global__ void __launch_bounds__(RowCfg<BK, BN, NEW_>::BOUND_THREADS, 1)

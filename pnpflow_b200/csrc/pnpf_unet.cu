@@ -41,9 +41,10 @@ struct Act {                      // bf16 NHWC activation [B][side][side][C]
 };
 
 struct Op {
-    enum Kind { MEMSET, IN_SHIM, TEMB, TC, GN_STATS, GN_APPLY, SOFTMAX, UPSAMPLE } kind;
+    enum Kind { MEMSET, IN_SHIM, TEMB, TC, GN_STATS, GN_APPLY, SOFTMAX, UPSAMPLE, ATTN } kind;
     std::string name;
     TcOp tc;
+    AttnOp attn;                  // kind == ATTN: fused attention core (pnpf_attn.cuh)
     GnSrc gsrc{};
     int HW = 0;
     double* stats = nullptr;
@@ -736,6 +737,26 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 gv.M = C; gv.N = Lk; gv.K = C;
                 gv.out = t_a2; gv.out_mode = 0; gv.out_img_stride = (long long)C * Lk; gv.out_row_stride = Lk;
                 if (int rc = add_gemm(p + ".vT", gv)) return rc;
+                if (attn_core_eligible(Lk, C)) {
+                    // fused core: S = q k^T in TMEM -> row softmax in registers -> P v -> proj_out + bias + residual, one launch;
+                    // the fp32 logits and the probabilities never reach HBM (pnpf_attn.cuh)
+                    Act y = new_h(C, side, L.push);
+                    Op o;
+                    o.kind = Op::ATTN; o.name = p; o.impl = "attn_core<256,256> S->softmax->PV->proj fused";
+                    AttnDesc ad;
+                    ad.qk = t_qk; ad.vT = t_a2; ad.residual = h.p; ad.out = y.p; ad.stats_out = y.stats; ad.B = Bm; ad.L = Lk; ad.C = C;
+                    if (real) {
+                        ad.w = wptr<bf16>(e, p + ".proj.w"); ad.bias = wptr<float>(e, p + ".proj.b");
+                        if (int rc = prepare_attn(o.attn, ad)) return rc;
+                    }
+                    o.flops = 2.0 * Lk * Lk * C * 2 + 2.0 * Lk * C * C;
+                    o.bytes = 2.0 * (3.0 * Lk * C + 2.0 * Lk * C);          // q, k, v^T, residual in; y out
+                    flops += o.flops;
+                    set_out(o, y.p, C, side);
+                    ops.push_back(o);
+                    h = y;
+                    break;
+                }
                 GemmDesc gs;                                   // S[b] = q[b] k[b]^T   (fp32 logits)
                 gs.A = t_qk; gs.lda = 2 * C; gs.a_bstride = px * 2 * C; gs.a_batched = 1;
                 gs.Bm = t_qk + C; gs.ldb = 2 * C; gs.b_bstride = px * 2 * C; gs.b_batched = 1;
@@ -929,6 +950,9 @@ static int run_ops(pnpf_engine* e, const float* x, const float* t, float* v, int
             case Op::SOFTMAX:
                 rc = launch_softmax_rows(o.S, o.P, o.rows_per_img * batch, o.L, st);
                 break;
+            case Op::ATTN:
+                rc = launch_attn(o.attn, batch, st);
+                break;
             case Op::UPSAMPLE:
                 rc = launch_upsample2x(o.up_src, batch, o.up_side, o.up_side, o.up_C, o.dst, st);
                 break;
@@ -1011,7 +1035,7 @@ extern "C" int pnpf_profile_forward(pnpf_engine* e, const float* x, const float*
 // kind: 1 = tensor-core (conv_gemm) op, 0 = SIMT / memset; flops and algorithmic HBM bytes are PER IMAGE
 extern "C" int pnpf_debug_op_info(pnpf_engine* e, int i, int* kind, double* flops, double* bytes) {
     PNPF_REQUIRE(e && i >= 0 && i < (int)e->ops.size() && kind && flops && bytes, "bad argument");
-    *kind = e->ops[i].kind == Op::TC ? 1 : 0;
+    *kind = (e->ops[i].kind == Op::TC || e->ops[i].kind == Op::ATTN) ? 1 : 0;
     *flops = e->ops[i].flops;
     *bytes = e->ops[i].bytes;
     return 0;

@@ -157,3 +157,34 @@ def test_unsupported_shape_is_an_error_not_a_fallback():
     out = torch.zeros(1, 8, 8, 16, device="cuda")
     rc = lib.pnpf_conv2d_nhwc(x.data_ptr(), 1, 8, 8, 24, w.data_ptr(), None, 16, 3, 1, None, 0, None, None, out.data_ptr(), 1, None)
     assert rc != 0 and b"multiples of 32" in lib.pnpf_last_error()
+
+
+@pytest.mark.parametrize("B", [1, 5, 150])
+def test_fused_attention_core_vs_torch(B):
+    """pnpf_attn.cuh: out = x + softmax(q k^T) v Wo^T + b for the 16x16 attention blocks (models.py:145-162), logits in TMEM,
+    softmax in registers, probabilities and O through shared memory.  B = 150 gives every CTA more than one (image, query tile)
+    unit, which exercises the barrier phases and the shared-memory / TMEM hand-over between units."""
+    from pnpflow_b200 import _lib
+    lib = _lib.load()
+    L = C = 256
+    g = torch.Generator().manual_seed(11 + B)
+    q = (torch.randn(B, L, C, generator=g) * 0.125).bfloat16()           # logits ~ N(0, 4): a peaked but not one-hot softmax
+    k = torch.randn(B, L, C, generator=g).bfloat16()
+    v = torch.randn(B, L, C, generator=g).bfloat16()
+    wo = (torch.randn(C, C, generator=g) * 0.05).bfloat16().float()
+    bias = torch.randn(C, generator=g)
+    res = torch.randn(B, L, C, generator=g).bfloat16()
+    qk = torch.cat([q, k], dim=-1).contiguous().cuda()
+    vT = v.transpose(1, 2).contiguous().cuda()
+    out = torch.empty(B, L, C, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.pnpf_attn_core_nhwc(qk.data_ptr(), vT.data_ptr(), wo.contiguous().data_ptr(), bias.data_ptr(), res.cuda().data_ptr(),
+                                       out.data_ptr(), B, L, C, None))
+    qf, kf, vf = q.float().cuda(), k.float().cuda(), v.float().cuda()
+    P = torch.softmax(qf @ kf.transpose(1, 2), dim=-1)
+    ref = res.float().cuda() + (P @ vf) @ wo.cuda().t() + bias.cuda()
+    got = out.float()
+    assert torch.isfinite(got).all()
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel < 6e-3, rel          # bf16 P, bf16 O and the bf16 output rounding
+    attn_only = ((got - res.float().cuda() - bias.cuda()) - (ref - res.float().cuda() - bias.cuda())).norm() / (ref - res.float().cuda() - bias.cuda()).norm()
+    assert attn_only.item() < 2e-2, attn_only.item()
