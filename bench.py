@@ -155,8 +155,13 @@ def time_hbm_kernels(sess, x, y, pk, K=10):
             ("push_accum", lambda: _lib.check(lib.pnpf_push_accum(sess.zt.data_ptr(), sess.v.data_ptr(), 0.3, S, sess.xbuf[0].data_ptr(), n, sp())), (8.0 * S + 4.0) * n)):
         ms = timed(fn)
         tr, src = ncu_traffic({"datafit_step": "blur" if opname == "GaussianDeblurring" else "datafit_diag"}.get(name.split("[")[0], name))
-        out.append({"kernel": name, "ms": ms, "algorithmic_bytes": by, "achieved": by / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": by / (ms * 1e-3) / 1e9 / pk["hbm"], "traffic": tr, "traffic_source": src})
+        row = {"kernel": name, "ms": ms, "algorithmic_bytes": by, "achieved": by / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+               "frac": by / (ms * 1e-3) / 1e9 / pk["hbm"], "traffic": tr, "traffic_source": src,
+               "note": "one launch timed alone with CUDA events (includes ~2 us of launch latency on a 10-30 us kernel)"}
+        if opname == "GaussianDeblurring" and name.startswith("datafit"):
+            row["note"] = ("two launches of the separable circular 61-tap filter: 244 FMA per pixel out of shared memory — bound by the "
+                           "shared-memory pipe, not by HBM; the HBM fraction is reported for completeness")
+        out.append(row)
     return out
 
 
@@ -293,6 +298,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     net = synth.NETS[c["net"]]
     side, B, S, T = net["input_height"], c["b_per_gpu"], c["S"], c["T"]
@@ -427,9 +433,30 @@ def main():
                 for i in range(2):
                     x1 = sess1.step(x1, y_full, 50 + i)              # world-1 semantics: randn_like of the full batch
                 d = (x1 - full).abs().max().item()
-                shard_check = {"what": "2 PnP steps, seed 77: gathered sharded result vs the same full batch run unsharded on rank 0",
-                               "max_abs_diff": d, "equal_within_1e-3": bool(d < 1e-3),
+                # noise floor of the comparison: the SAME unsharded run with the images in reversed order.  A different batch
+                # composition changes how rows are split over CTAs, hence the grouping of the fp32 partial sums behind the
+                # GroupNorm statistics, hence an occasional bf16 rounding flip — the only way two runs of the engine differ.
+                idx = torch.arange(Btot - 1, -1, -1, device=dev)
+                op_rev = sharding.shard_operator(op_full, 0, Btot, Btot)
+                if hasattr(op_rev, "_host_mask"):
+                    fwd_mask = op_rev._host_mask
+                    op_rev._host_mask = lambda B_, H_, W_: fwd_mask(B_, H_, W_)[::-1].copy()
+                y_rev = y_full.index_select(0, idx).contiguous()
+                sess2 = P.PnPFlowSession(eng, op_rev, y_shape, steps_pnp=T, lr_pnp=1.0, alpha=c["alpha"], num_samples=S, device=dev)
+                torch.manual_seed(77)
+                g77 = [torch.randn(full_shape, device=dev).index_select(0, idx).contiguous() for _ in range(2 * S)]
+                x2 = sess2.initial_state(y_rev)
+                it77 = iter(g77)
+                for i in range(2):
+                    x2 = sess2.step(x2, y_rev, 50 + i, it77)
+                floor = (x2.index_select(0, idx) - x1).abs().max().item()
+                rel = ((x1 - full).norm() / x1.norm()).item()
+                shard_check = {"what": "2 PnP steps, seed 77: gathered sharded result vs the same full batch run unsharded on rank 0; floor = the "
+                                       "unsharded run repeated with the images in reversed order (same arithmetic, different CTA work split)",
+                               "max_abs_diff": d, "rel_l2": rel, "reorder_floor_max_abs_diff": floor,
+                               "consistent": bool(d <= max(3.0 * floor, 1e-3)),
                                "checksum_sharded": full.double().sum().item(), "checksum_unsharded": x1.double().sum().item()}
+                del sess2
                 del sess1
             except Exception as ex:
                 shard_check = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}

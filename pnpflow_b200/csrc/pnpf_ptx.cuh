@@ -56,6 +56,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Poll with a back-off: for waits that are OFF the critical path (a producer running several slots ahead, an epilogue that idles a
+// third of the time).  Every failed try_wait + branch is four warp instructions, and the row kernel runs at 77 % of its issue
+// slots (round-2 ncu), so idle pollers take issue slots from the roles that limit the row rate.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+#ifdef PNPF_NO_POLL_SLEEP                      // A/B build switch
+    (void)ns;
+    mbar_wait(bar, parity);
+#else
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+#endif
+}
+__device__ __forceinline__ void mbar_wait_warp_sleep(uint64_t* bar, uint32_t parity, int lane, unsigned ns) {
+    if (lane == 0) mbar_wait_sleep(bar, parity, ns);
+    __syncwarp();
+}
+
 // one lane polls, the warp follows
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
     if (lane == 0) mbar_wait(bar, parity);

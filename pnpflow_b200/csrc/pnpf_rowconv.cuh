@@ -262,7 +262,11 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 row += he - hb;
                 const int j0 = max(hb - 1, 0), j1 = min(he, p.H - 1);
                 for (int j = j0; j <= j1; ++j) {
-                    PNPF_TIMED_WAIT(&empty_bar[slot], phase ^ 1, c_wait);
+                    {   // the producer runs nslot rows ahead: back off instead of spinning (see mbar_wait_sleep)
+                        const long long _t0 = PNPF_CLK();
+                        mbar_wait_sleep(&empty_bar[slot], phase ^ 1, 200);
+                        c_wait += PNPF_CLK() - _t0;
+                    }
                     ++c_rows;
                     uint8_t* sp = slots + slot * p.slot_bytes;
                     const bool centre = (j >= hb) && (j < he) && p.kchunks2;
@@ -476,7 +480,13 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // One halo tile: all of a thread's 16-byte chunks are loaded first (independent ld.shared in flight), then
                 // transformed as one straight-line block (the activation is a compile-time branch and invalid rows are computed
                 // and discarded, so the scheduler can interleave the dependent chains) and stored with a predicate.
+                // The NIT iterations cover NIT * RPI >= 130 pixel rows; only rows 128 and 129 fall into the LAST iteration, i.e. only
+                // the first warp of the transform group has valid lanes there: every other warp skips it (warp-uniform branch).
+                // Round-2 ncu: the kernel issues 3490 warp instructions per row on four schedulers in ~ 1140 clocks (77 % of the
+                // issue slots), 1500 of them here — the rows are issue-bound, so instructions are what has to go.
                 constexpr int NIT = (Cfg::HALO_ROWS + RPI - 1) / RPI;
+                static_assert((NIT - 1) * RPI < Cfg::HALO_ROWS && (NIT - 1) * RPI + NTT / CPR > Cfg::HALO_ROWS - 1, "only the last iteration is partial");
+                const bool last_it = ((tt & ~31) / CPR + (NIT - 1) * RPI) < Cfg::HALO_ROWS;       // warp-uniform
                 auto transform_tile = [&](auto silu_tag, uint32_t sbase, int c) {
                     constexpr bool kSilu = decltype(silu_tag)::value;
                     uint4 u[NIT];
@@ -487,24 +497,26 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int wpix = w0 - 1 + r;
                         ok[k] = (r < Cfg::HALO_ROWS) && (wpix >= 0) && (wpix < p.W);       // conv zero padding stays zero
                         u[k] = make_uint4(0u, 0u, 0u, 0u);
-                        if (r < Cfg::HALO_ROWS) u[k] = lds128_nc(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes);
+                        if (k < NIT - 1 || last_it)
+                            if (r < Cfg::HALO_ROWS) u[k] = lds128_nc(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes);
                     }
 #pragma unroll
                     for (int k = 0; k < NIT; ++k) {
+                        if (k == NIT - 1 && !last_it) break;
                         uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
 #pragma unroll
                         for (int e2 = 0; e2 < 4; ++e2) {
                             float y0 = fmaf(__uint_as_float(wds[e2] << 16), tsc[c][2 * e2], tsh[c][2 * e2]);
                             float y1 = fmaf(__uint_as_float(wds[e2] & 0xFFFF0000u), tsc[c][2 * e2 + 1], tsh[c][2 * e2 + 1]);
                             if constexpr (kSilu) {
-                                // fp16 tanh (3 more mantissa bits than the bf16 result: the output rounding dominates the error)
-                                const __half2 hh = __floats2half2_rn(y0, y1);
-                                uint32_t hb2 = *reinterpret_cast<const uint32_t*>(&hh), tb;
-                                asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(hb2));
-                                const __half2 th = *reinterpret_cast<const __half2*>(&tb);
-                                const float2 o = __half22float2(__hfma2(hh, th, hh));
-                                y0 = o.x;
-                                y1 = o.y;
+                                // silu(2h) = h + h tanh(h), fp32 MUFU.TANH per element.  (tanh.approx.f16x2 is split into two
+                                // MUFU.TANH.F16 by ptxas on sm_100a and needs three extra conversions: 11-12 instructions per pair
+                                // against 9 here.)
+                                float t0, t1;
+                                asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(y0));
+                                asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(y1));
+                                y0 = fmaf(y0, t0, y0);
+                                y1 = fmaf(y1, t1, y1);
                             }
                             __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
                             wds[e2] = *reinterpret_cast<uint32_t*>(&b2);
@@ -580,7 +592,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const long long pix = static_cast<long long>(r) * p.W + w0 + m;
                 {
                     const long long _t0 = PNPF_CLK();
-                    mbar_wait_warp(&tfull_bar[acc], (g / NACC) & 1, lane);
+                    mbar_wait_warp_sleep(&tfull_bar[acc], (g / NACC) & 1, lane, 32);
                     c_tfull += PNPF_CLK() - _t0;
                 }
                 ++c_rows;
