@@ -16,7 +16,8 @@
 //   tmW : packed projection weights [N = C_out][K = C]                                                          B operand, box {64, 256}
 // Shared memory (192 KB): R1 = 64 KB (Q, then P, then O: four 128 x 64 K-major SW128 tiles), R2 = 128 KB (K, then V^T, then Wo:
 // four 256 x 64 tiles).  TMEM (512 columns): S in [0, 256), O and then Y in [256, 512).
-// Warps: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax / epilogue (warp w owns TMEM lanes [32 (w & 3), +32)).
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = softmax / epilogue in two sets of four (warp w owns TMEM lanes [32 (w & 3), +32);
+// set 0 takes keys / columns [0, 128), set 1 [128, 256); the row max and row sum are exchanged through shared memory).
 // Per unit every mbarrier completes exactly once, so its wait parity is the unit counter's low bit.
 #pragma once
 #include "pnpf_gemm.cuh"
@@ -35,8 +36,9 @@ struct AttnCfg {
     static constexpr int B_TILE = 256 * 128;            // 256 rows x 64 bf16, SW128
     static constexpr int R1_BYTES = 4 * A_TILE;         // 64 KB
     static constexpr int R2_BYTES = 4 * B_TILE;         // 128 KB
-    static constexpr int SMEM_BYTES = R1_BYTES + R2_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-    static constexpr int THREADS = 6 * 32;
+    static constexpr int XCH_BYTES = 2 * 2 * 128 * 4;   // row max / row sum of the two warp sets
+    static constexpr int SMEM_BYTES = R1_BYTES + R2_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + XCH_BYTES;
+    static constexpr int THREADS = 10 * 32;
     static constexpr int TMEM_COLS = 512;
 };
 
@@ -63,6 +65,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint64_t* o_ready = bars + 6;       // epilogue warps: normalised O written
     uint64_t* y_full = bars + 7;        // MMA: Y complete (O, Wo no longer read)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    float* xch = reinterpret_cast<float*>(bars) + 64;   // [2 quantities][2 sets][128 rows] at byte offset 256
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -77,10 +80,10 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(qk_full, 1);
         mbar_init(s_full, 1);
         mbar_init(v_full, 1);
-        mbar_init(p_ready, 4);
+        mbar_init(p_ready, 8);
         mbar_init(o_full, 1);
         mbar_init(w_full, 1);
-        mbar_init(o_ready, 4);
+        mbar_init(o_ready, 8);
         mbar_init(y_full, 1);
         fence_barrier_init();
     }
@@ -153,11 +156,17 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             gemm(tmem_base + 256, y_full);                             // Y = O Wo^T  (O has been drained to shared memory)
         }
     } else {
-        // ===================== softmax / epilogue warps 2..5 =====================
+        // ===================== softmax / epilogue warps 2..9: two sets, each half of the keys / output columns =====================
+        const int set = (warp - 2) >> 2;
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;                             // query row of this thread inside the tile
+        const int cbase = set * 128;                                   // first key / column of this set
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const uint32_t r1_addr = smem_u32(r1);
+        float* xmax = xch + set * 128;                                 // [set][row]
+        float* xsum = xch + 256 + set * 128;
+        const float* omax = xch + (set ^ 1) * 128;
+        const float* osum = xch + 256 + (set ^ 1) * 128;
         uint32_t par = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x, par ^= 1) {
             const int img = u / tiles_per_img, q0 = (u - img * tiles_per_img) * 128;
@@ -166,7 +175,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tc_fence_after();
             float mx = -INFINITY;
 #pragma unroll 1
-            for (int c0 = 0; c0 < 256; c0 += 32) {
+            for (int c0 = cbase; c0 < cbase + 128; c0 += 32) {
                 uint32_t r[2][16];
                 tmem_ld_x16(t_row + c0, r[0]);
                 tmem_ld_x16(t_row + c0 + 16, r[1]);
@@ -174,10 +183,13 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(r[0][j]), __uint_as_float(r[1][j])));
             }
+            xmax[m] = mx;
+            asm volatile("bar.sync 1, 256;" ::: "memory");             // both sets: row maxima exchanged
+            mx = fmaxf(mx, omax[m]);
             const float mxl = mx * 1.4426950408889634f;                // exp(s - mx) = exp2(s * log2e - mx * log2e)
             float sum = 0.f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < 256; c0 += 32) {
+            for (int c0 = cbase; c0 < cbase + 128; c0 += 32) {
                 uint32_t r[2][16];
                 tmem_ld_x16(t_row + c0, r[0]);
                 tmem_ld_x16(t_row + c0 + 16, r[1]);
@@ -201,16 +213,18 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(tile + sw128_off(m, u0 + 1)), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
                 }
             }
-            const float inv_sum = 1.f / sum;
+            xsum[m] = sum;
             fence_proxy_async_smem();                                  // generic-proxy writes of P -> visible to the tensor core
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_ready);
+            asm volatile("bar.sync 1, 256;" ::: "memory");             // row sums exchanged (also orders the xmax reuse of the next unit)
+            const float inv_sum = 1.f / (sum + osum[m]);
             // ---- O = P V (unnormalised) -> scale rows by 1 / sum -> bf16 A operand of the projection (R1; P is consumed)
             mbar_wait_warp(o_full, par, lane);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < 256; c0 += 32) {
+            for (int c0 = cbase; c0 < cbase + 128; c0 += 32) {
                 uint32_t r[2][16];
                 tmem_ld_x16(t_row + 256 + c0, r[0]);
                 tmem_ld_x16(t_row + 256 + c0 + 16, r[1]);
@@ -239,7 +253,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tc_fence_after();
             const long long pix = q0 + m;
 #pragma unroll 1
-            for (int c0 = 0; c0 < 256; c0 += 32) epilogue_chunk32(p.epi, t_row + 256, img, pix, true, c0, lane);
+            for (int c0 = cbase; c0 < cbase + 128; c0 += 32) epilogue_chunk32(p.epi, t_row + 256, img, pix, true, c0, lane);
             tc_fence_before();                                         // ordered before this warp's next p_ready arrival, which gates the next O
         }
     }
