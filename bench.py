@@ -10,7 +10,7 @@ costs T such steps, so   images/sec = (N * B_per_gpu) / (T * seconds_per_step).
 Workload at every N: cfg4 of BASELINE.json (AFHQ-Cat 256x256x3, 4x super-resolution, T=100, S=5 MC draws, the
 reference default of config/method_config/pnp_flow.yaml), 16 images per GPU (128 over 8) -> weak scaling.
 
-engine arm:      pnpflow_b200 (hand-written sm_100a CUDA behind the C ABI), bf16 tensor-core operands / fp32 accumulate.
+engine arm:      pnpflow_b200 (hand-written sm_100a CUDA behind the C ABI), fp16 tensor-core operands (11-bit significand) / fp32 accumulate.
 torch_gpu_baseline: the reference's own GPU path like for like (oracle port, eager PyTorch + cuDNN TF32 on the same B200).
 reference arm:   the reference algorithm on the host CPU cores (oracle port; the reference itself is pure PyTorch and
                  its tree does not exist on the GPU box), rank 0 only, a bounded sample extrapolated linearly.
@@ -435,7 +435,7 @@ def main():
                 d = (x1 - full).abs().max().item()
                 # noise floor of the comparison: the SAME unsharded run with the images in reversed order.  A different batch
                 # composition changes how rows are split over CTAs, hence the grouping of the fp32 partial sums behind the
-                # GroupNorm statistics, hence an occasional bf16 rounding flip — the only way two runs of the engine differ.
+                # GroupNorm statistics, hence an occasional fp16 rounding flip — the only way two runs of the engine differ.
                 idx = torch.arange(Btot - 1, -1, -1, device=dev)
                 op_rev = sharding.shard_operator(op_full, 0, Btot, Btot)
                 if hasattr(op_rev, "_host_mask"):
@@ -560,7 +560,7 @@ def main():
             tgpu = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
             "impl": "engine", "config": cfg_desc, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": y_host.numel() * 4, "d2h_bytes_per_step": x_host.numel() * 4,
                     "ms_per_step": ms_e / K},

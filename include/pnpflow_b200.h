@@ -13,7 +13,8 @@
  *  - return value 0 = success; otherwise pnpf_last_error() (thread-local) describes the failure.
  *    There is NO CPU fallback: unsupported shapes are errors.
  *  - image tensors at the boundary are fp32 NCHW contiguous exactly like the reference's
- *    (SURVEY.md §8a); inside the engine activations are bf16 NHWC.
+ *    (SURVEY.md §8a); inside the engine activations and weights are IEEE fp16 (NHWC; 11-bit significand like
+ *    the TF32 operands of the reference's cuDNN path), accumulated in fp32.
  */
 #ifndef PNPFLOW_B200_H
 #define PNPFLOW_B200_H
@@ -58,7 +59,7 @@ int pnpf_load_weight(pnpf_engine* e, const char* name, const float* host_data, c
 int pnpf_num_weights(pnpf_engine* e);
 const char* pnpf_weight_name(pnpf_engine* e, int i);
 int pnpf_weight_shape(pnpf_engine* e, int i, int64_t shape[4], int* ndim);
-/* Repack all loaded weights to the engine layout (bf16 K-major GEMM operands, folded attention scale/bias)
+/* Repack all loaded weights to the engine layout (fp16 K-major GEMM operands, folded attention scale/bias)
  * and upload them.  Fails if any expected entry is missing.  Synchronous (allocates device memory). */
 int pnpf_finalize_weights(pnpf_engine* e);
 
@@ -72,7 +73,7 @@ int pnpf_bind_workspace(pnpf_engine* e, void* workspace, size_t bytes, int max_b
 int pnpf_unet_forward(pnpf_engine* e, const float* x, const float* t, float* v, int batch, void* stream);
 
 /* Debug/parity taps: number of ops in the plan, their names, and "run the first n_ops ops only" so that a
- * test can read an intermediate activation (bf16 NHWC) back through pnpf_debug_read_op_output. */
+ * test can read an intermediate activation (fp16 NHWC) back through pnpf_debug_read_op_output. */
 int pnpf_debug_num_ops(pnpf_engine* e);
 const char* pnpf_debug_op_name(pnpf_engine* e, int i);
 int pnpf_debug_forward_partial(pnpf_engine* e, const float* x, const float* t, int batch, int n_ops, void* stream);
@@ -155,11 +156,11 @@ int pnpf_euler_step(pnpf_engine* e, const float* x, float t0, float dt, int B, i
 /* ------------------------------------------------------------------------------------------------
  * Layer-level entry points (parity tests of the individual kernels; same kernels the plan uses)
  * ---------------------------------------------------------------------------------------------- */
-/* F.conv2d(x, w, b, stride, padding=ksize//2) on bf16 NHWC activations with the tcgen05 implicit-GEMM kernel.
- * x: device bf16 [B,Hin,Win,Cin]; host_w: HOST fp32 OIHW [Cout,Cin,k,k]; host_bias: HOST fp32 [Cout] or NULL;
- * x2/host_w2: optional fused 1x1 over a second bf16 NHWC source at output resolution (ResBlock shortcut,
- * models.py:85-92,108); residual: optional bf16 NHWC [B,Hout,Wout,Cout] added in the epilogue;
- * out: device, bf16 NHWC (out_f32=0) or fp32 NHWC (out_f32=1), [B,Hout,Wout,Cout].  Synchronous. */
+/* F.conv2d(x, w, b, stride, padding=ksize//2) on fp16 NHWC activations with the tcgen05 implicit-GEMM kernel.
+ * x: device fp16 [B,Hin,Win,Cin]; host_w: HOST fp32 OIHW [Cout,Cin,k,k]; host_bias: HOST fp32 [Cout] or NULL;
+ * x2/host_w2: optional fused 1x1 over a second fp16 NHWC source at output resolution (ResBlock shortcut,
+ * models.py:85-92,108); residual: optional fp16 NHWC [B,Hout,Wout,Cout] added in the epilogue;
+ * out: device, fp16 NHWC (out_f32=0) or fp32 NHWC (out_f32=1), [B,Hout,Wout,Cout].  Synchronous. */
 int pnpf_conv2d_nhwc(const void* x, int B, int Hin, int Win, int Cin, const float* host_w, const float* host_bias, int Cout,
                      int ksize, int stride, const void* x2, int C2, const float* host_w2, const void* residual, void* out,
                      int out_f32, void* stream);
@@ -174,16 +175,16 @@ int pnpf_gn_conv2d_nhwc(const void* xa, int Ca, const void* xb, int Cb, int B, i
  * low-resolution pixels (h-1+a+i, w-1+b+j).  Host-only (no GPU needed). */
 int pnpf_fold_subpixel_weights(const float* host_w, int Cout, int Cin, int a, int b, float* host_out);
 /* conv3x3(nearest_x2(x)) + bias computed as four sub-pixel phases on the low-resolution tensor (patch-streaming kernel,
- * opt-in in the U-Net plan with PNPF_SUBPIXEL_UP=1).  x: device bf16 [B,H,W,Cin]; out: device bf16 [B,2H,2W,Cout];
+ * the form the U-Net plan uses for the three up convs).  x: device fp16 [B,H,W,Cin]; out: device fp16 [B,2H,2W,Cout];
  * W <= 128, Cin % 64 == 0, Cout in {64,128,256}.  Synchronous. */
 int pnpf_upconv2x_nhwc(const void* x, int B, int H, int W, int Cin, const float* host_w, const float* host_bias, int Cout,
                        void* out, void* stream);
-/* out[b] = A[b] (M x K) * Bm[b]^T (N x K), bf16 row-major operands, fp32 (out_f32=1) or bf16 output. Synchronous. */
+/* out[b] = A[b] (M x K) * Bm[b]^T (N x K), fp16 row-major operands, fp32 (out_f32=1) or fp16 output. Synchronous. */
 int pnpf_gemm_nt(const void* A, const void* Bm, void* out, int batch, int M, int N, int K, int out_f32, void* stream);
 /* Fused attention core of the 16x16 attention blocks (models.py:145-162 after the q/k/v projections):
  * out = residual + softmax(q k^T) v Wo^T + bias, one kernel, logits and probabilities stay on chip (pnpf_attn.cuh).
- * qk: device bf16 [B,L,2C] (q already scaled by C^-1/2 | k); vT: device bf16 [B,C,L]; host_wo: HOST fp32 [C,C] (proj_out, OI);
- * host_bias: HOST fp32 [C] or NULL; residual: device bf16 [B,L,C] or NULL; out: device bf16 [B,L,C].  L = C = 256.  Synchronous. */
+ * qk: device fp16 [B,L,2C] (q already scaled by C^-1/2 | k); vT: device fp16 [B,C,L]; host_wo: HOST fp32 [C,C] (proj_out, OI);
+ * host_bias: HOST fp32 [C] or NULL; residual: device fp16 [B,L,C] or NULL; out: device fp16 [B,L,C].  L = C = 256.  Synchronous. */
 int pnpf_attn_core_nhwc(const void* qk, const void* vT, const float* host_wo, const float* host_bias, const void* residual, void* out,
                         int B, int L, int C, void* stream);
 

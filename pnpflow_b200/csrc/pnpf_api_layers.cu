@@ -29,26 +29,26 @@ extern "C" int pnpf_conv2d_nhwc(const void* x, int B, int Hin, int Win, int Cin,
     const int Hout = (Hin + 2 * (ksize / 2) - ksize) / stride + 1;
     const int Wout = (Win + 2 * (ksize / 2) - ksize) / stride + 1;
     const long long Ktot = (long long)ksize * ksize * Cin + (x2 ? C2 : 0);
-    std::vector<bf16> wp((size_t)N_pad * Ktot);
+    std::vector<act16> wp((size_t)N_pad * Ktot);
     pack_conv_weight(wp.data(), host_w, Cout, Cin, ksize, N_pad, Cin, x2 ? host_w2 : nullptr, x2 ? C2 : 0, 1.0f);
     std::vector<float> bp(N_pad, 0.f);
     if (host_bias)
         for (int i = 0; i < Cout; ++i) bp[i] = host_bias[i];
-    bf16* dw = nullptr;
+    act16* dw = nullptr;
     float* db = nullptr;
-    PNPF_CHECK_CUDA(cudaMalloc(&dw, wp.size() * sizeof(bf16)));
+    PNPF_CHECK_CUDA(cudaMalloc(&dw, wp.size() * sizeof(act16)));
     PNPF_CHECK_CUDA(cudaMalloc(&db, bp.size() * sizeof(float)));
-    PNPF_CHECK_CUDA(cudaMemcpyAsync(dw, wp.data(), wp.size() * sizeof(bf16), cudaMemcpyHostToDevice, s));
+    PNPF_CHECK_CUDA(cudaMemcpyAsync(dw, wp.data(), wp.size() * sizeof(act16), cudaMemcpyHostToDevice, s));
     PNPF_CHECK_CUDA(cudaMemcpyAsync(db, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice, s));
     ConvDesc d;
-    d.x = static_cast<const bf16*>(x);
+    d.x = static_cast<const act16*>(x);
     d.B = B; d.Hin = Hin; d.Win = Win; d.Cin = Cin; d.x_pitch = Cin;
-    d.x2 = static_cast<const bf16*>(x2); d.C2 = C2; d.x2_pitch = C2;
+    d.x2 = static_cast<const act16*>(x2); d.C2 = C2; d.x2_pitch = C2;
     d.w = dw; d.N_pad = N_pad; d.ksize = ksize; d.stride = stride; d.Hout = Hout; d.Wout = Wout;
     d.out = out; d.out_mode = out_f32 ? 1 : 0;
     d.out_img_stride = (long long)Hout * Wout * Cout; d.out_row_stride = Cout; d.n_valid = Cout;
     d.bias = db;
-    d.residual = static_cast<const bf16*>(residual);
+    d.residual = static_cast<const act16*>(residual);
     d.res_img_stride = (long long)Hout * Wout * Cout; d.res_row_stride = Cout;
     TcOp op;
     int rc = prepare_conv(op, d);
@@ -101,22 +101,22 @@ extern "C" int pnpf_upconv2x_nhwc(const void* x, int B, int H, int W, int Cin, c
     if (host_bias)
         for (int i = 0; i < Cout; ++i) bp[i] = host_bias[i];
     const size_t wn = (size_t)N_pad * 4 * Cin;
-    std::vector<bf16> wp(4 * wn);
+    std::vector<act16> wp(4 * wn);
     std::vector<float> f((size_t)Cout * Cin * 4);
     for (int ph = 0; ph < 4; ++ph) {
         fold_subpixel_weights(host_w, Cout, Cin, ph >> 1, ph & 1, f.data());
         pack_conv_weight(wp.data() + ph * wn, f.data(), Cout, Cin, 2, N_pad, Cin, nullptr, 0, 1.0f);
     }
-    bf16* dw = nullptr;
+    act16* dw = nullptr;
     float* db = nullptr;
-    PNPF_CHECK_CUDA(cudaMalloc(&dw, wp.size() * sizeof(bf16)));
+    PNPF_CHECK_CUDA(cudaMalloc(&dw, wp.size() * sizeof(act16)));
     PNPF_CHECK_CUDA(cudaMalloc(&db, bp.size() * sizeof(float)));
-    PNPF_CHECK_CUDA(cudaMemcpyAsync(dw, wp.data(), wp.size() * sizeof(bf16), cudaMemcpyHostToDevice, s));
+    PNPF_CHECK_CUDA(cudaMemcpyAsync(dw, wp.data(), wp.size() * sizeof(act16), cudaMemcpyHostToDevice, s));
     PNPF_CHECK_CUDA(cudaMemcpyAsync(db, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice, s));
     int rc = 0;
     for (int ph = 0; ph < 4 && !rc; ++ph) {
         ConvDesc d;
-        d.x = static_cast<const bf16*>(x);
+        d.x = static_cast<const act16*>(x);
         d.B = B; d.Hin = d.Hout = H; d.Win = d.Wout = W; d.Cin = Cin; d.x_pitch = Cin;
         d.w = dw + ph * wn; d.N_pad = N_pad; d.ksize = 3; d.stride = 1;
         d.subpix = 1; d.sp_a = ph >> 1; d.sp_b = ph & 1;
@@ -143,8 +143,8 @@ extern "C" int pnpf_upconv2x_nhwc(const void* x, int B, int H, int W, int Cin, c
 extern "C" int pnpf_gemm_nt(const void* A, const void* Bm, void* out, int batch, int M, int N, int K, int out_f32, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     GemmDesc d;
-    d.A = static_cast<const bf16*>(A); d.lda = K; d.a_bstride = (long long)M * K; d.a_batched = 1;
-    d.Bm = static_cast<const bf16*>(Bm); d.ldb = K; d.b_bstride = (long long)N * K; d.b_batched = 1;
+    d.A = static_cast<const act16*>(A); d.lda = K; d.a_bstride = (long long)M * K; d.a_batched = 1;
+    d.Bm = static_cast<const act16*>(Bm); d.ldb = K; d.b_bstride = (long long)N * K; d.b_batched = 1;
     d.batch = batch; d.M = M; d.N = N; d.K = K;
     d.out = out; d.out_mode = out_f32 ? 1 : 0; d.out_img_stride = (long long)M * N; d.out_row_stride = N;
     TcOp op;
@@ -165,31 +165,31 @@ extern "C" int pnpf_gn_conv2d_nhwc(const void* xa, int Ca, const void* xb, int C
     const int Cin = Ca + Cb;
     const int N_pad = round_up_n(Cout);
     const long long Ktot = 9LL * Cin;
-    std::vector<bf16> wp((size_t)N_pad * Ktot);
+    std::vector<act16> wp((size_t)N_pad * Ktot);
     pack_conv_weight(wp.data(), host_w, Cout, Cin, 3, N_pad, Cin, nullptr, 0, 1.0f);
     std::vector<float> bp(N_pad, 0.f);
     if (host_bias)
         for (int i = 0; i < Cout; ++i) bp[i] = host_bias[i];
-    bf16* dw = nullptr;
+    act16* dw = nullptr;
     float *db = nullptr, *dg = nullptr, *dbeta = nullptr;
     double *sta = nullptr, *stb = nullptr;
-    PNPF_CHECK_CUDA(cudaMalloc(&dw, wp.size() * sizeof(bf16)));
+    PNPF_CHECK_CUDA(cudaMalloc(&dw, wp.size() * sizeof(act16)));
     PNPF_CHECK_CUDA(cudaMalloc(&db, bp.size() * sizeof(float)));
     PNPF_CHECK_CUDA(cudaMalloc(&dg, Cin * sizeof(float)));
     PNPF_CHECK_CUDA(cudaMalloc(&dbeta, Cin * sizeof(float)));
     PNPF_CHECK_CUDA(cudaMalloc(&sta, (size_t)B * Ca * 2 * sizeof(double)));
     PNPF_CHECK_CUDA(cudaMalloc(&stb, (size_t)B * (Cb ? Cb : 1) * 2 * sizeof(double)));
-    PNPF_CHECK_CUDA(cudaMemcpyAsync(dw, wp.data(), wp.size() * sizeof(bf16), cudaMemcpyHostToDevice, s));
+    PNPF_CHECK_CUDA(cudaMemcpyAsync(dw, wp.data(), wp.size() * sizeof(act16), cudaMemcpyHostToDevice, s));
     PNPF_CHECK_CUDA(cudaMemcpyAsync(db, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice, s));
     PNPF_CHECK_CUDA(cudaMemcpyAsync(dg, host_gamma, Cin * sizeof(float), cudaMemcpyHostToDevice, s));
     PNPF_CHECK_CUDA(cudaMemcpyAsync(dbeta, host_beta, Cin * sizeof(float), cudaMemcpyHostToDevice, s));
     PNPF_CHECK_CUDA(cudaMemsetAsync(sta, 0, (size_t)B * Ca * 2 * sizeof(double), s));
     PNPF_CHECK_CUDA(cudaMemsetAsync(stb, 0, (size_t)B * (Cb ? Cb : 1) * 2 * sizeof(double), s));
-    int rc = launch_gn_stats(GnSrc{static_cast<const bf16*>(xa), Ca, Ca, nullptr, 0, 0, nullptr, nullptr}, B, H * W, sta, s);
-    if (!rc && Cb) rc = launch_gn_stats(GnSrc{static_cast<const bf16*>(xb), Cb, Cb, nullptr, 0, 0, nullptr, nullptr}, B, H * W, stb, s);
+    int rc = launch_gn_stats(GnSrc{static_cast<const act16*>(xa), Ca, Ca, nullptr, 0, 0, nullptr, nullptr}, B, H * W, sta, s);
+    if (!rc && Cb) rc = launch_gn_stats(GnSrc{static_cast<const act16*>(xb), Cb, Cb, nullptr, 0, 0, nullptr, nullptr}, B, H * W, stb, s);
     ConvDesc d;
-    d.x = static_cast<const bf16*>(xa); d.x_pitch = Ca; d.Cin = Cin;
-    d.xb = static_cast<const bf16*>(xb); d.Cb = Cb; d.xb_pitch = Cb;
+    d.x = static_cast<const act16*>(xa); d.x_pitch = Ca; d.Cin = Cin;
+    d.xb = static_cast<const act16*>(xb); d.Cb = Cb; d.xb_pitch = Cb;
     d.B = B; d.Hin = d.Hout = H; d.Win = d.Wout = W;
     d.w = dw; d.N_pad = N_pad; d.ksize = 3; d.stride = 1;
     d.out = out; d.out_mode = out_f32 ? 1 : 0;
@@ -223,27 +223,27 @@ extern "C" int pnpf_gn_conv2d_nhwc(const void* xa, int Ca, const void* xb, int C
     return 0;
 }
 
-// Fused attention core on device tensors (parity test of pnpf_attn.cuh): qk bf16 [B][L][2C] (q scaled | k), vT bf16 [B][C][L],
-// host_wo fp32 [C][C] (proj_out weight, OI), host_bias fp32 [C] or NULL, residual bf16 [B][L][C] or NULL -> out bf16 [B][L][C].
+// Fused attention core on device tensors (parity test of pnpf_attn.cuh): qk fp16 [B][L][2C] (q scaled | k), vT fp16 [B][C][L],
+// host_wo fp32 [C][C] (proj_out weight, OI), host_bias fp32 [C] or NULL, residual fp16 [B][L][C] or NULL -> out fp16 [B][L][C].
 extern "C" int pnpf_attn_core_nhwc(const void* qk, const void* vT, const float* host_wo, const float* host_bias, const void* residual, void* out,
                                    int B, int L, int C, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     PNPF_REQUIRE(qk && vT && host_wo && out, "null pointer");
     PNPF_REQUIRE(attn_core_eligible(L, C), "fused attention core handles L = 256 tokens, C = 256 channels (got %d, %d)", L, C);
-    std::vector<bf16> wp((size_t)C * C);
+    std::vector<act16> wp((size_t)C * C);
     pack_conv_weight(wp.data(), host_wo, C, C, 1, C, C, nullptr, 0, 1.0f);
     std::vector<float> bp(C, 0.f);
     if (host_bias)
         for (int i = 0; i < C; ++i) bp[i] = host_bias[i];
-    bf16* dw = nullptr;
+    act16* dw = nullptr;
     float* db = nullptr;
-    PNPF_CHECK_CUDA(cudaMalloc(&dw, wp.size() * sizeof(bf16)));
+    PNPF_CHECK_CUDA(cudaMalloc(&dw, wp.size() * sizeof(act16)));
     PNPF_CHECK_CUDA(cudaMalloc(&db, bp.size() * sizeof(float)));
-    PNPF_CHECK_CUDA(cudaMemcpyAsync(dw, wp.data(), wp.size() * sizeof(bf16), cudaMemcpyHostToDevice, s));
+    PNPF_CHECK_CUDA(cudaMemcpyAsync(dw, wp.data(), wp.size() * sizeof(act16), cudaMemcpyHostToDevice, s));
     PNPF_CHECK_CUDA(cudaMemcpyAsync(db, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice, s));
     AttnDesc d;
-    d.qk = static_cast<const bf16*>(qk); d.vT = static_cast<const bf16*>(vT); d.w = dw; d.bias = db;
-    d.residual = static_cast<const bf16*>(residual); d.out = static_cast<bf16*>(out); d.B = B; d.L = L; d.C = C;
+    d.qk = static_cast<const act16*>(qk); d.vT = static_cast<const act16*>(vT); d.w = dw; d.bias = db;
+    d.residual = static_cast<const act16*>(residual); d.out = static_cast<act16*>(out); d.B = B; d.L = L; d.C = C;
     AttnOp op;
     int rc = prepare_attn(op, d);
     if (!rc) rc = launch_attn(op, B, s);

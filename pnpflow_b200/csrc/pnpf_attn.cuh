@@ -4,12 +4,12 @@
 //
 // one CTA per (image, 128-query tile), everything between the q/k/v projections and the block output on chip:
 // S lives in TMEM (128 lanes x 256 fp32 columns), the softmax runs in registers (one thread = one query row), P goes to shared
-// memory as the bf16 A operand of the second GEMM, O comes back through TMEM, is normalised by the row sums, goes to shared
+// memory as the fp16 A operand of the second GEMM, O comes back through TMEM, is normalised by the row sums, goes to shared
 // memory as the A operand of the output projection, and the projection's epilogue adds bias + residual, accumulates the
-// GroupNorm statistics of the block output and stores bf16 NHWC.  The fp32 logits (256 KB per image) and the bf16 probabilities
+// GroupNorm statistics of the block output and stores fp16 NHWC.  The fp32 logits (256 KB per image) and the fp16 probabilities
 // never touch HBM; five launches (qk^T, softmax, pv, proj + the S/P round trips) become one.
 //
-// Operands (all bf16, produced by the existing kernels of the plan):
+// Operands (all fp16, produced by the existing kernels of the plan):
 //   tmQ : [img][L][2C] "qk" tensor of the fused q|k projection, channels [0, C) (q already carries C^-1/2)   A operand, box {64, 128}
 //   tmK : same tensor, channels [C, 2C): k as [N = L keys][K = C]                                             B operand, box {64, 256}
 //   tmV : V^T [img][C][L] (the vT GEMM of the plan): [N = C][K = L keys]                                        B operand, box {64, 256}
@@ -27,13 +27,13 @@ namespace pnpf {
 struct AttnParams {
     int n_img;
     int L, C;              // must be 256, 256 (checked by the host)
-    EpiParams epi;         // bias (folded Wo bv + bo), residual x, output y (bf16 NHWC = [img][token][C]), statistics
+    EpiParams epi;         // bias (folded Wo bv + bo), residual x, output y (fp16 NHWC = [img][token][C]), statistics
 };
 
 struct AttnCfg {
     static constexpr int L = 256, C = 256;
-    static constexpr int A_TILE = 128 * 128;            // 128 rows x 64 bf16, SW128
-    static constexpr int B_TILE = 256 * 128;            // 256 rows x 64 bf16, SW128
+    static constexpr int A_TILE = 128 * 128;            // 128 rows x 64 fp16, SW128
+    static constexpr int B_TILE = 256 * 128;            // 256 rows x 64 fp16, SW128
     static constexpr int R1_BYTES = 4 * A_TILE;         // 64 KB
     static constexpr int R2_BYTES = 4 * B_TILE;         // 128 KB
     static constexpr int XCH_BYTES = 2 * 2 * 128 * 4;   // row max / row sum of the two warp sets
@@ -126,7 +126,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer: three 128 x 256 x 256 GEMMs per unit =====================
-        constexpr uint32_t idesc = make_idesc_bf16(128, 256);
+        constexpr uint32_t idesc = make_idesc_act16(128, 256);
         const uint32_t a_base = smem_u32(r1), b_base = smem_u32(r2);
         uint32_t par = 0;
         auto gemm = [&](uint32_t d_tmem, uint64_t* done_bar) {     // MMAs and their commit by the SAME elected thread
@@ -136,7 +136,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     const uint64_t adesc = make_smem_desc<128>(a_base + c * Cfg::A_TILE);
                     const uint64_t bdesc = make_smem_desc<128>(b_base + c * Cfg::B_TILE);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | kk) ? 1u : 0u);
+                    for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | kk) ? 1u : 0u);
                 }
                 umma_commit(done_bar);
             }
@@ -170,7 +170,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t par = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x, par ^= 1) {
             const int img = u / tiles_per_img, q0 = (u - img * tiles_per_img) * 128;
-            // ---- row softmax of S (fp32 in TMEM): max, then p = exp(s - max) rounded to bf16, row sum of the ROUNDED values
+            // ---- row softmax of S (fp32 in TMEM): max, then p = exp(s - max) rounded to fp16, row sum of the ROUNDED values
             mbar_wait_warp(s_full, par, lane);
             tc_fence_after();
             float mx = -INFINITY;
@@ -201,9 +201,9 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     for (int j = 0; j < 8; ++j) {
                         const float e0 = exp2f(fmaf(__uint_as_float(r[h][2 * j]), 1.4426950408889634f, -mxl));
                         const float e1 = exp2f(fmaf(__uint_as_float(r[h][2 * j + 1]), 1.4426950408889634f, -mxl));
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(e0, e1);
-                        pk[j] = *reinterpret_cast<uint32_t*>(&b2);
-                        sum += __uint_as_float(pk[j] << 16) + __uint_as_float(pk[j] & 0xFFFF0000u);
+                        pk[j] = pack2(e0, e1);
+                        const float2 pr = unpack2(pk[j]);
+                        sum += pr.x + pr.y;
                     }
                     // keys [c0 + 16 h, + 16) -> key chunk (c0 + 16 h) / 64, 16-byte units 2 ((c0 + 16 h) % 64) / 16 and + 1
                     const int key0 = c0 + 16 * h;
@@ -220,7 +220,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             if (lane == 0) mbar_arrive(p_ready);
             asm volatile("bar.sync 1, 256;" ::: "memory");             // row sums exchanged (also orders the xmax reuse of the next unit)
             const float inv_sum = 1.f / (sum + osum[m]);
-            // ---- O = P V (unnormalised) -> scale rows by 1 / sum -> bf16 A operand of the projection (R1; P is consumed)
+            // ---- O = P V (unnormalised) -> scale rows by 1 / sum -> fp16 A operand of the projection (R1; P is consumed)
             mbar_wait_warp(o_full, par, lane);
             tc_fence_after();
 #pragma unroll 1
@@ -234,8 +234,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(r[h][2 * j]) * inv_sum, __uint_as_float(r[h][2 * j + 1]) * inv_sum);
-                        pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+                        pk[j] = pack2(__uint_as_float(r[h][2 * j]) * inv_sum, __uint_as_float(r[h][2 * j + 1]) * inv_sum);
                     }
                     const int ch0 = c0 + 16 * h;
                     const uint32_t tile = r1_addr + (ch0 >> 6) * Cfg::A_TILE;
@@ -248,7 +247,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tc_fence_before();                                         // O has been read: the projection may overwrite its TMEM columns
             __syncwarp();
             if (lane == 0) mbar_arrive(o_ready);
-            // ---- y = x + O Wo^T + bias: bias / residual / GroupNorm statistics / bf16 NHWC store (shared epilogue)
+            // ---- y = x + O Wo^T + bias: bias / residual / GroupNorm statistics / fp16 NHWC store (shared epilogue)
             mbar_wait_warp(y_full, par, lane);
             tc_fence_after();
             const long long pix = q0 + m;

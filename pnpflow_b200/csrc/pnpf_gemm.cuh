@@ -2,12 +2,12 @@
 //
 //   D[128 pixels x BN] (+)= sum_{tap, cin-chunk} A_tap[128 x BK] * W[BN x BK]^T
 //
-// * A (activations) lives in HBM as NHWC bf16 and is fetched with a 4-D TILED tensor map (C, W, H, B) whose box is
+// * A (activations) lives in HBM as NHWC fp16 and is fetched with a 4-D TILED tensor map (C, W, H, B) whose box is
 //   {BK channels, TW, TH, 1}: one TMA per (tap, channel chunk) with the start coordinate shifted by (dw, dh).
 //   Out-of-bounds coordinates (including negative ones) are zero-filled by the TMA unit, which IS the conv's
 //   zero padding; the box lands in shared memory as 128 rows of BK*2 bytes with the hardware 128B/64B swizzle,
 //   i.e. exactly the canonical K-major UMMA operand layout.  Stride-2 convs use elementStrides = 2 in W and H.
-// * W (weights) is a [N_total, K_total] K-major bf16 matrix (K ordered tap-major then channel) fetched with a 3-D map.
+// * W (weights) is a [N_total, K_total] K-major fp16 matrix (K ordered tap-major then channel) fetched with a 3-D map.
 // * One elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM accumulator; 4 epilogue
 //   warps drain it with tcgen05.ld while the next tile's main loop runs (persistent CTAs, static tile striding).
 // * The same kernel runs the attention GEMMs (H=1, W=M rows, per-image B operand) and the fused 1x1 shortcut
@@ -20,13 +20,13 @@ namespace pnpf {
 // Epilogue description shared by the tensor-core kernels (bias / time-embedding / residual / store mode).
 struct EpiParams {
     void* out;
-    int out_mode;          // 0: bf16 [img][pix][col]   1: f32 [img][pix][col]   2: f32 [img][col][pix] (NCHW)
+    int out_mode;          // 0: fp16 [img][pix][col]   1: f32 [img][pix][col]   2: f32 [img][col][pix] (NCHW)
     long long out_img_stride, out_row_stride, out_col_stride;   // elements
     int n_valid;           // columns >= n_valid are not stored
     const float* bias;     // [N_total] or nullptr
     const float* bias_img; // [img][bias_img_stride] + col, or nullptr   (time-embedding projection)
     long long bias_img_stride;
-    const __nv_bfloat16* residual;   // [img][pix][col] bf16 or nullptr
+    const act16* residual;   // [img][pix][col] fp16 or nullptr
     long long res_img_stride, res_row_stride;
     double* stats;         // optional GroupNorm statistics of the OUTPUT: [img][n_valid][2] (sum, sumsq), fp64 atomics
 };
@@ -56,21 +56,19 @@ __device__ __forceinline__ void epilogue_apply16(const EpiParams& p, int img, lo
             const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                v[q * 8 + 2 * j] += __uint_as_float(uu[j] << 16);
-                v[q * 8 + 2 * j + 1] += __uint_as_float(uu[j] & 0xFFFF0000u);
+                const float2 t = unpack2(uu[j]);
+                v[q * 8 + 2 * j] += t.x;
+                v[q * 8 + 2 * j + 1] += t.y;
             }
         }
     }
 }
 __device__ __forceinline__ void epilogue_store16(const EpiParams& p, int img, long long pix, int col0, const float (&v)[16]) {
     if (p.out_mode == 0) {
-        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + img * p.out_img_stride + pix * p.out_row_stride + col0;
+        act16* op = reinterpret_cast<act16*>(p.out) + img * p.out_img_stride + pix * p.out_row_stride + col0;
         uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            pk[j] = *reinterpret_cast<uint32_t*>(&b2);
-        }
+        for (int j = 0; j < 8; ++j) pk[j] = pack2(v[2 * j], v[2 * j + 1]);
         uint4* o4 = reinterpret_cast<uint4*>(op);
         o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -178,8 +176,9 @@ __device__ __forceinline__ void epilogue_chunk32(const EpiParams& p, uint32_t t_
             const uint32_t uu[4] = {rs[h][q].x, rs[h][q].y, rs[h][q].z, rs[h][q].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                v[h][q * 8 + 2 * j] += __uint_as_float(uu[j] << 16);
-                v[h][q * 8 + 2 * j + 1] += __uint_as_float(uu[j] & 0xFFFF0000u);
+                const float2 t = unpack2(uu[j]);
+                v[h][q * 8 + 2 * j] += t.x;
+                v[h][q * 8 + 2 * j + 1] += t.y;
             }
         }
     }
@@ -364,7 +363,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ===================== MMA issuer: converged warp, one ELECTED lane issues (pair: the leader CTA only) =====================
         if (!PAIR || rank == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, BN);
+            constexpr uint32_t idesc = make_idesc_act16(PAIR ? 256 : 128, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -385,8 +384,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int kk = 0; kk < BK / 16; ++kk) {
                             // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr>>4) field
-                            if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) ? 1u : 0u);
-                            else umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) ? 1u : 0u);
+                            if constexpr (PAIR) umma_f16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) ? 1u : 0u);
+                            else umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) ? 1u : 0u);
                         }
                         if constexpr (PAIR) {
                             umma_commit_pair(&empty_bar[stage]);  // frees this stage in BOTH CTAs

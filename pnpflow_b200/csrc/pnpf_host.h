@@ -49,11 +49,11 @@ private:
 };
 
 // ---- tensor maps ----
-// Activation map: bf16 NHWC buffer viewed as 4-D (C, W, H, B); `pitch` = channel pitch of the buffer in elements
+// Activation map: fp16 NHWC buffer viewed as 4-D (C, W, H, B); `pitch` = channel pitch of the buffer in elements
 // (>= C when the view is a channel slice).  box = {bk, tw, th, 1}; `estride` = traversal stride in W and H (1 or 2).
 int make_act_tmap(CUtensorMap* m, const void* base, int C, long long pitch, int W, int H, int B, int bk, int tw, int th,
                   int estride);
-// Weight / B-operand map: bf16 [batch][N][K] K-major viewed as 3-D (K, N, batch); row pitch `ldk` elements,
+// Weight / B-operand map: fp16 [batch][N][K] K-major viewed as 3-D (K, N, batch); row pitch `ldk` elements,
 // batch stride `bstride` elements (ignored when batch == 1).  box = {bk, bn, 1}.
 int make_b_tmap(CUtensorMap* m, const void* base, long long K, long long ldk, int N, int batch, long long bstride, int bk,
                 int bn);

@@ -12,20 +12,18 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        f[2 * j] = __uint_as_float(w[j] << 16);
-        f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+        const float2 t = unpack2(w[j]);
+        f[2 * j] = t.x;
+        f[2 * j + 1] = t.y;
     }
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-        w[j] = *reinterpret_cast<uint32_t*>(&b);
-    }
+    for (int j = 0; j < 4; ++j) w[j] = pack2(f[2 * j], f[2 * j + 1]);
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
-__device__ __forceinline__ const bf16* src_ptr(const GnSrc& s, int img, long long pix, int HW, int c0) {
+__device__ __forceinline__ const act16* src_ptr(const GnSrc& s, int img, long long pix, int HW, int c0) {
     if (c0 < s.C1) return s.p1 + ((long long)img * HW + pix) * s.pitch1 + c0;
     return s.p2 + ((long long)img * HW + pix) * s.pitch2 + (c0 - s.C1);
 }
@@ -102,7 +100,7 @@ int launch_gn_stats(const GnSrc& s, int B, int HW, double* stats, cudaStream_t s
 }
 
 // =================================================================================================
-// GroupNorm apply (+ SiLU) -> bf16 NHWC conv operand; optional raw concat copy
+// GroupNorm apply (+ SiLU) -> fp16 NHWC conv operand; optional raw concat copy
 // =================================================================================================
 // Prologue: one thread per GROUP reduces the fp64 channel statistics (a group may straddle the two concatenated
 // sources) to mean / rstd, then one thread per channel derives scale / shift in fp32.  Main loop: a thread owns one
@@ -124,8 +122,8 @@ __device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {  // write
 template <int U, bool STREAM>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(GnSrc s, int HW, int pix_per_block, const float* __restrict__ gamma,
-                const float* __restrict__ beta, float eps, int gs, int silu, bf16* __restrict__ dst,
-                bf16* __restrict__ raw_dst) {
+                const float* __restrict__ beta, float eps, int gs, int silu, act16* __restrict__ dst,
+                act16* __restrict__ raw_dst) {
     extern __shared__ float ss[];                     // scale[C] | shift[C] | mean[G] | rstd[G]
     const int C = s.C1 + s.C2;
     const int G = C / gs;
@@ -197,7 +195,7 @@ gn_apply_kernel(GnSrc s, int HW, int pix_per_block, const float* __restrict__ ga
 }
 
 int launch_gn_apply(const GnSrc& s, int B, int HW, const float* gamma, const float* beta, float eps,
-                    int groups, int silu, bf16* dst, bf16* raw_dst, cudaStream_t st) {
+                    int groups, int silu, act16* dst, act16* raw_dst, cudaStream_t st) {
     const int C = s.C1 + s.C2;
     PNPF_REQUIRE(C % groups == 0 && C % 8 == 0 && s.C1 % 8 == 0, "GroupNorm channels (%d+%d) unsupported", s.C1, s.C2);
     const int threads = gn_threads(C);
@@ -212,9 +210,9 @@ int launch_gn_apply(const GnSrc& s, int B, int HW, const float* gamma, const flo
 }
 
 // =================================================================================================
-// row softmax: one warp per row, fp32 in, bf16 out
+// row softmax: one warp per row, fp32 in, fp16 out
 // =================================================================================================
-__global__ void softmax_rows_kernel(const float* __restrict__ S, bf16* __restrict__ P, long long rows, int L) {
+__global__ void softmax_rows_kernel(const float* __restrict__ S, act16* __restrict__ P, long long rows, int L) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -234,19 +232,19 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, bf16* __restric
 #pragma unroll
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float inv = 1.f / sum;
-    bf16* p = P + row * L;
+    act16* p = P + row * L;
     for (int i = lane * 4; i < L; i += 128) {
         const float4 v = *reinterpret_cast<const float4*>(s + i);
-        __nv_bfloat162 a = __floats2bfloat162_rn(__expf(v.x - m) * inv, __expf(v.y - m) * inv);
-        __nv_bfloat162 b = __floats2bfloat162_rn(__expf(v.z - m) * inv, __expf(v.w - m) * inv);
+        const uint32_t a = pack2(__expf(v.x - m) * inv, __expf(v.y - m) * inv);
+        const uint32_t b = pack2(__expf(v.z - m) * inv, __expf(v.w - m) * inv);
         uint2 o2;
-        o2.x = *reinterpret_cast<uint32_t*>(&a);
-        o2.y = *reinterpret_cast<uint32_t*>(&b);
+        o2.x = a;
+        o2.y = b;
         *reinterpret_cast<uint2*>(p + i) = o2;
     }
 }
 
-int launch_softmax_rows(const float* S, bf16* P, long long rows, int L, cudaStream_t st) {
+int launch_softmax_rows(const float* S, act16* P, long long rows, int L, cudaStream_t st) {
     PNPF_REQUIRE(L % 4 == 0, "softmax length %d must be a multiple of 4", L);
     const int wpb = 8;
     softmax_rows_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(S, P, rows, L);
@@ -305,12 +303,12 @@ int launch_temb(const TembWeights& w, const float* t, int B, float* out, cudaStr
 // =================================================================================================
 // layout shims
 // =================================================================================================
-__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, int C, int HW, bf16* __restrict__ dst, int Cpad,
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, int C, int HW, act16* __restrict__ dst, int Cpad,
                                         long long total_pix) {
     const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gp >= total_pix) return;
     const long long img = gp / HW, p = gp - img * HW;
-    bf16* o = dst + gp * Cpad;
+    act16* o = dst + gp * Cpad;
     for (int c0 = 0; c0 < Cpad; c0 += 8) {
         float f[8];
 #pragma unroll
@@ -318,23 +316,23 @@ __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, int C, int 
         *reinterpret_cast<uint4*>(o + c0) = pack8(f);
     }
 }
-int launch_nchw_to_nhwc_pad(const float* x, int B, int C, int HW, bf16* dst, int Cpad, cudaStream_t st) {
+int launch_nchw_to_nhwc_pad(const float* x, int B, int C, int HW, act16* dst, int Cpad, cudaStream_t st) {
     const long long n = (long long)B * HW;
     nchw_to_nhwc_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, C, HW, dst, Cpad, n);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-__global__ void nhwc_to_nchw_f32_kernel(const bf16* __restrict__ src, long long pitch, int C, int HW, float* __restrict__ dst,
+__global__ void nhwc_to_nchw_f32_kernel(const act16* __restrict__ src, long long pitch, int C, int HW, float* __restrict__ dst,
                                         long long total) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over [B][C][HW]
     if (i >= total) return;
     const long long p = i % HW;
     const long long bc = i / HW;
     const long long c = bc % C, b = bc / C;
-    dst[i] = __bfloat162float(src[(b * HW + p) * pitch + c]);
+    dst[i] = act16_to_float(src[(b * HW + p) * pitch + c]);
 }
-int launch_nhwc_to_nchw_f32(const bf16* src, long long pitch, int B, int C, int HW, float* dst, cudaStream_t st) {
+int launch_nhwc_to_nchw_f32(const act16* src, long long pitch, int B, int C, int HW, float* dst, cudaStream_t st) {
     const long long n = (long long)B * C * HW;
     nhwc_to_nchw_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, pitch, C, HW, dst, n);
     PNPF_CHECK_CUDA(cudaGetLastError());
@@ -352,7 +350,7 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ src, int H, int W, i
     const long long b = r / (2 * H);
     dst[i] = __ldg(src + ((b * H + (oh >> 1)) * W + (ow >> 1)) * Cv + cv);
 }
-int launch_upsample2x(const bf16* src, int B, int H, int W, int C, bf16* dst, cudaStream_t st) {
+int launch_upsample2x(const act16* src, int B, int H, int W, int C, act16* dst, cudaStream_t st) {
     PNPF_REQUIRE(C % 8 == 0, "upsample channels %d", C);
     const long long n = (long long)B * 4 * H * W * (C / 8);
     upsample2x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src), H, W, C / 8,

@@ -6,12 +6,11 @@
 
 namespace pnpf {
 
-typedef __nv_bfloat16 bf16;
 
-// ---- GroupNorm over a (virtual) channel concat of up to two bf16 NHWC sources ----------------------------
+// ---- GroupNorm over a (virtual) channel concat of up to two fp16 NHWC sources ----------------------------
 struct GnSrc {
-    const bf16* p1; int C1; long long pitch1;
-    const bf16* p2; int C2; long long pitch2;     // p2 == nullptr -> single source
+    const act16* p1; int C1; long long pitch1;
+    const act16* p2; int C2; long long pitch2;     // p2 == nullptr -> single source
     const double* st1; const double* st2;         // per-source statistics [img][C_src][2] (sum, sumsq), written by the
                                                   // producing conv's epilogue (or by launch_gn_stats)
 };
@@ -19,10 +18,10 @@ struct GnSrc {
 int launch_gn_stats(const GnSrc& s, int B, int HW, double* stats, cudaStream_t st);
 // dst[img][pix][C] = act((x-mean_g)*rstd_g*gamma+beta); raw_dst (optional) receives the un-normalised concat
 int launch_gn_apply(const GnSrc& s, int B, int HW, const float* gamma, const float* beta, float eps,
-                    int groups, int silu, bf16* dst, bf16* raw_dst, cudaStream_t st);
+                    int groups, int silu, act16* dst, act16* raw_dst, cudaStream_t st);
 
-// ---- softmax over the last dim: S fp32 [rows][L] -> P bf16 [rows][L] --------------------------------------
-int launch_softmax_rows(const float* S, bf16* P, long long rows, int L, cudaStream_t st);
+// ---- softmax over the last dim: S fp32 [rows][L] -> P fp16 [rows][L] --------------------------------------
+int launch_softmax_rows(const float* S, act16* P, long long rows, int L, cudaStream_t st);
 
 // ---- time embedding (models.py:253-299 + every ResidualBlock.temb_proj, :101) ------------------------------
 struct TembWeights {
@@ -36,9 +35,9 @@ struct TembWeights {
 int launch_temb(const TembWeights& w, const float* t, int B, float* out, cudaStream_t st);
 
 // ---- layout shims ------------------------------------------------------------------------------------------
-int launch_nchw_to_nhwc_pad(const float* x, int B, int C, int HW, bf16* dst, int Cpad, cudaStream_t st);
-int launch_nhwc_to_nchw_f32(const bf16* src, long long pitch, int B, int C, int HW, float* dst, cudaStream_t st);
-int launch_upsample2x(const bf16* src, int B, int H, int W, int C, bf16* dst, cudaStream_t st);
+int launch_nchw_to_nhwc_pad(const float* x, int B, int C, int HW, act16* dst, int Cpad, cudaStream_t st);
+int launch_nhwc_to_nchw_f32(const act16* src, long long pitch, int B, int C, int HW, float* dst, cudaStream_t st);
+int launch_upsample2x(const act16* src, int B, int H, int W, int C, act16* dst, cudaStream_t st);
 
 // ---- PnP-Flow per-pixel kernels (fp32 NCHW) ----------------------------------------------------------------
 struct OpDesc {                        // device-side view of pnpf_operator

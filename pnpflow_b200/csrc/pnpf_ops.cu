@@ -68,7 +68,7 @@ static bool rowconv_shape(const ConvDesc& d, RowShape& r) {
         if (BN < 16 || (BN * rowb) % 1024 != 0) continue;        // stacked vertical-tap tiles must keep the swizzle phase
         const int w_tile = (BN * r.BK * 2 + 1023) / 1024 * 1024;
         const int w_bytes = 3 * r.kch * (3 * BN * rowb) + r.kch2 * w_tile;
-        // bf16 NHWC outputs with full 32-channel blocks are transposed through per-warp staging tiles (RowCfg::STAGE_BYTES)
+        // fp16 NHWC outputs with full 32-channel blocks are transposed through per-warp staging tiles (RowCfg::STAGE_BYTES)
         const bool staged = d.out_mode == 0 && BN >= 32 && d.n_valid == d.N_pad && d.out_col_stride == 1;
         // Warp-role configuration (RowCfg): WIDE (n_epi = 12: 8 epilogue + 8 transform warps) for the fused-GroupNorm layers.
         // It accumulates the output statistics in the staged store, so it needs it (the only unstaged outputs without
@@ -455,14 +455,14 @@ int launch_attn(const AttnOp& op, int n_img, cudaStream_t s) {
     return 0;
 }
 
-static inline bf16 f2bf(float f) { return __float2bfloat16_rn(f); }
+static inline act16 f2bf(float f) { return to_act16(f); }
 
-void pack_conv_weight(bf16* dst, const float* w, int O, int Cin, int ks, int N_pad, int Cin_pad, const float* w2, int C2,
+void pack_conv_weight(act16* dst, const float* w, int O, int Cin, int ks, int N_pad, int Cin_pad, const float* w2, int C2,
                       float scale) {
     const long long Ktot = (long long)ks * ks * Cin_pad + C2;
     for (long long i = 0; i < (long long)N_pad * Ktot; ++i) dst[i] = f2bf(0.f);
     for (int o = 0; o < O; ++o) {
-        bf16* row = dst + (long long)o * Ktot;
+        act16* row = dst + (long long)o * Ktot;
         for (int kh = 0; kh < ks; ++kh)
             for (int kw = 0; kw < ks; ++kw)
                 for (int c = 0; c < Cin; ++c)

@@ -7,7 +7,6 @@
 
 namespace pnpf {
 
-typedef __nv_bfloat16 bf16;
 
 // ------------------------------------------------------------------ tensor-core ops
 struct TcOp {               // a prepared conv_gemm launch
@@ -25,18 +24,18 @@ struct TcOp {               // a prepared conv_gemm launch
 };
 
 struct ConvDesc {
-    // input: bf16 NHWC [B][Hin][Win][x_pitch], channels [c_base, c_base+Cin) are read
-    const bf16* x = nullptr;
+    // input: fp16 NHWC [B][Hin][Win][x_pitch], channels [c_base, c_base+Cin) are read
+    const act16* x = nullptr;
     int B = 0, Hin = 0, Win = 0, Cin = 0;
     long long x_pitch = 0;
     int c_base = 0;
-    // optional second source for a fused 1x1 (extra K) at OUTPUT resolution: bf16 NHWC [B][Hout][Wout][x2_pitch]
-    const bf16* x2 = nullptr;
+    // optional second source for a fused 1x1 (extra K) at OUTPUT resolution: fp16 NHWC [B][Hout][Wout][x2_pitch]
+    const act16* x2 = nullptr;
     int C2 = 0;
     long long x2_pitch = 0;
     int x2_identity = 0;            // the fused 1x1 is the identity (residual add done by the tensor core): not counted as FLOPs
-    // weights: packed bf16 [N_pad][Ktot], Ktot = ksize*ksize*Cin + C2 (pack_conv_weight)
-    const bf16* w = nullptr;
+    // weights: packed fp16 [N_pad][Ktot], Ktot = ksize*ksize*Cin + C2 (pack_conv_weight)
+    const act16* w = nullptr;
     int N_pad = 0;
     int ksize = 3, stride = 1;
     int Hout = 0, Wout = 0;
@@ -48,16 +47,16 @@ struct ConvDesc {
     const float* bias = nullptr;
     const float* bias_img = nullptr;
     long long bias_img_stride = 0;
-    const bf16* residual = nullptr;
+    const act16* residual = nullptr;
     long long res_img_stride = 0, res_row_stride = 0;
     double* stats_out = nullptr;    // optional [B][n_valid][2] GroupNorm statistics of the output (must be zeroed)
     int allow_rowconv = 1;          // use the row-streaming kernel when the shape qualifies
     // ---- row-streaming kernel only (rowconv_eligible(d) must hold, else prepare_conv fails loudly) ----
     // channel concat [x | xb] as main input, [x2 | x2b] as fused 1x1 input: Cin / C2 are the TOTAL channel counts
-    const bf16* xb = nullptr;
+    const act16* xb = nullptr;
     int Cb = 0;
     long long xb_pitch = 0;
-    const bf16* x2b = nullptr;
+    const act16* x2b = nullptr;
     int C2b = 0;
     long long x2b_pitch = 0;
     // fused GroupNorm(+SiLU) of the main input with statistics from the producers' epilogues
@@ -79,10 +78,10 @@ int rowconv_max_smem();
 void describe_conv_impl(const ConvDesc& d, char* buf, size_t n);   // which kernel prepare_conv would pick (PNPF_PLAN_DUMP)
 
 struct GemmDesc {           // out[b][m][n] = sum_k A[b|0][m][k] * Bm[b|0][n][k]  (+bias[n]) (+residual)
-    const bf16* A = nullptr;
+    const act16* A = nullptr;
     long long lda = 0, a_bstride = 0;
     int a_batched = 1;
-    const bf16* Bm = nullptr;
+    const act16* Bm = nullptr;
     long long ldb = 0, b_bstride = 0;
     int b_batched = 1;
     int batch = 1, M = 0, N = 0, K = 0;
@@ -90,7 +89,7 @@ struct GemmDesc {           // out[b][m][n] = sum_k A[b|0][m][k] * Bm[b|0][n][k]
     int out_mode = 0;
     long long out_img_stride = 0, out_row_stride = 0;
     const float* bias = nullptr;
-    const bf16* residual = nullptr;
+    const act16* residual = nullptr;
     long long res_img_stride = 0, res_row_stride = 0;
 };
 int prepare_gemm(TcOp& op, const GemmDesc& d);
@@ -103,12 +102,12 @@ struct AttnOp {
     double flops = 0;
 };
 struct AttnDesc {
-    const bf16* qk = nullptr;       // [B][L][2C]: q (scaled) | k
-    const bf16* vT = nullptr;       // [B][C][L]
-    const bf16* w = nullptr;        // packed projection weights [N_pad = C][C]
+    const act16* qk = nullptr;       // [B][L][2C]: q (scaled) | k
+    const act16* vT = nullptr;       // [B][C][L]
+    const act16* w = nullptr;        // packed projection weights [N_pad = C][C]
     const float* bias = nullptr;    // [C]
-    const bf16* residual = nullptr; // [B][L][C]
-    bf16* out = nullptr;            // [B][L][C]
+    const act16* residual = nullptr; // [B][L][C]
+    act16* out = nullptr;            // [B][L][C]
     double* stats_out = nullptr;    // optional [B][C][2]
     int B = 0, L = 0, C = 0;
 };
@@ -116,9 +115,9 @@ bool attn_core_eligible(int L, int C);
 int prepare_attn(AttnOp& op, const AttnDesc& d);
 int launch_attn(const AttnOp& op, int n_img, cudaStream_t s);
 
-// host-side weight repack: OIHW fp32 (reference layout) -> [N_pad][k*k*Cin_pad + C2] bf16, K ordered (kh, kw, cin),
+// host-side weight repack: OIHW fp32 (reference layout) -> [N_pad][k*k*Cin_pad + C2] fp16, K ordered (kh, kw, cin),
 // optionally followed by the 1x1 shortcut weights w2 [O][C2]; rows >= O and channels >= Cin are zero.
-void pack_conv_weight(bf16* dst, const float* w, int O, int Cin, int ks, int N_pad, int Cin_pad, const float* w2, int C2,
+void pack_conv_weight(act16* dst, const float* w, int O, int Cin, int ks, int N_pad, int Cin_pad, const float* w2, int C2,
                       float scale);
 // 3x3 weights [O][Cin][3][3] -> the 2x2 weights [O][Cin][2][2] of phase (a, b) of the equivalent sub-pixel convolution:
 // out[o][c][i][j] = sum_{kh in R(a,i)} sum_{kw in R(b,j)} w[o][c][kh][kw],  R(0,0)={0}, R(0,1)={1,2}, R(1,0)={0,1}, R(1,1)={2}

@@ -205,7 +205,7 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ===================== MMA issuer (pair: the leader CTA only) =====================
         if (!PAIR || rank == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, BN);
+            constexpr uint32_t idesc = make_idesc_act16(PAIR ? 256 : 128, BN);
             int aslot = 0, bslot = 0;
             uint32_t aphase = 0, bphase = 0;
             int acc = 0;
@@ -242,8 +242,8 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (elect_one_sync()) {
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk) {
-                                    if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
-                                    else umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
+                                    if constexpr (PAIR) umma_f16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
+                                    else umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
                                 }
                                 if constexpr (PAIR) {
                                     umma_commit_pair(&b_empty[bslot]);
@@ -273,8 +273,8 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                     const uint64_t bdesc = make_smem_desc<128>(pb + static_cast<uint32_t>(j * Cfg::B_BYTES));
 #pragma unroll
                                     for (int kk = 0; kk < 4; ++kk) {
-                                        if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
-                                        else umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
+                                        if constexpr (PAIR) umma_f16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
+                                        else umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
                                     }
                                 }
                                 const bool last = t0 + ng == ntap;

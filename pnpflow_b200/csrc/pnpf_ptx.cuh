@@ -6,8 +6,28 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace pnpf {
+
+// ------------------------------------------------------------------ the engine's 16-bit element type
+// Activations between layers, weights and every tcgen05.mma operand are IEEE fp16 (11-bit significand = TF32's, the
+// reference's own cuDNN precision; fp32 accumulation in TMEM).  Round 1 used bf16 (8 bits): same tensor rate, 8x the rounding —
+// enough to leave the 0.01 dB PSNR bar once |v| grows.  Conversions saturate to the finite range (+-65504).
+typedef __half act16;
+__device__ __forceinline__ float2 unpack2(uint32_t w) {                    // two packed elements -> fp32 (lo, hi)
+    return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {            // round to nearest even, saturate to finite
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__host__ __device__ inline act16 to_act16(float f) {
+    const float lim = 65504.f;
+    return __float2half_rn(f > lim ? lim : (f < -lim ? -lim : f));
+}
+__device__ __forceinline__ float act16_to_float(act16 v) { return __half2float(v); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -109,8 +129,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {     // whole warp
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 x bf16 -> fp32), issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 x fp16 -> fp32), issued by ONE thread.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -178,7 +198,7 @@ __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorM
         : "memory");
 }
 // D[tmem, both CTAs] (+)= A (128 rows per CTA) * B (N/2 rows per CTA), issued by ONE thread of the leader CTA
-__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -211,10 +231,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     d |= layout << 61;
     return d;
 }
-// Instruction descriptor for kind::f16 with BF16 A/B (both K-major), FP32 accumulator, dense, no negate.
-// [4,6) c_format=1(F32)  [7,10) a_format=1(BF16)  [10,13) b_format=1(BF16)  [17,23) N>>3  [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+// Instruction descriptor for kind::f16 with FP16 A/B (both K-major), FP32 accumulator, dense, no negate.
+// [4,6) c_format=1(F32)  [7,10) a_format=0(F16; 1 would be BF16)  [10,13) b_format=0(F16)  [17,23) N>>3  [24,29) M>>4
+__host__ __device__ constexpr uint32_t make_idesc_act16(int M, int N) {
+    return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 }  // namespace pnpf

@@ -50,7 +50,7 @@ struct RowConvParams {
     const double* gn_st_a; // [img][Ca][2]
     const double* gn_st_b; // [img][Cb][2]
     int mma2;              // 1: two MMA-issuing warps on alternate input rows (RowCfg::NMMA == 2 only)
-    int staged_store;      // bf16 NHWC output through the per-warp staging tiles (coalesced); else per-thread global stores
+    int staged_store;      // fp16 NHWC output through the per-warp staging tiles (coalesced); else per-thread global stores
     long long* dbg;        // optional [32] cycle counters of CTA 0 (profiling experiments), else nullptr
     EpiParams epi;
 };
@@ -76,7 +76,7 @@ struct RowCfg {
     static constexpr bool WIDE = NEW_ == 12;
     // Below 128 registers the per-thread GroupNorm statistics of the output (2 x 32 accumulators) would spill, so they are
     // accumulated in the READ phase of the staged store instead (a lane sees 8 channels of 4 pixels per row: 16 accumulators), on
-    // the bf16 values that are actually stored — exactly the tensor the next GroupNorm normalises.  The host selects this
+    // the fp16 values that are actually stored — exactly the tensor the next GroupNorm normalises.  The host selects this
     // configuration only together with the staged store.
     static constexpr bool STAGED_STATS = WIDE;
     static constexpr int NACC = (512 / BN) > 16 ? 16 : (512 / BN);
@@ -93,7 +93,7 @@ struct RowCfg {
     static_assert(NACC >= 8, "accumulator ring too shallow");
     static constexpr bool ROW_SPLIT = BN <= 32 && NEW == 8;  // the two sets alternate rows (else set s owns columns [32 s, 32 s + 32))
     static constexpr int NTW = WIDE ? 8 : 4;                 // transform warps
-    // bf16 NHWC outputs are transposed through a per-warp staging tile (32 pixels x 64 bytes, 64B-swizzled): a lane packs its
+    // fp16 NHWC outputs are transposed through a per-warp staging tile (32 pixels x 64 bytes, 64B-swizzled): a lane packs its
     // pixel's 32 channels with four conflict-free st.shared.v4, then the warp stores eight whole 64-byte pixel rows per
     // instruction (per-lane 16-byte stores at a 64/128-byte stride cost one L1 wavefront per lane).  Warp-local: no barrier.
     static constexpr int STAGE_WARP = 32 * 64;
@@ -309,7 +309,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t lo_flags = static_cast<uint32_t>(proto);
             constexpr uint32_t ROW16 = Cfg::kRowBytes / 16, HALO16 = Cfg::HALO_TILE / 16, X216 = Cfg::X2_TILE / 16, WT16 = Cfg::W_TILE / 16,
                                WS16 = Cfg::W_STACK / 16, KH16 = Cfg::KH_BYTES / 16;
-            constexpr uint32_t idesc1 = make_idesc_bf16(128, BN), idesc2 = make_idesc_bf16(128, 2 * BN), idesc3 = make_idesc_bf16(128, 3 * BN);
+            constexpr uint32_t idesc1 = make_idesc_act16(128, BN), idesc2 = make_idesc_act16(128, 2 * BN), idesc3 = make_idesc_act16(128, 3 * BN);
             mbar_wait(wbar, 0);
             tc_fence_after();
             const uint32_t w_lo0 = (smem_u32(wsm) >> 4) | lo_flags;
@@ -506,8 +506,9 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
 #pragma unroll
                         for (int e2 = 0; e2 < 4; ++e2) {
-                            float y0 = fmaf(__uint_as_float(wds[e2] << 16), tsc[c][2 * e2], tsh[c][2 * e2]);
-                            float y1 = fmaf(__uint_as_float(wds[e2] & 0xFFFF0000u), tsc[c][2 * e2 + 1], tsh[c][2 * e2 + 1]);
+                            const float2 xin = unpack2(wds[e2]);
+                            float y0 = fmaf(xin.x, tsc[c][2 * e2], tsh[c][2 * e2]);
+                            float y1 = fmaf(xin.y, tsc[c][2 * e2 + 1], tsh[c][2 * e2 + 1]);
                             if constexpr (kSilu) {
                                 // silu(2h) = h + h tanh(h), fp32 MUFU.TANH per element.  (tanh.approx.f16x2 is split into two
                                 // MUFU.TANH.F16 by ptxas on sm_100a and needs three extra conversions: 11-12 instructions per pair
@@ -518,8 +519,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 y0 = fmaf(y0, t0, y0);
                                 y1 = fmaf(y1, t1, y1);
                             }
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
-                            wds[e2] = *reinterpret_cast<uint32_t*>(&b2);
+                            wds[e2] = pack2(y0, y1);
                         }
                         // stored as soon as it is ready: the fence below waits for the stores still in flight
                         if (ok[k]) sts128_nc(sbase + c * Cfg::HALO_TILE + k * RPI * Cfg::kRowBytes, make_uint4(wds[0], wds[1], wds[2], wds[3]));
@@ -636,8 +636,9 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj) {
-                                v[h2 * 8 + 2 * jj] += __uint_as_float(uu[jj] << 16);
-                                v[h2 * 8 + 2 * jj + 1] += __uint_as_float(uu[jj] & 0xFFFF0000u);
+                                const float2 t = unpack2(uu[jj]);
+                                v[h2 * 8 + 2 * jj] += t.x;
+                                v[h2 * 8 + 2 * jj + 1] += t.y;
                             }
                         }
                     }
@@ -651,13 +652,10 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     if constexpr (CPT == 32) {
-                        if (p.staged_store) {                          // pack to bf16 into this pixel's swizzled staging row
+                        if (p.staged_store) {                          // pack to fp16 into this pixel's swizzled staging row
                             uint32_t pk[8];
 #pragma unroll
-                            for (int jj = 0; jj < 8; ++jj) {
-                                __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * jj], v[2 * jj + 1]);
-                                pk[jj] = *reinterpret_cast<uint32_t*>(&b2);
-                            }
+                            for (int jj = 0; jj < 8; ++jj) pk[jj] = pack2(v[2 * jj], v[2 * jj + 1]);
                             sts128(st_wr + (((2 * q) ^ st_wr_sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
                             sts128(st_wr + (((2 * q + 1) ^ st_wr_sw) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
                             continue;
@@ -671,7 +669,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (p.staged_store) {
                         __syncwarp();
                         // 4 instructions x (8 pixels x 64 bytes): whole 64-byte pixel rows per store
-                        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.epi.out) + img * p.epi.out_img_stride +
+                        act16* orow = reinterpret_cast<act16*>(p.epi.out) + img * p.epi.out_img_stride +
                                               (static_cast<long long>(r) * p.W + w0 + quarter * 32) * p.epi.out_row_stride + n_off + colbase + rd_chunk * 8;
                         uint4 o4[4];
 #pragma unroll
@@ -688,7 +686,8 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     const uint32_t ww[4] = {o4[i].x, o4[i].y, o4[i].z, o4[i].w};
 #pragma unroll
                                     for (int e2 = 0; e2 < 4; ++e2) {
-                                        const float f0 = __uint_as_float(ww[e2] << 16), f1 = __uint_as_float(ww[e2] & 0xFFFF0000u);
+                                        const float2 t = unpack2(ww[e2]);
+                                        const float f0 = t.x, f1 = t.y;
                                         ssum[2 * e2] += f0;
                                         ssq[2 * e2] = fmaf(f0, f0, ssq[2 * e2]);
                                         ssum[2 * e2 + 1] += f1;

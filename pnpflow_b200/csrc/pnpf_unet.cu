@@ -33,8 +33,8 @@ struct WEntry {
     bool loaded = false;
 };
 
-struct Act {                      // bf16 NHWC activation [B][side][side][C]
-    bf16* p = nullptr;
+struct Act {                      // fp16 NHWC activation [B][side][side][C]
+    act16* p = nullptr;
     int C = 0, side = 0;
     double* stats = nullptr;      // [B][C][2] per-channel (sum, sumsq) written by the producing conv's epilogue
     long long elems_per_img() const { return (long long)C * side * side; }
@@ -51,19 +51,19 @@ struct Op {
     const float* gamma = nullptr;
     const float* beta = nullptr;
     int silu = 0;
-    bf16* dst = nullptr;
-    bf16* raw_dst = nullptr;
+    act16* dst = nullptr;
+    act16* raw_dst = nullptr;
     const float* S = nullptr;     // softmax
-    bf16* P = nullptr;
+    act16* P = nullptr;
     long long rows_per_img = 0;
     int L = 0;
-    const bf16* up_src = nullptr; // upsample
+    const act16* up_src = nullptr; // upsample
     int up_side = 0, up_C = 0;
     std::string impl;             // kernel that runs the op (pnpf_debug_op_impl)
     double flops = 0;             // algorithmic 2*MAC per image (tensor-core ops)
     double bytes = 0;             // algorithmic HBM bytes per image: every operand read once + every output written once
-    // debug view of the output (bf16 NHWC), C == 0 -> not readable
-    const bf16* out_p = nullptr;
+    // debug view of the output (fp16 NHWC), C == 0 -> not readable
+    const act16* out_p = nullptr;
     int out_C = 0, out_side = 0;
     long long out_pitch = 0;
 };
@@ -87,7 +87,7 @@ struct pnpf_engine {
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     std::vector<Op> ops;
-    bf16* in_nhwc = nullptr;
+    act16* in_nhwc = nullptr;
     float* tproj = nullptr;
     double* stats_arena = nullptr;
     size_t stats_bytes = 0;
@@ -224,7 +224,7 @@ static int build_layers(pnpf_engine* e) {
 }
 
 // Residual blocks without a shortcut conv on the row-streaming levels add their input through the tensor core: conv2's
-// packed weights get an identity 1x1 block appended (exact: bf16 x 1.0 accumulated in fp32), so the residual rides the
+// packed weights get an identity 1x1 block appended (exact: fp16 x 1.0 accumulated in fp32), so the residual rides the
 // kernel's TMA/MMA path instead of per-thread global loads in the epilogue.
 static bool identity_shortcut(const LayerSpec& L) {
     static const bool off = getenv("PNPF_NO_IDENTITY") != nullptr;     // A/B switch (tools/ab_env.py)
@@ -293,7 +293,7 @@ struct Packer {
         return o;
     }
     float* f32(const std::string& name, size_t n) { size_t o = reserve(name, n * 4); return reinterpret_cast<float*>(host.data() + o); }
-    bf16* b16(const std::string& name, size_t n) { size_t o = reserve(name, n * 2); return reinterpret_cast<bf16*>(host.data() + o); }
+    act16* b16(const std::string& name, size_t n) { size_t o = reserve(name, n * 2); return reinterpret_cast<act16*>(host.data() + o); }
 };
 int round_n(int cout) {
     if (cout <= 16) return 16;
@@ -368,7 +368,7 @@ extern "C" int pnpf_finalize_weights(pnpf_engine* e) {
         switch (L.kind) {
             case LayerSpec::CONV: {
                 const int np = round_n(L.out_ch);
-                bf16* d = pk.b16(p + ".w", (size_t)np * 9 * CIN_PAD);
+                act16* d = pk.b16(p + ".w", (size_t)np * 9 * CIN_PAD);
                 pack_conv_weight(d, W(e, p + ".weight").data(), L.out_ch, L.in_ch, 3, np, CIN_PAD, nullptr, 0, 1.f);
                 pack_bias(p + ".b", np, W(e, p + ".bias"), nullptr);
                 break;
@@ -376,7 +376,7 @@ extern "C" int pnpf_finalize_weights(pnpf_engine* e) {
             case LayerSpec::DOWN:
             case LayerSpec::UP: {
                 const int np = round_n(L.out_ch);
-                bf16* d = pk.b16(p + ".w", (size_t)np * 9 * L.in_ch);
+                act16* d = pk.b16(p + ".w", (size_t)np * 9 * L.in_ch);
                 pack_conv_weight(d, W(e, p + ".weight").data(), L.out_ch, L.in_ch, 3, np, L.in_ch, nullptr, 0, 1.f);
                 pack_bias(p + ".b", np, W(e, p + ".bias"), nullptr);
                 if (L.kind == LayerSpec::UP && subpixel_up_enabled()) {
@@ -384,7 +384,7 @@ extern "C" int pnpf_finalize_weights(pnpf_engine* e) {
                     std::vector<float> f((size_t)L.out_ch * L.in_ch * 4);
                     for (int ph = 0; ph < 4; ++ph) {
                         fold_subpixel_weights(W(e, p + ".weight").data(), L.out_ch, L.in_ch, ph >> 1, ph & 1, f.data());
-                        bf16* ds = pk.b16(p + ".w_sp" + std::to_string(ph), (size_t)np * 4 * L.in_ch);
+                        act16* ds = pk.b16(p + ".w_sp" + std::to_string(ph), (size_t)np * 4 * L.in_ch);
                         pack_conv_weight(ds, f.data(), L.out_ch, L.in_ch, 2, np, L.in_ch, nullptr, 0, 1.f);
                     }
                 }
@@ -394,18 +394,18 @@ extern "C" int pnpf_finalize_weights(pnpf_engine* e) {
                 const int np = round_n(L.out_ch);
                 pack_gn(p + ".norm1");
                 pack_gn(p + ".norm2");
-                bf16* d1 = pk.b16(p + ".conv1.w", (size_t)np * 9 * L.in_ch);
+                act16* d1 = pk.b16(p + ".conv1.w", (size_t)np * 9 * L.in_ch);
                 pack_conv_weight(d1, W(e, p + ".conv1.weight").data(), L.out_ch, L.in_ch, 3, np, L.in_ch, nullptr, 0, 1.f);
                 pack_bias(p + ".conv1.b", np, W(e, p + ".conv1.bias"), nullptr);
                 const bool sc = L.in_ch != L.out_ch;
-                bf16* d2 = pk.b16(p + ".conv2.w", (size_t)np * (9 * L.out_ch + (sc ? L.in_ch : 0)));
+                act16* d2 = pk.b16(p + ".conv2.w", (size_t)np * (9 * L.out_ch + (sc ? L.in_ch : 0)));
                 pack_conv_weight(d2, W(e, p + ".conv2.weight").data(), L.out_ch, L.out_ch, 3, np, L.out_ch,
                                  sc ? W(e, p + ".shortcut.weight").data() : nullptr, sc ? L.in_ch : 0, 1.f);
                 pack_bias(p + ".conv2.b", np, W(e, p + ".conv2.bias"), sc ? &W(e, p + ".shortcut.bias") : nullptr);
                 if (identity_shortcut(L)) {
                     std::vector<float> eye((size_t)L.out_ch * L.out_ch, 0.f);
                     for (int o = 0; o < L.out_ch; ++o) eye[(size_t)o * L.out_ch + o] = 1.f;
-                    bf16* d3 = pk.b16(p + ".conv2.wid", (size_t)np * (9 * L.out_ch + L.out_ch));
+                    act16* d3 = pk.b16(p + ".conv2.wid", (size_t)np * (9 * L.out_ch + L.out_ch));
                     pack_conv_weight(d3, W(e, p + ".conv2.weight").data(), L.out_ch, L.out_ch, 3, np, L.out_ch, eye.data(), L.out_ch, 1.f);
                 }
                 break;
@@ -415,7 +415,7 @@ extern "C" int pnpf_finalize_weights(pnpf_engine* e) {
                 pack_gn(p + ".norm");
                 const float scale = 1.0f / sqrtf((float)C);               // models.py:154 folded into Wq, bq
                 const int np = round_n(2 * C);
-                bf16* dqk = pk.b16(p + ".qk.w", (size_t)np * C);
+                act16* dqk = pk.b16(p + ".qk.w", (size_t)np * C);
                 std::vector<float> wqk((size_t)2 * C * C), bqk(2 * C);
                 const std::vector<float>&wq = W(e, p + ".attn_q.weight"), &wk = W(e, p + ".attn_k.weight");
                 const std::vector<float>&bq = W(e, p + ".attn_q.bias"), &bk = W(e, p + ".attn_k.bias");
@@ -429,11 +429,11 @@ extern "C" int pnpf_finalize_weights(pnpf_engine* e) {
                 }
                 pack_conv_weight(dqk, wqk.data(), 2 * C, C, 1, np, C, nullptr, 0, 1.f);
                 pack_bias(p + ".qk.b", np, bqk, nullptr);
-                bf16* dv = pk.b16(p + ".v.w", (size_t)C * C);              // A operand of the V^T GEMM: [C rows][C k]
+                act16* dv = pk.b16(p + ".v.w", (size_t)C * C);              // A operand of the V^T GEMM: [C rows][C k]
                 const std::vector<float>& wv = W(e, p + ".attn_v.weight");
-                for (size_t i = 0; i < (size_t)C * C; ++i) dv[i] = __float2bfloat16_rn(wv[i]);
+                for (size_t i = 0; i < (size_t)C * C; ++i) dv[i] = to_act16(wv[i]);
                 const int npo = round_n(C);
-                bf16* dpo = pk.b16(p + ".proj.w", (size_t)npo * C);
+                act16* dpo = pk.b16(p + ".proj.w", (size_t)npo * C);
                 const std::vector<float>& wo = W(e, p + ".proj_out.weight");
                 pack_conv_weight(dpo, wo.data(), C, C, 1, npo, C, nullptr, 0, 1.f);
                 // softmax rows sum to 1 => P(V + 1 bv^T) = PV + 1 bv^T: fold Wo*bv into the projection bias
@@ -450,7 +450,7 @@ extern "C" int pnpf_finalize_weights(pnpf_engine* e) {
             case LayerSpec::END: {
                 pack_gn(p + ".0");
                 const int np = round_n(L.out_ch);
-                bf16* d = pk.b16(p + ".2.w", (size_t)np * 9 * L.in_ch);
+                act16* d = pk.b16(p + ".2.w", (size_t)np * 9 * L.in_ch);
                 pack_conv_weight(d, W(e, p + ".2.weight").data(), L.out_ch, L.in_ch, 3, np, L.in_ch, nullptr, 0, 1.f);
                 pack_bias(p + ".2.b", np, W(e, p + ".2.bias"), nullptr);
                 break;
@@ -532,19 +532,19 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 break;
         }
     }
-    bf16* in_nhwc = A.take<bf16>((size_t)Bm * side0 * side0 * CIN_PAD);
+    act16* in_nhwc = A.take<act16>((size_t)Bm * side0 * side0 * CIN_PAD);
     float* tproj = A.take<float>((size_t)Bm * e->total_proj);
     double* stats = A.take<double>((size_t)Bm * stats_elems);
     const size_t stats_bytes = (size_t)Bm * stats_elems * sizeof(double);
-    bf16* t_a1 = A.take<bf16>((size_t)Bm * m_a1);       // normalised conv1 / attention input
-    bf16* t_xcat = A.take<bf16>((size_t)Bm * m_a1);     // raw concat (shortcut operand)
-    bf16* t_h1 = A.take<bf16>((size_t)Bm * m_h1);       // conv1 output / attention O
-    bf16* t_a2 = A.take<bf16>((size_t)Bm * m_h1);       // normalised conv2 input / V^T
-    bf16* t_up = A.take<bf16>((size_t)Bm * m_up);
-    bf16* t_h[2] = {A.take<bf16>((size_t)Bm * m_h), A.take<bf16>((size_t)Bm * m_h)};
-    bf16* t_qk = A.take<bf16>((size_t)Bm * m_qk);
+    act16* t_a1 = A.take<act16>((size_t)Bm * m_a1);       // normalised conv1 / attention input
+    act16* t_xcat = A.take<act16>((size_t)Bm * m_a1);     // raw concat (shortcut operand)
+    act16* t_h1 = A.take<act16>((size_t)Bm * m_h1);       // conv1 output / attention O
+    act16* t_a2 = A.take<act16>((size_t)Bm * m_h1);       // normalised conv2 input / V^T
+    act16* t_up = A.take<act16>((size_t)Bm * m_up);
+    act16* t_h[2] = {A.take<act16>((size_t)Bm * m_h), A.take<act16>((size_t)Bm * m_h)};
+    act16* t_qk = A.take<act16>((size_t)Bm * m_qk);
     float* t_S = A.take<float>((size_t)Bm * m_S);
-    bf16* t_P = A.take<bf16>((size_t)Bm * m_P);
+    act16* t_P = A.take<act16>((size_t)Bm * m_P);
 
     size_t stats_off = 0;   // in doubles, per image block layout: [op][img][C][2] -> we give every GN op its own [Bm][C][2]
     auto new_stats = [&](int C) {
@@ -558,14 +558,14 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
         a.C = C;
         a.side = side;
         a.stats = new_stats(C);
-        if (push) a.p = A.take<bf16>((size_t)Bm * a.elems_per_img());
+        if (push) a.p = A.take<act16>((size_t)Bm * a.elems_per_img());
         else { a.p = t_h[hsel]; hsel ^= 1; }
         return a;
     };
-    auto set_out = [&](Op& o, const bf16* p, int C, int side) { o.out_p = p; o.out_C = C; o.out_side = side; o.out_pitch = C; };
+    auto set_out = [&](Op& o, const act16* p, int C, int side) { o.out_p = p; o.out_C = C; o.out_side = side; o.out_pitch = C; };
 
-    auto add_gn = [&](const std::string& name, const GnSrc& src, int side, const std::string& wname, int silu, bf16* dst,
-                      bf16* raw) {
+    auto add_gn = [&](const std::string& name, const GnSrc& src, int side, const std::string& wname, int silu, act16* dst,
+                      act16* raw) {
         const int C = src.C1 + src.C2;
         Op a;
         a.kind = Op::GN_APPLY; a.name = name; a.gsrc = src; a.HW = side * side; a.impl = "gn_apply";
@@ -575,7 +575,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
         set_out(a, dst, C, side);
         ops.push_back(a);
     };
-    auto add_conv = [&](const std::string& name, ConvDesc d, const bf16* dbg_out, int dbg_C, int dbg_side) -> int {
+    auto add_conv = [&](const std::string& name, ConvDesc d, const act16* dbg_out, int dbg_C, int dbg_side) -> int {
         Op o;
         o.kind = Op::TC; o.name = name;
         d.B = Bm;
@@ -634,7 +634,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 ConvDesc d;
                 d.x = in_nhwc; d.Hin = d.Win = d.Hout = d.Wout = side; d.Cin = CIN_PAD; d.x_pitch = CIN_PAD;
                 d.N_pad = round_n(L.out_ch); d.ksize = 3; d.stride = 1;
-                if (real) { d.w = wptr<bf16>(e, p + ".w"); d.bias = wptr<float>(e, p + ".b"); }
+                if (real) { d.w = wptr<act16>(e, p + ".w"); d.bias = wptr<float>(e, p + ".b"); }
                 d.stats_out = y.stats;
                 d.out = y.p; d.out_mode = 0; d.out_img_stride = px * L.out_ch; d.out_row_stride = L.out_ch; d.n_valid = L.out_ch;
                 if (int rc = add_conv(p, d, y.p, y.C, side)) return rc;
@@ -662,7 +662,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 d1.Hin = d1.Win = d1.Hout = d1.Wout = side;
                 d1.N_pad = round_n(L.out_ch); d1.ksize = 3; d1.stride = 1;
                 if (real) {
-                    d1.w = wptr<bf16>(e, p + ".conv1.w"); d1.bias = wptr<float>(e, p + ".conv1.b");
+                    d1.w = wptr<act16>(e, p + ".conv1.w"); d1.bias = wptr<float>(e, p + ".conv1.b");
                     d1.gn_gamma = wptr<float>(e, p + ".norm1.gamma"); d1.gn_beta = wptr<float>(e, p + ".norm1.beta");
                 } else {
                     d1.gn_gamma = reinterpret_cast<const float*>(0x10); d1.gn_beta = d1.gn_gamma;   // shape analysis only
@@ -677,7 +677,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 d2.Hin = d2.Win = d2.Hout = d2.Wout = side;
                 d2.N_pad = round_n(L.out_ch); d2.ksize = 3; d2.stride = 1;
                 if (real) {
-                    d2.w = wptr<bf16>(e, p + ".conv2.w"); d2.bias = wptr<float>(e, p + ".conv2.b");
+                    d2.w = wptr<act16>(e, p + ".conv2.w"); d2.bias = wptr<float>(e, p + ".conv2.b");
                     d2.gn_gamma = wptr<float>(e, p + ".norm2.gamma"); d2.gn_beta = wptr<float>(e, p + ".norm2.beta");
                 } else {
                     d2.gn_gamma = reinterpret_cast<const float*>(0x10); d2.gn_beta = d2.gn_gamma;
@@ -693,7 +693,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                         ConvDesc di = d2;
                         di.residual = nullptr;
                         di.x2 = h.p; di.x2_pitch = h.C; di.C2 = L.in_ch; di.x2_identity = 1;
-                        if (real) di.w = wptr<bf16>(e, p + ".conv2.wid");
+                        if (real) di.w = wptr<act16>(e, p + ".conv2.wid");
                         if (rowconv_eligible(di)) d2 = di;
                     }
                 }
@@ -728,11 +728,11 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 ConvDesc dq;                                   // [q*scale | k] = hn * [Wq*scale ; Wk]^T
                 dq.x = t_a1; dq.Hin = dq.Win = dq.Hout = dq.Wout = side; dq.Cin = C; dq.x_pitch = C;
                 dq.N_pad = round_n(2 * C); dq.ksize = 1; dq.stride = 1;
-                if (real) { dq.w = wptr<bf16>(e, p + ".qk.w"); dq.bias = wptr<float>(e, p + ".qk.b"); }
+                if (real) { dq.w = wptr<act16>(e, p + ".qk.w"); dq.bias = wptr<float>(e, p + ".qk.b"); }
                 dq.out = t_qk; dq.out_mode = 0; dq.out_img_stride = px * 2 * C; dq.out_row_stride = 2 * C; dq.n_valid = 2 * C;
                 if (int rc = add_conv(p + ".qk", dq, t_qk, 2 * C, side)) return rc;
                 GemmDesc gv;                                   // V^T[b] (C x L) = Wv (C x C) * hn[b]^T
-                gv.A = real ? wptr<bf16>(e, p + ".v.w") : nullptr; gv.lda = C; gv.a_batched = 0;
+                gv.A = real ? wptr<act16>(e, p + ".v.w") : nullptr; gv.lda = C; gv.a_batched = 0;
                 gv.Bm = t_a1; gv.ldb = C; gv.b_bstride = px * C; gv.b_batched = 1;
                 gv.M = C; gv.N = Lk; gv.K = C;
                 gv.out = t_a2; gv.out_mode = 0; gv.out_img_stride = (long long)C * Lk; gv.out_row_stride = Lk;
@@ -746,7 +746,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                     AttnDesc ad;
                     ad.qk = t_qk; ad.vT = t_a2; ad.residual = h.p; ad.out = y.p; ad.stats_out = y.stats; ad.B = Bm; ad.L = Lk; ad.C = C;
                     if (real) {
-                        ad.w = wptr<bf16>(e, p + ".proj.w"); ad.bias = wptr<float>(e, p + ".proj.b");
+                        ad.w = wptr<act16>(e, p + ".proj.w"); ad.bias = wptr<float>(e, p + ".proj.b");
                         if (int rc = prepare_attn(o.attn, ad)) return rc;
                     }
                     o.flops = 2.0 * Lk * Lk * C * 2 + 2.0 * Lk * C * C;
@@ -779,7 +779,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 ConvDesc dp;                                   // y = x + proj_out(O) (+ folded V bias)
                 dp.x = t_h1; dp.Hin = dp.Win = dp.Hout = dp.Wout = side; dp.Cin = C; dp.x_pitch = C;
                 dp.N_pad = round_n(C); dp.ksize = 1; dp.stride = 1;
-                if (real) { dp.w = wptr<bf16>(e, p + ".proj.w"); dp.bias = wptr<float>(e, p + ".proj.b"); }
+                if (real) { dp.w = wptr<act16>(e, p + ".proj.w"); dp.bias = wptr<float>(e, p + ".proj.b"); }
                 dp.residual = h.p; dp.res_img_stride = px * C; dp.res_row_stride = C;
                 dp.stats_out = y.stats;
                 dp.out = y.p; dp.out_mode = 0; dp.out_img_stride = px * C; dp.out_row_stride = C; dp.n_valid = C;
@@ -793,7 +793,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 ConvDesc d;
                 d.x = h.p; d.Hin = d.Win = side; d.Hout = d.Wout = so; d.Cin = L.in_ch; d.x_pitch = L.in_ch;
                 d.N_pad = round_n(L.out_ch); d.ksize = 3; d.stride = 2;
-                if (real) { d.w = wptr<bf16>(e, p + ".w"); d.bias = wptr<float>(e, p + ".b"); }
+                if (real) { d.w = wptr<act16>(e, p + ".w"); d.bias = wptr<float>(e, p + ".b"); }
                 d.stats_out = y.stats;
                 d.out = y.p; d.out_mode = 0; d.out_img_stride = (long long)so * so * L.out_ch; d.out_row_stride = L.out_ch; d.n_valid = L.out_ch;
                 if (int rc = add_conv(p, d, y.p, y.C, so)) return rc;
@@ -814,7 +814,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                         d.out = y.p; d.stats_out = y.stats;
                         for (int ph = 0; ph < 4; ++ph) {
                             d.sp_a = ph >> 1; d.sp_b = ph & 1;
-                            if (real) { d.w = wptr<bf16>(e, p + ".w_sp" + std::to_string(ph)); d.bias = wptr<float>(e, p + ".b"); }
+                            if (real) { d.w = wptr<act16>(e, p + ".w_sp" + std::to_string(ph)); d.bias = wptr<float>(e, p + ".b"); }
                             // the op that completes the tensor carries the layer's name (debug taps compare it with the oracle)
                             const std::string nm = ph == 3 ? p : p + ".phase" + std::to_string(ph);
                             if (int rc = add_conv(nm, d, ph == 3 ? y.p : nullptr, y.C, so)) return rc;
@@ -834,7 +834,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 ConvDesc d;
                 d.x = t_up; d.Hin = d.Win = d.Hout = d.Wout = so; d.Cin = L.in_ch; d.x_pitch = L.in_ch;
                 d.N_pad = round_n(L.out_ch); d.ksize = 3; d.stride = 1;
-                if (real) { d.w = wptr<bf16>(e, p + ".w"); d.bias = wptr<float>(e, p + ".b"); }
+                if (real) { d.w = wptr<act16>(e, p + ".w"); d.bias = wptr<float>(e, p + ".b"); }
                 d.stats_out = y.stats;
                 d.out = y.p; d.out_mode = 0; d.out_img_stride = (long long)so * so * L.out_ch; d.out_row_stride = L.out_ch; d.n_valid = L.out_ch;
                 if (int rc = add_conv(p, d, y.p, y.C, so)) return rc;
@@ -846,7 +846,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 d.x = h.p; d.x_pitch = h.C; d.Hin = d.Win = d.Hout = d.Wout = side; d.Cin = L.in_ch;
                 d.N_pad = round_n(L.out_ch); d.ksize = 3; d.stride = 1;
                 if (real) {
-                    d.w = wptr<bf16>(e, p + ".2.w"); d.bias = wptr<float>(e, p + ".2.b");
+                    d.w = wptr<act16>(e, p + ".2.w"); d.bias = wptr<float>(e, p + ".2.b");
                     d.gn_gamma = wptr<float>(e, p + ".0.gamma"); d.gn_beta = wptr<float>(e, p + ".0.beta");
                     d.gn_stats_a = h.stats;
                 } else {
@@ -992,7 +992,7 @@ extern "C" int pnpf_debug_forward_partial(pnpf_engine* e, const float* x, const 
 extern "C" int pnpf_debug_read_op_output(pnpf_engine* e, int i, int batch, float* dst, size_t dst_elems, int dims[3], void* stream) {
     PNPF_REQUIRE(e && i >= 0 && i < (int)e->ops.size(), "bad op index");
     const Op& o = e->ops[i];
-    PNPF_REQUIRE(o.out_C > 0, "op %d (%s) has no readable bf16 NHWC output", i, o.name.c_str());
+    PNPF_REQUIRE(o.out_C > 0, "op %d (%s) has no readable act16 NHWC output", i, o.name.c_str());
     const size_t n = (size_t)batch * o.out_C * o.out_side * o.out_side;
     dims[0] = o.out_C; dims[1] = o.out_side; dims[2] = o.out_side;
     PNPF_REQUIRE(dst_elems >= n, "destination too small");

@@ -1,6 +1,7 @@
 """GPU parity of the tcgen05 implicit-GEMM kernel (through the C ABI) against torch fp32 conv2d / bmm on the same
-bf16-rounded operands.  Inputs and weights are exactly representable in bf16, so the only differences are the fp32
-accumulation order (and bf16 rounding of the output when out is bf16)."""
+fp16-rounded operands.  Inputs and weights are exactly representable in fp16 (the engine's storage / MMA operand type), so the
+only differences are the fp32 accumulation order (and fp16 rounding of the output when out is fp16; `bf16out` below is the
+historical name of that switch)."""
 import ctypes as C
 
 import pytest
@@ -21,28 +22,28 @@ def _conv_case(B, H, W, Cin, Cout, k, s, C2=0, res=False, bf16out=False, seed=0)
     torch.backends.cuda.matmul.allow_tf32 = False
     g = torch.Generator().manual_seed(seed)
     dev = "cuda"
-    x = torch.randn(B, Cin, H, W, generator=g).to(dev).bfloat16()
-    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).bfloat16().float().contiguous()
+    x = torch.randn(B, Cin, H, W, generator=g).to(dev).half()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).half().float().contiguous()
     b = torch.randn(Cout, generator=g).contiguous()
     Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
     xn = x.permute(0, 2, 3, 1).contiguous()
     x2n = w2 = rn = None
     ref = F.conv2d(x.float(), w.to(dev), b.to(dev), stride=s, padding=k // 2)
     if C2:
-        x2 = torch.randn(B, C2, Ho, Wo, generator=g).to(dev).bfloat16()
-        w2 = (torch.randn(Cout, C2, 1, 1, generator=g) / C2 ** 0.5).bfloat16().float().contiguous()
+        x2 = torch.randn(B, C2, Ho, Wo, generator=g).to(dev).half()
+        w2 = (torch.randn(Cout, C2, 1, 1, generator=g) / C2 ** 0.5).half().float().contiguous()
         x2n = x2.permute(0, 2, 3, 1).contiguous()
         ref = ref + F.conv2d(x2.float(), w2.to(dev))
     if res:
-        r = torch.randn(B, Cout, Ho, Wo, generator=g).to(dev).bfloat16()
+        r = torch.randn(B, Cout, Ho, Wo, generator=g).to(dev).half()
         rn = r.permute(0, 2, 3, 1).contiguous()
         ref = ref + r.float()
-    out = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.bfloat16 if bf16out else torch.float32)
+    out = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.float16 if bf16out else torch.float32)
     L.check(lib.pnpf_conv2d_nhwc(xn.data_ptr(), B, H, W, Cin, w.data_ptr(), b.data_ptr(), Cout, k, s,
                                  x2n.data_ptr() if C2 else None, C2, w2.data_ptr() if C2 else None,
                                  rn.data_ptr() if res else None, out.data_ptr(), 0 if bf16out else 1, None))
     got = out.float().permute(0, 3, 1, 2)
-    tol = max(3e-2, ref.abs().max().item() * 2.0 ** -8) if bf16out else 2e-3     # bf16 output: half an ulp of the largest value
+    tol = max(4e-3, ref.abs().max().item() * 2.0 ** -11) if bf16out else 2e-3     # fp16 output: half an ulp of the largest value
     err = (got - ref).abs().max().item()
     assert err < tol, f"max abs err {err}"
 
@@ -90,27 +91,27 @@ def test_rowconv_fused_groupnorm_two_sources(B, H, W, Ca, Cb, Cout, silu, bf16ou
     g = torch.Generator().manual_seed(B + H + Ca + Cb)
     dev = "cuda"
     C = Ca + Cb
-    xa = (torch.randn(B, Ca, H, W, generator=g) * 1.5 + 0.3).to(dev).bfloat16()
-    xb = (torch.randn(B, Cb, H, W, generator=g) * 0.7 - 0.2).to(dev).bfloat16() if Cb else None
+    xa = (torch.randn(B, Ca, H, W, generator=g) * 1.5 + 0.3).to(dev).half()
+    xb = (torch.randn(B, Cb, H, W, generator=g) * 0.7 - 0.2).to(dev).half() if Cb else None
     gamma = (1 + 0.2 * torch.randn(C, generator=g)).contiguous()
     beta = (0.1 * torch.randn(C, generator=g)).contiguous()
-    w = (torch.randn(Cout, C, 3, 3, generator=g) / (C * 9) ** 0.5).bfloat16().float().contiguous()
+    w = (torch.randn(Cout, C, 3, 3, generator=g) / (C * 9) ** 0.5).half().float().contiguous()
     b = torch.randn(Cout, generator=g).contiguous()
     x = torch.cat([xa, xb], 1).float() if Cb else xa.float()
     a = F.group_norm(x, 32, gamma.to(dev), beta.to(dev), eps=1e-6)
     if silu:
         a = torch.sigmoid(a) * a
-    ref = F.conv2d(a.bfloat16().float(), w.to(dev), b.to(dev), padding=1)
+    ref = F.conv2d(a.half().float(), w.to(dev), b.to(dev), padding=1)
     xan = xa.permute(0, 2, 3, 1).contiguous()
     xbn = xb.permute(0, 2, 3, 1).contiguous() if Cb else None
-    out = torch.full((B, H, W, Cout), float("nan"), device=dev, dtype=torch.bfloat16 if bf16out else torch.float32)
+    out = torch.full((B, H, W, Cout), float("nan"), device=dev, dtype=torch.float16 if bf16out else torch.float32)
     L.check(lib.pnpf_gn_conv2d_nhwc(xan.data_ptr(), Ca, xbn.data_ptr() if Cb else None, Cb, B, H, W, gamma.data_ptr(), beta.data_ptr(),
                                     w.data_ptr(), b.data_ptr(), Cout, silu, out.data_ptr(), 0 if bf16out else 1, None))
     got = out.float().permute(0, 3, 1, 2)
-    # the engine rounds the normalised activation to bf16 like the reference above; tanh.approx / rounding-boundary
-    # flips give rare 1-ulp(bf16) operand differences -> compare in relative L2 and with a loose max
+    # the engine rounds the normalised activation to fp16 like the reference above; tanh.approx / rounding-boundary
+    # flips give rare 1-ulp(fp16) operand differences -> compare in relative L2 and with a loose max
     rel = ((got - ref).norm() / ref.norm()).item()
-    assert rel < (5e-3 if bf16out else 3e-3), rel          # bf16 output rounding adds ~2^-9 relative
+    assert rel < 3e-3, rel          # (tanh.approx.f32: 2^-11 relative; fp16 output rounding adds ~2^-12)
     assert (got - ref).abs().max().item() < 5e-2
 
 
@@ -142,8 +143,8 @@ def test_gemm_nt(batch, M, N, K):
     lib, L = _lib()
     torch.backends.cuda.matmul.allow_tf32 = False
     g = torch.Generator().manual_seed(1)
-    A = torch.randn(batch, M, K, generator=g).cuda().bfloat16()
-    Bm = torch.randn(batch, N, K, generator=g).cuda().bfloat16()
+    A = torch.randn(batch, M, K, generator=g).cuda().half()
+    Bm = torch.randn(batch, N, K, generator=g).cuda().half()
     out = torch.full((batch, M, N), float("nan"), device="cuda")
     L.check(lib.pnpf_gemm_nt(A.data_ptr(), Bm.data_ptr(), out.data_ptr(), batch, M, N, K, 1, None))
     ref = torch.bmm(A.float(), Bm.float().transpose(1, 2))
@@ -152,7 +153,7 @@ def test_gemm_nt(batch, M, N, K):
 
 def test_unsupported_shape_is_an_error_not_a_fallback():
     lib, L = _lib()
-    x = torch.zeros(1, 8, 8, 24, device="cuda", dtype=torch.bfloat16)
+    x = torch.zeros(1, 8, 8, 24, device="cuda", dtype=torch.float16)
     w = torch.zeros(16, 24, 3, 3)
     out = torch.zeros(1, 8, 8, 16, device="cuda")
     rc = lib.pnpf_conv2d_nhwc(x.data_ptr(), 1, 8, 8, 24, w.data_ptr(), None, 16, 3, 1, None, 0, None, None, out.data_ptr(), 1, None)
@@ -168,15 +169,15 @@ def test_fused_attention_core_vs_torch(B):
     lib = _lib.load()
     L = C = 256
     g = torch.Generator().manual_seed(11 + B)
-    q = (torch.randn(B, L, C, generator=g) * 0.125).bfloat16()           # logits ~ N(0, 4): a peaked but not one-hot softmax
-    k = torch.randn(B, L, C, generator=g).bfloat16()
-    v = torch.randn(B, L, C, generator=g).bfloat16()
-    wo = (torch.randn(C, C, generator=g) * 0.05).bfloat16().float()
+    q = (torch.randn(B, L, C, generator=g) * 0.125).half()           # logits ~ N(0, 4): a peaked but not one-hot softmax
+    k = torch.randn(B, L, C, generator=g).half()
+    v = torch.randn(B, L, C, generator=g).half()
+    wo = (torch.randn(C, C, generator=g) * 0.05).half().float()
     bias = torch.randn(C, generator=g)
-    res = torch.randn(B, L, C, generator=g).bfloat16()
+    res = torch.randn(B, L, C, generator=g).half()
     qk = torch.cat([q, k], dim=-1).contiguous().cuda()
     vT = v.transpose(1, 2).contiguous().cuda()
-    out = torch.empty(B, L, C, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(B, L, C, device="cuda", dtype=torch.float16)
     _lib.check(lib.pnpf_attn_core_nhwc(qk.data_ptr(), vT.data_ptr(), wo.contiguous().data_ptr(), bias.data_ptr(), res.cuda().data_ptr(),
                                        out.data_ptr(), B, L, C, None))
     qf, kf, vf = q.float().cuda(), k.float().cuda(), v.float().cuda()
@@ -185,6 +186,6 @@ def test_fused_attention_core_vs_torch(B):
     got = out.float()
     assert torch.isfinite(got).all()
     rel = ((got - ref).norm() / ref.norm()).item()
-    assert rel < 6e-3, rel          # bf16 P, bf16 O and the bf16 output rounding
+    assert rel < 2e-3, rel          # fp16 P, fp16 O and the fp16 output rounding
     attn_only = ((got - res.float().cuda() - bias.cuda()) - (ref - res.float().cuda() - bias.cuda())).norm() / (ref - res.float().cuda() - bias.cuda()).norm()
-    assert attn_only.item() < 2e-2, attn_only.item()
+    assert attn_only.item() < 5e-3, attn_only.item()

@@ -2,15 +2,15 @@
 engine vs the fp32 oracle run on the same GPU (eager torch, TF32 off) on identical y / weights / noise.
 
 The tolerance is the north star's: |dPSNR| < 0.01 dB PER IMAGE (BASELINE.json: "PSNR equal to 2 decimals").  This is what
-licenses the engine's bf16 operand / activation storage.  Cases:
+licenses the engine's 16-bit operand / activation storage (fp16 since round 2).  Cases:
   * cfg2-like  CelebA 128^2 box inpainting (half 20, sigma .05, alpha .5) — SEEDED path: ``noise=None`` on both sides, the
     engine must consume the same Philox stream as the reference's ``torch.randn_like`` calls (pnp_flow.py:48)
   * cfg3-like  CelebA 128^2 Gaussian deblurring (sigma_b 1, k 61) — through the plugin: ``PNP_FLOW.solve_ip`` (measurement
     synthesis :77-80 + loop) against ``oracle.loop.synthesize_measurement`` + ``pnp_flow_restore``
   * cfg4       AFHQ 256^2 SR x4, S = 5, injected noise
   * cfg5-like  AFHQ 256^2 random inpainting p = .7, S = 5, T reduced 200 -> 100, injected noise
-  * a loop at a trained-net-like velocity magnitude (end_conv gain 3e-2 / 1e-1 instead of the recipe's 1e-3): reported
-    honestly (gpurun_out/parity_baseline.json), asserted only against a loose bound.
+  * the loop at larger velocity magnitudes (end_conv gain 1e-2 / 3e-2 instead of the recipe's 1e-3) next to the reference's own
+    TF32 spread: reported as measured (gpurun_out/parity_baseline.json).
 Every case appends its numbers to gpurun_out/parity_baseline.json (copied to profiles/ by the builder).
 """
 import json
@@ -129,8 +129,8 @@ def test_loop_at_larger_velocity_magnitude(end_gain):
     the 100-step loop CHAOTIC: any perturbation of an evaluation is amplified step after step, so "engine
     vs fp32 oracle" has to be read next to the reference's OWN numeric spread.  Three runs on identical y / weights / noise:
     the fp32 oracle (TF32 off), the oracle with cuDNN TF32 allowed (= the reference's default GPU numerics), and
-    the engine.  Reported as measured (gpurun_out/parity_baseline.json); asserted only for sanity — this is NOT the 0.01 dB
-    claim, which is pinned above on the SURVEY §8d weight recipe."""
+    the engine.  Reported as measured (gpurun_out/parity_baseline.json).  With fp16 operands (round 2) the engine stays inside
+    the reference's own TF32 spread: the 0.01 dB bar is asserted at gain 1e-2 as well, the chaotic 3e-2 case for sanity only."""
     import pnpflow_b200 as P
     cfg = oracle.CELEBA_128
     B, T, S = 2, 100, 2
@@ -153,6 +153,8 @@ def test_loop_at_larger_velocity_magnitude(end_gain):
     p_ref = oracle.psnr(x_ref, clean)
     d_tf32 = (oracle.psnr(x_tf32, clean) - p_ref).abs().max().item()
     rel_tf32 = ((x_tf32 - x_ref).norm() / x_ref.norm()).item()
+    # gain 1e-2 (rms|v| ~ 0.2): still well-posed -> the 0.01 dB bar holds (measured 7e-4 dB, the reference's own TF32 path 2.3e-3);
+    # gain 3e-2 (rms|v| ~ 0.4): chaotic, the reference's TF32 path itself ends 0.3 dB from its fp32 run -> sanity bound only
     _compare(f"celeba128/{problem}/end_gain{end_gain}", x, x_ref, clean,
              dict(rms_v_first=vr[0], rms_v_last=vr[-1], reference_tf32_vs_fp32_dpsnr_max=d_tf32, reference_tf32_vs_fp32_rel_l2=rel_tf32,
-                  note="chaotic regime: compare dpsnr_max with reference_tf32_vs_fp32_dpsnr_max; sanity bound only"), tol=3.0)
+                  note="compare dpsnr_max with reference_tf32_vs_fp32_dpsnr_max"), tol=TOL_DB if end_gain <= 1e-2 else 3.0)

@@ -122,7 +122,7 @@ def test_laplace_loop_vs_oracle_injected_noise(problem):
     eng = P.UNetEngine(cfg, sd, max_batch=2 * S)
     x = P.restore(eng, y.cuda(), eng_op, 0.05, steps_pnp=T, num_samples=S, alpha=0.5, lr_pnp=0.05, noise_type='laplace',
                   noise=[n.cuda() for n in noise]).cpu()
-    # the sign nonlinearity turns the engine's bf16 U-Net deviation into occasional +-gamma flips: compare in aggregate
+    # the sign nonlinearity turns the engine's 16-bit U-Net deviation into occasional +-gamma flips: compare in aggregate
     rel = ((x - x_ref).norm() / x_ref.norm()).item()
     dpsnr = (oracle.psnr(x, clean) - oracle.psnr(x_ref, clean)).abs().max().item()
     assert rel < 4e-2, (problem, rel)

@@ -1,6 +1,6 @@
 """GPU parity of the U-Net engine against the oracle (teacher-forced single evaluations) and the reference-produced
-golden vector.  Tolerances: the engine multiplies bf16 operands with fp32 accumulation and stores activations in
-bf16; SURVEY Appendix C predicts rel-L2 ~ 2e-2 per evaluation at scale-1 weights for bf16 operands."""
+golden vector.  Tolerances: the engine multiplies fp16 operands (11-bit significand, like the TF32 operands of the reference's
+cuDNN path) with fp32 accumulation and stores activations in fp16; round 1's bf16 gave rel-L2 ~ 2.6e-2 per evaluation."""
 import os
 
 import numpy as np
@@ -35,7 +35,7 @@ def test_small3_matches_reference_golden():
     v = eng(x.cuda(), t.cuda()).cpu()
     ref = torch.from_numpy(np.load(os.path.join(G, 'unet_small3.npz'))['v_ref'])
     assert torch.isfinite(v).all()
-    assert _rel(v, ref) < 3e-2, _rel(v, ref)
+    assert _rel(v, ref) < 1e-2, _rel(v, ref)          # measured 3.2e-3 (fp16 operands / storage); bf16 gave 2.6e-2
 
 
 @pytest.mark.parametrize("cfg,B", [(mg.SMALL3, 3), (oracle.UNetConfig(3, 64, 32, (1, 2, 4), 2, (16,)), 2),
@@ -44,7 +44,7 @@ def test_small3_matches_reference_golden():
                                    # 64 -> 128+64 channel up path at 128^2: output channels split over CTA pairs
                                    (oracle.UNetConfig(3, 128, 64, (1, 2), 1, ()), 2)])
 def test_layerwise_taps_vs_oracle(cfg, B):
-    """Every layer output the engine can expose (bf16 NHWC) against the oracle's fp32 activation."""
+    """Every layer output the engine can expose (fp16 NHWC) against the oracle's fp32 activation."""
     from pnpflow_b200 import UNetEngine
     sd = oracle.init_state_dict(cfg, seed=5, perturb=0.1)
     g = torch.Generator().manual_seed(3)
@@ -62,7 +62,7 @@ def test_layerwise_taps_vs_oracle(cfg, B):
             r = _rel(a, taps[n])
             worst = max(worst, r)
             checked += 1
-            assert r < 4e-2, (n, r)
+            assert r < 1.5e-2, (n, r)
     assert checked >= len([L for L in oracle.unet_layer_spec(cfg)]) - 2
 
 
@@ -78,7 +78,7 @@ def test_full_nets_teacher_forced(cfg, B):
     v = eng(x, t)
     assert torch.isfinite(v).all()
     r = _rel(v, ref)
-    assert r < 4e-2, r
+    assert r < 1e-2, r
     # CUDA-graph replay gives the same bits as eager launches
     xb, tb, vb, replay = eng.graphed(B)
     xb.copy_(x); tb.copy_(t)

@@ -48,8 +48,8 @@ def run_case(name):
     dev = "cuda"
     res = dict(case=name, **{k: v for k, v in p.items()})
     if kind == "gemm":
-        A = torch.randn(p["batch"], p["M"], p["K"], generator=g).to(dev).bfloat16()
-        Bm = torch.randn(p["batch"], p["N"], p["K"], generator=g).to(dev).bfloat16()
+        A = torch.randn(p["batch"], p["M"], p["K"], generator=g).to(dev).half()
+        Bm = torch.randn(p["batch"], p["N"], p["K"], generator=g).to(dev).half()
         out = torch.full((p["batch"], p["M"], p["N"]), float("nan"), device=dev, dtype=torch.float32)
         rc = lib.pnpf_gemm_nt(A.data_ptr(), Bm.data_ptr(), out.data_ptr(), p["batch"], p["M"], p["N"], p["K"], 1, None)
         if rc:
@@ -66,22 +66,22 @@ def run_case(name):
         return res
     B, H, W, Cin, Cout, k, s = p["B"], p["H"], p["W"], p["Cin"], p["Cout"], p["k"], p["s"]
     C2 = p.get("C2", 0)
-    x = torch.randn(B, Cin, H, W, generator=g).to(dev).bfloat16()
-    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).bfloat16().float()
+    x = torch.randn(B, Cin, H, W, generator=g).to(dev).half()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).half().float()
     b = torch.randn(Cout, generator=g)
     Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
     x_nhwc = x.permute(0, 2, 3, 1).contiguous()
     x2 = w2 = None
     if C2:
-        x2 = torch.randn(B, C2, Ho, Wo, generator=g).to(dev).bfloat16()
-        w2 = (torch.randn(Cout, C2, 1, 1, generator=g) / C2 ** 0.5).bfloat16().float()
+        x2 = torch.randn(B, C2, Ho, Wo, generator=g).to(dev).half()
+        w2 = (torch.randn(Cout, C2, 1, 1, generator=g) / C2 ** 0.5).half().float()
         x2_nhwc = x2.permute(0, 2, 3, 1).contiguous()
     resid = None
     if p.get("res"):
-        resid = torch.randn(B, Cout, Ho, Wo, generator=g).to(dev).bfloat16()
+        resid = torch.randn(B, Cout, Ho, Wo, generator=g).to(dev).half()
         resid_nhwc = resid.permute(0, 2, 3, 1).contiguous()
     f32 = 0 if p.get("bf16out") else 1
-    out = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+    out = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.float32 if f32 else torch.float16)
     wc, bc = w.contiguous(), b.contiguous()
     w2c = w2.contiguous() if C2 else None
     args = (x_nhwc.data_ptr(), B, H, W, Cin, wc.data_ptr(), bc.data_ptr(), Cout, k, s,

@@ -24,24 +24,24 @@ for (H, W, Cin, Cout, C2, res) in () if ONLY_GN else ((256, 256, 32, 32, 0, 0), 
                                    (128, 128, 64, 64, 128, 0),
                                    (64, 64, 128, 128, 0, 0), (64, 64, 128, 128, 0, 1), (64, 64, 256, 128, 0, 0), (64, 64, 128, 128, 256, 0),
                                    (32, 32, 256, 256, 0, 0), (32, 32, 512, 256, 0, 0), (32, 32, 256, 256, 512, 0)):
-    x = torch.randn(B, H, W, Cin, device="cuda").bfloat16()
+    x = torch.randn(B, H, W, Cin, device="cuda").half()
     w = torch.randn(Cout, Cin, 3, 3) * 0.05
-    x2 = torch.randn(B, H, W, C2, device="cuda").bfloat16() if C2 else None
+    x2 = torch.randn(B, H, W, C2, device="cuda").half() if C2 else None
     w2 = torch.randn(Cout, C2, 1, 1) * 0.05 if C2 else None
-    r = torch.randn(B, H, W, Cout, device="cuda").bfloat16() if res else None
-    out = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    r = torch.randn(B, H, W, Cout, device="cuda").half() if res else None
+    out = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.float16)
     print(f"--- B={B} {H}x{W} {Cin}->{Cout} C2={C2} res={res}", flush=True)
     timed(lambda: _lib.check(lib.pnpf_conv2d_nhwc(x.data_ptr(), B, H, W, Cin, w.data_ptr(), None, Cout, 3, 1, x2.data_ptr() if C2 else None, C2,
                                                   w2.data_ptr() if C2 else None, r.data_ptr() if res else None, out.data_ptr(), 0, None)))
 print("=== fused GroupNorm variants", flush=True)
 for (H, W, Ca, Cb, Cout) in ((256, 256, 32, 0, 32), (256, 256, 32, 32, 32), (256, 256, 64, 32, 32), (128, 128, 64, 0, 64), (128, 128, 64, 64, 64),
                              (128, 128, 64, 32, 64)):
-    xa = torch.randn(B, H, W, Ca, device="cuda").bfloat16()
-    xb = torch.randn(B, H, W, Cb, device="cuda").bfloat16() if Cb else None
+    xa = torch.randn(B, H, W, Ca, device="cuda").half()
+    xb = torch.randn(B, H, W, Cb, device="cuda").half() if Cb else None
     Cc = Ca + Cb
     w = torch.randn(Cout, Cc, 3, 3) * 0.05
     gam, bet = torch.ones(Cc), torch.zeros(Cc)
-    out = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.float16)
     print(f"--- GN B={B} {H}x{W} {Ca}+{Cb}->{Cout}", flush=True)
     timed(lambda: _lib.check(lib.pnpf_gn_conv2d_nhwc(xa.data_ptr(), Ca, xb.data_ptr() if Cb else None, Cb, B, H, W, gam.data_ptr(), bet.data_ptr(),
                                                      w.data_ptr(), None, Cout, 1, out.data_ptr(), 0, None)))
