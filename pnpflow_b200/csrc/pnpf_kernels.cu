@@ -119,77 +119,87 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {        // read-onc
 __device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {  // write-once data: evict-first
     asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// Persistent form: the grid is exactly ONE wave (occupancy x SMs CTAs, all resident at once) and CTA b owns the contiguous
+// pixel range [b T / G, (b + 1) T / G) of the flattened (image, pixel) space, T = B * HW — equal work for every CTA, no tail.
+// (Round 1 launched (HW / ppb) x B blocks: 640 blocks on 444 resident slots = 1.44 waves, i.e. 72 % of the achievable rate, which
+// is what the 0.70-0.74 of HBM in profiles/r01_gn_apply_ncu.json was.)  A CTA touches one image, rarely two: the per-image
+// scale / shift table is rebuilt when the image changes.
 template <int U, bool STREAM>
-__global__ void __launch_bounds__(256)
-gn_apply_kernel(GnSrc s, int HW, int pix_per_block, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, 3)
+gn_apply_kernel(GnSrc s, int HW, long long total_pix, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, int gs, int silu, act16* __restrict__ dst,
                 act16* __restrict__ raw_dst) {
     extern __shared__ float ss[];                     // scale[C] | shift[C] | mean[G] | rstd[G]
     const int C = s.C1 + s.C2;
     const int G = C / gs;
-    const int img = blockIdx.y;
     float* gmean = ss + 2 * C;
     float* grstd = gmean + G;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        double S = 0, Q = 0;
-        for (int j = 0; j < gs; ++j) {
-            const int cc = g * gs + j;
-            const double* sp = (cc < s.C1) ? s.st1 + ((long long)img * s.C1 + cc) * 2 : s.st2 + ((long long)img * s.C2 + (cc - s.C1)) * 2;
-            S += sp[0];
-            Q += sp[1];
-        }
-        const double n = (double)gs * HW;
-        const double mean = S / n;
-        double var = Q / n - mean * mean;
-        if (var < 0) var = 0;
-        gmean[g] = (float)mean;
-        grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
-    }
-    __syncthreads();
-    const float half = silu ? 0.5f : 1.f;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / gs;
-        const float sc = grstd[g] * gamma[c];
-        ss[c] = half * sc;
-        ss[C + c] = half * (beta[c] - gmean[g] * sc);
-    }
-    __syncthreads();
     const int nvec = C >> 3;
     const int ppb = blockDim.x / nvec;
     const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
-    const int p0 = blockIdx.x * pix_per_block;
-    const int p1 = min(p0 + pix_per_block, HW);
-    float sc[8], sh[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = ss[v * 8 + j];
-        sh[j] = ss[C + v * 8 + j];
-    }
-    for (int p = p0 + pl; p < p1; p += U * ppb) {
-        uint4 u[U];
-#pragma unroll
-        for (int k = 0; k < U; ++k)
-            if (p + k * ppb < p1) {
-                const uint4* sp = reinterpret_cast<const uint4*>(src_ptr(s, img, p + k * ppb, HW, v * 8));
-                u[k] = STREAM ? ldg_stream(sp) : __ldg(sp);
+    const float half = silu ? 0.5f : 1.f;
+    const long long g_begin = total_pix * blockIdx.x / gridDim.x, g_end = total_pix * (blockIdx.x + 1) / gridDim.x;
+    for (long long g0 = g_begin; g0 < g_end;) {
+        const int img = (int)(g0 / HW);
+        const int p0 = (int)(g0 - (long long)img * HW);
+        const int p1 = (int)min((long long)HW, p0 + (g_end - g0));
+        g0 += p1 - p0;
+        __syncthreads();                              // the previous image's table is no longer read
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            double S = 0, Q = 0;
+            for (int j = 0; j < gs; ++j) {
+                const int cc = g * gs + j;
+                const double* sp = (cc < s.C1) ? s.st1 + ((long long)img * s.C1 + cc) * 2 : s.st2 + ((long long)img * s.C2 + (cc - s.C1)) * 2;
+                S += sp[0];
+                Q += sp[1];
             }
+            const double n = (double)gs * HW;
+            const double mean = S / n;
+            double var = Q / n - mean * mean;
+            if (var < 0) var = 0;
+            gmean[g] = (float)mean;
+            grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const int g = c / gs;
+            const float sc = grstd[g] * gamma[c];
+            ss[c] = half * sc;
+            ss[C + c] = half * (beta[c] - gmean[g] * sc);
+        }
+        __syncthreads();
+        float sc[8], sh[8];
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            if (p + k * ppb >= p1) break;
-            const long long o = ((long long)img * HW + p + k * ppb) * C + v * 8;
-            if (raw_dst) {
-                if (STREAM) stg_stream(reinterpret_cast<uint4*>(raw_dst + o), u[k]);
-                else *reinterpret_cast<uint4*>(raw_dst + o) = u[k];
-            }
-            float f[8];
-            unpack8(u[k], f);
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = ss[v * 8 + j];
+            sh[j] = ss[C + v * 8 + j];
+        }
+        for (int p = p0 + pl; p < p1; p += U * ppb) {
+            uint4 u[U];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float h = fmaf(f[j], sc[j], sh[j]);
-                f[j] = silu ? fmaf(h, tanh_approx(h), h) : h;
+            for (int k = 0; k < U; ++k)
+                if (p + k * ppb < p1) {
+                    const uint4* sp = reinterpret_cast<const uint4*>(src_ptr(s, img, p + k * ppb, HW, v * 8));
+                    u[k] = STREAM ? ldg_stream(sp) : __ldg(sp);
+                }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                if (p + k * ppb >= p1) break;
+                const long long o = ((long long)img * HW + p + k * ppb) * C + v * 8;
+                if (raw_dst) {
+                    if (STREAM) stg_stream(reinterpret_cast<uint4*>(raw_dst + o), u[k]);
+                    else *reinterpret_cast<uint4*>(raw_dst + o) = u[k];
+                }
+                float f[8];
+                unpack8(u[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float h = fmaf(f[j], sc[j], sh[j]);
+                    f[j] = silu ? fmaf(h, tanh_approx(h), h) : h;
+                }
+                if (STREAM) stg_stream(reinterpret_cast<uint4*>(dst + o), pack8(f));
+                else *reinterpret_cast<uint4*>(dst + o) = pack8(f);
             }
-            if (STREAM) stg_stream(reinterpret_cast<uint4*>(dst + o), pack8(f));
-            else *reinterpret_cast<uint4*>(dst + o) = pack8(f);
         }
     }
 }
@@ -199,12 +209,25 @@ int launch_gn_apply(const GnSrc& s, int B, int HW, const float* gamma, const flo
     const int C = s.C1 + s.C2;
     PNPF_REQUIRE(C % groups == 0 && C % 8 == 0 && s.C1 % 8 == 0, "GroupNorm channels (%d+%d) unsupported", s.C1, s.C2);
     const int threads = gn_threads(C);
-    const int ppb_blk = gn_pix_per_block(HW, B);
-    dim3 grid((HW + ppb_blk - 1) / ppb_blk, B);
     PNPF_REQUIRE(s.st1 && (s.C2 == 0 || s.st2), "GroupNorm apply without statistics");
+    const size_t smem = (2 * C + 2 * groups) * sizeof(float);
+    // one wave: resident CTAs per SM for this block size (register-limited: 3 at 256 threads) x SMs
+    static DeviceCache cache[9];                      // per block-size class (threads / 32)
+    int per_sm = 0;
+    DeviceCache& dc = cache[(threads / 32) % 9];
+    if (!dc.lookup(&per_sm)) {
+        PNPF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_apply_kernel<8, true>, threads, smem));
+        if (per_sm < 1) per_sm = 1;
+        dc.store(per_sm);
+    }
+    const long long total_pix = (long long)B * HW;
+    long long grid = (long long)per_sm * num_sms();
+    const long long max_grid = (total_pix + 63) / 64;         // at least 64 pixels per CTA
+    if (grid > max_grid) grid = max_grid;
+    if (grid < 1) grid = 1;
     // 8 independent 16-byte loads per thread in flight + streaming cache hints: 13 % faster than 4 loads / default caching
     // (same-box sweep, profiles/r01_ab_experiments.md)
-    gn_apply_kernel<8, true><<<grid, threads, (2 * C + 2 * groups) * sizeof(float), st>>>(s, HW, ppb_blk, gamma, beta, eps, C / groups, silu, dst, raw_dst);
+    gn_apply_kernel<8, true><<<(unsigned)grid, threads, smem, st>>>(s, HW, total_pix, gamma, beta, eps, C / groups, silu, dst, raw_dst);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
