@@ -100,12 +100,19 @@ extern "C" int pnpf_upconv2x_nhwc(const void* x, int B, int H, int W, int Cin, c
     std::vector<float> bp(N_pad, 0.f);
     if (host_bias)
         for (int i = 0; i < Cout; ++i) bp[i] = host_bias[i];
-    const size_t wn = (size_t)N_pad * 4 * Cin;
-    std::vector<act16> wp(4 * wn);
+    // same choice as the U-Net plan: two column phases per launch (2 launches) when 2 * Cout <= 256, else four single phases
+    const bool pairph = 2 * N_pad <= 256 && getenv("PNPF_NO_SUBPIX2") == nullptr;
+    const size_t wn = pairph ? (size_t)2 * N_pad * 6 * Cin : (size_t)N_pad * 4 * Cin;
+    const int nlaunch = pairph ? 2 : 4;
+    std::vector<act16> wp(nlaunch * wn);
     std::vector<float> f((size_t)Cout * Cin * 4);
-    for (int ph = 0; ph < 4; ++ph) {
-        fold_subpixel_weights(host_w, Cout, Cin, ph >> 1, ph & 1, f.data());
-        pack_conv_weight(wp.data() + ph * wn, f.data(), Cout, Cin, 2, N_pad, Cin, nullptr, 0, 1.0f);
+    for (int ph = 0; ph < nlaunch; ++ph) {
+        if (pairph) {
+            pack_subpixel_pair_weights(wp.data() + ph * wn, host_w, Cout, Cin, ph);
+        } else {
+            fold_subpixel_weights(host_w, Cout, Cin, ph >> 1, ph & 1, f.data());
+            pack_conv_weight(wp.data() + ph * wn, f.data(), Cout, Cin, 2, N_pad, Cin, nullptr, 0, 1.0f);
+        }
     }
     act16* dw = nullptr;
     float* db = nullptr;
@@ -114,12 +121,13 @@ extern "C" int pnpf_upconv2x_nhwc(const void* x, int B, int H, int W, int Cin, c
     PNPF_CHECK_CUDA(cudaMemcpyAsync(dw, wp.data(), wp.size() * sizeof(act16), cudaMemcpyHostToDevice, s));
     PNPF_CHECK_CUDA(cudaMemcpyAsync(db, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice, s));
     int rc = 0;
-    for (int ph = 0; ph < 4 && !rc; ++ph) {
+    for (int ph = 0; ph < nlaunch && !rc; ++ph) {
         ConvDesc d;
         d.x = static_cast<const act16*>(x);
         d.B = B; d.Hin = d.Hout = H; d.Win = d.Wout = W; d.Cin = Cin; d.x_pitch = Cin;
-        d.w = dw + ph * wn; d.N_pad = N_pad; d.ksize = 3; d.stride = 1;
-        d.subpix = 1; d.sp_a = ph >> 1; d.sp_b = ph & 1;
+        d.w = dw + ph * wn; d.ksize = 3; d.stride = 1;
+        if (pairph) { d.N_pad = 2 * N_pad; d.subpix = 2; d.sp_a = ph; d.sp_b = 0; }
+        else { d.N_pad = N_pad; d.subpix = 1; d.sp_a = ph >> 1; d.sp_b = ph & 1; }
         d.out = out; d.out_mode = 0;
         d.out_img_stride = 4LL * H * W * Cout; d.out_row_stride = Cout; d.n_valid = Cout;
         d.bias = db;

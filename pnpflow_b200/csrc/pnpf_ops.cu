@@ -3,6 +3,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace pnpf {
 
@@ -101,6 +102,7 @@ static bool patchconv_shape(const ConvDesc& d, PatchShape& r) {
     if (!(d.N_pad == 64 || d.N_pad == 128 || d.N_pad == 256) || d.c_base != 0 || d.xb || d.x2b || d.gn_gamma) return false;
     if (d.Cin % 64 || d.C2 % 64 || d.Cin < 64) return false;
     if (d.subpix && (d.x2 || d.C2 || d.residual || d.out_mode != 0)) return false;
+    if (d.subpix == 2 && (d.N_pad != 2 * d.n_valid || d.N_pad > 256)) return false;       // two column phases: 2 * C_out accumulator columns
     r.P = d.Wout + 2;
     r.NR = (r.P - 1 + 127) / r.P + 1 + 2;          // rows a tile of 128 positions can touch, plus the two halo rows
     r.patch_bytes = (r.NR * r.P * 128 + 1023) / 1024 * 1024;
@@ -127,7 +129,7 @@ void describe_conv_impl(const ConvDesc& d, char* buf, size_t n) {
                  r.nslot, r.kch2, r.w_bytes / 1024, r.slot_bytes / 1024, r.stage_bytes / 1024, r.n_epi, d.gn_gamma ? 1 : 0);
     else if (PatchShape ps; patchconv_shape(d, ps))
         snprintf(buf, n, "patchconv<%d> P=%d NR=%d patch=%dKB na=%d nb=%d tiles/img=%d%s", d.N_pad, ps.P, ps.NR, ps.patch_bytes / 1024, ps.na, ps.nb,
-                 ps.tiles_per_img, d.subpix ? " subpix" : "");
+                 ps.tiles_per_img, d.subpix == 2 ? " subpix2" : (d.subpix ? " subpix" : ""));
     else
         snprintf(buf, n, "conv_gemm<%d,%d> k=%d s=%d", (d.Cin % 64 == 0 && d.C2 % 64 == 0) ? 64 : 32, d.N_pad > 256 ? 256 : d.N_pad, d.ksize, d.stride);
 }
@@ -185,18 +187,18 @@ static int try_prepare_patchconv(TcOp& op, const ConvDesc& d) {
     q.kchunks = d.Cin / 64; q.kchunks2 = d.x2 ? d.C2 / 64 : 0;
     q.patch_bytes = sh.patch_bytes; q.na = sh.na; q.nb = sh.nb;
     op.patch_nb_pair = sh.nb_pair;
-    op.patch_subpix = d.subpix ? 1 : 0;
+    op.patch_subpix = d.subpix;
     q.sp_a = d.sp_a; q.sp_b = d.sp_b;
     PNPF_REQUIRE(!d.subpix || ((d.sp_a | d.sp_b) & ~1) == 0, "sub-pixel phase (%d,%d) must be 0/1", d.sp_a, d.sp_b);
     fill_epi(q.epi, d);
     op.kind = 2; op.BK = 64; op.BN = d.N_pad;
-    const long long Ktot = d.subpix ? 4LL * d.Cin : 9LL * d.Cin + (d.x2 ? d.C2 : 0);
+    const long long Ktot = d.subpix == 2 ? 6LL * d.Cin : (d.subpix ? 4LL * d.Cin : 9LL * d.Cin + (d.x2 ? d.C2 : 0));
     if (int e = make_act_tmap(&op.tmA, d.x, d.Cin, d.x_pitch, d.Win, d.Hin, d.B, 64, sh.P, sh.NR, 1)) return e;
     op.tmA2 = op.tmA;
     if (d.x2) { if (int e = make_act_tmap(&op.tmA2, d.x2, d.C2, d.x2_pitch, d.Wout, d.Hout, d.B, 64, sh.P, sh.NR, 1)) return e; }
     if (int e = make_b_tmap(&op.tmB, d.w, Ktot, Ktot, d.N_pad, 1, 0, 64, d.N_pad)) return e;
     if (int e = make_b_tmap(&op.tmBh, d.w, Ktot, Ktot, d.N_pad, 1, 0, 64, d.N_pad / 2)) return e;
-    op.flops = 2.0 * d.B * d.Hout * d.Wout * (double)d.n_valid * (double)Ktot;
+    op.flops = 2.0 * d.B * d.Hout * d.Wout * (double)d.n_valid * (double)(d.subpix == 2 ? 8LL * d.Cin : Ktot);     // useful MACs (two phases x 4 taps)
     return 0;
 }
 
@@ -330,7 +332,7 @@ static int launch_row_t(const TcOp& op, cudaStream_t stream) {
     return 0;
 }
 
-template <int BN, bool PAIR, bool SUBPIX = false, int TG = 1>
+template <int BN, bool PAIR, int SUBPIX = 0, int TG = 1>
 static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
     using Cfg = PatchCfg<BN, PAIR>;
     PatchConvParams q = op.pp;
@@ -380,18 +382,31 @@ int launch_tc(const TcOp& op, cudaStream_t s) {
     if (op.kind == 2) {
         static const bool no_pair = getenv("PNPF_NO_PAIR") != nullptr;
         const bool pair = !no_pair && op.pp.n_img % 2 == 0;
+        if (op.patch_subpix == 2) {                   // two column phases per launch: 2 x 3 taps, tap groups of three
+            const bool tg = (pair ? op.patch_nb_pair : op.pp.nb) >= 6;
+            if (op.BN == 128) {
+                if (tg) return pair ? launch_patch_t<128, true, 2, 3>(op, s) : launch_patch_t<128, false, 2, 3>(op, s);
+                return pair ? launch_patch_t<128, true, 2>(op, s) : launch_patch_t<128, false, 2>(op, s);
+            }
+            if (op.BN == 256) {
+                if (tg) return pair ? launch_patch_t<256, true, 2, 3>(op, s) : launch_patch_t<256, false, 2, 3>(op, s);
+                return pair ? launch_patch_t<256, true, 2>(op, s) : launch_patch_t<256, false, 2>(op, s);
+            }
+            set_error("no two-phase sub-pixel instantiation for BN=%d", op.BN);
+            return 2;
+        }
         if (op.patch_subpix) {
-            if (op.BN == 64) return pair ? launch_patch_t<64, true, true>(op, s) : launch_patch_t<64, false, true>(op, s);
-            if (op.BN == 128) return pair ? launch_patch_t<128, true, true>(op, s) : launch_patch_t<128, false, true>(op, s);
-            if (op.BN == 256) return pair ? launch_patch_t<256, true, true>(op, s) : launch_patch_t<256, false, true>(op, s);
+            if (op.BN == 64) return pair ? launch_patch_t<64, true, 1>(op, s) : launch_patch_t<64, false, 1>(op, s);
+            if (op.BN == 128) return pair ? launch_patch_t<128, true, 1>(op, s) : launch_patch_t<128, false, 1>(op, s);
+            if (op.BN == 256) return pair ? launch_patch_t<256, true, 1>(op, s) : launch_patch_t<256, false, 1>(op, s);
         }
         // three taps (one kernel row) per weight-ring slot: the issuer waits and commits once per 12 MMAs instead of once per 4
         // (same arithmetic in the same order; r02 A/B: profiles/r02_optin_validation.log).  Needs >= 2 slots of 3 tiles.
         static const bool tg1 = getenv("PNPF_PATCH_TG1") != nullptr;        // A/B switch (tools/ab_env.py)
         if (!tg1 && (pair ? op.patch_nb_pair : op.pp.nb) >= 6) {
-            if (op.BN == 64) return pair ? launch_patch_t<64, true, false, 3>(op, s) : launch_patch_t<64, false, false, 3>(op, s);
-            if (op.BN == 128) return pair ? launch_patch_t<128, true, false, 3>(op, s) : launch_patch_t<128, false, false, 3>(op, s);
-            if (op.BN == 256) return pair ? launch_patch_t<256, true, false, 3>(op, s) : launch_patch_t<256, false, false, 3>(op, s);
+            if (op.BN == 64) return pair ? launch_patch_t<64, true, 0, 3>(op, s) : launch_patch_t<64, false, 0, 3>(op, s);
+            if (op.BN == 128) return pair ? launch_patch_t<128, true, 0, 3>(op, s) : launch_patch_t<128, false, 0, 3>(op, s);
+            if (op.BN == 256) return pair ? launch_patch_t<256, true, 0, 3>(op, s) : launch_patch_t<256, false, 0, 3>(op, s);
         }
         if (op.BN == 64) return pair ? launch_patch_t<64, true>(op, s) : launch_patch_t<64, false>(op, s);
         if (op.BN == 128) return pair ? launch_patch_t<128, true>(op, s) : launch_patch_t<128, false>(op, s);
@@ -469,6 +484,21 @@ void pack_conv_weight(act16* dst, const float* w, int O, int Cin, int ks, int N_
                     row[(long long)(kh * ks + kw) * Cin_pad + c] = f2bf(scale * w[(((long long)o * Cin + c) * ks + kh) * ks + kw]);
         if (w2)
             for (int c = 0; c < C2; ++c) row[(long long)ks * ks * Cin_pad + c] = f2bf(w2[(long long)o * C2 + c]);
+    }
+}
+
+void pack_subpixel_pair_weights(act16* dst, const float* w, int O, int Cin, int a) {
+    const long long Ktot = 6LL * Cin;
+    std::vector<float> f((size_t)O * Cin * 4);
+    for (long long i = 0; i < 2LL * O * Ktot; ++i) dst[i] = f2bf(0.f);
+    for (int b = 0; b < 2; ++b) {
+        fold_subpixel_weights(w, O, Cin, a, b, f.data());                 // [O][Cin][2][2]
+        for (int o = 0; o < O; ++o) {
+            act16* row = dst + (long long)(b * O + o) * Ktot;
+            for (int i = 0; i < 2; ++i)
+                for (int j = 0; j < 2; ++j)
+                    for (int ch = 0; ch < Cin; ++ch) row[(long long)(i * 3 + (b + j)) * Cin + ch] = f2bf(f[(((size_t)o * Cin + ch) * 2 + i) * 2 + j]);
+        }
     }
 }
 

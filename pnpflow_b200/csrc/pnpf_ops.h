@@ -16,7 +16,7 @@ struct TcOp {               // a prepared conv_gemm launch
     RowConvParams rp;       // kind == 1: row-streaming conv (pnpf_rowconv.cuh)
     PatchConvParams pp;     // kind == 2: patch-streaming conv (pnpf_patchconv.cuh)
     int patch_nb_pair = 0;  // weight-ring depth of the CTA-pair launch (half tiles)
-    int patch_subpix = 0;   // patch conv computes one phase of a sub-pixel (nearest x2 + 3x3) convolution
+    int patch_subpix = 0;   // patch conv computes one phase (1) / the two column phases of a row parity (2) of a sub-pixel convolution
     int kind = 0;           // 0: conv_gemm_kernel, 1: rowconv_kernel, 2: patchconv_kernel
     int BK = 0, BN = 0;
     int n_epi = 8;          // row conv: epilogue warps (RowCfg::NEW), the other worker warps run the GroupNorm transform
@@ -69,6 +69,8 @@ struct ConvDesc {
     // ---- patch-streaming kernel only: one phase (sp_a, sp_b) of "nearest x2 upsampling + 3x3 conv" on the LOW-resolution input.
     // Hin/Win/Hout/Wout describe the low-resolution grid, the out_* strides the high-resolution tensor [B][2H][2W][C];
     // w = folded 2x2 weights of this phase, packed [N_pad][4*Cin] in (i, j, cin) order (fold_subpixel_weights + pack).
+    // subpix = 2: both column phases of row parity sp_a in one launch: N_pad = 2 * C_out accumulator columns (b-major), n_valid =
+    // C_out channels, bias [C_out], w = pack_subpixel_pair_weights (2 x 3 taps, [2*C_out][6*Cin]).
     int subpix = 0, sp_a = 0, sp_b = 0;
 };
 int prepare_conv(TcOp& op, const ConvDesc& d);
@@ -122,5 +124,8 @@ void pack_conv_weight(act16* dst, const float* w, int O, int Cin, int ks, int N_
 // 3x3 weights [O][Cin][3][3] -> the 2x2 weights [O][Cin][2][2] of phase (a, b) of the equivalent sub-pixel convolution:
 // out[o][c][i][j] = sum_{kh in R(a,i)} sum_{kw in R(b,j)} w[o][c][kh][kw],  R(0,0)={0}, R(0,1)={1,2}, R(1,0)={0,1}, R(1,1)={2}
 void fold_subpixel_weights(const float* w, int O, int Cin, int a, int b, float* out);
+// 3x3 weights [O][Cin][3][3] -> packed [2*O][6*Cin] operand of the SUBPIX = 2 launch for output-row parity a: row b*O + o, K index
+// (i*3 + c)*Cin + ch holds W_ab[o][ch][i][c - b] (fold_subpixel_weights) when c - b is 0 or 1, else 0.
+void pack_subpixel_pair_weights(act16* dst, const float* w, int O, int Cin, int a);
 
 }  // namespace pnpf

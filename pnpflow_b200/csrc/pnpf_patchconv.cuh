@@ -22,6 +22,13 @@
 // materialised.  In the padded-linear space tap (i,j) is simply patch-row offset (a+i)*P + (b+j); the epilogue scatters the
 // tile to the stride-2 lattice of the high-resolution output.
 //
+// SUBPIX = 2 (round 2, default for C_out <= 128): BOTH column phases b = 0, 1 of an output-row parity a in one launch, as a
+// 2 x 3-tap convolution with N = 2 C_out: tap (i, c) reads patch-row offset (a + i) P + c, accumulator columns [b C_out, (b+1) C_out)
+// belong to output pixel (2h + a, 2w + b), and the packed weights hold W_ab[i][c - b] (zero where c - b is not 0 / 1:
+// pack_subpixel_pair_weights).  The patch is fetched once for two phases (the single-phase form at C_out = 64 was bound by the
+// L2 -> shared-memory patch fill: 66 KB per 16 short MMAs), every MMA is N = 128 / 256 wide instead of 64 / 128, a thread's two
+// output pixels are adjacent (2 C_out contiguous values), and an up conv is two launches instead of four.
+//
 // TG (opt-in, PNPF_PATCH_TG=3): taps per weight-ring slot.  The MMA issuer pays a barrier wait and a tcgen05.commit per weight
 // slot (~ 100 clocks), which is exposed when the four MMAs of a tap are short (N = 128: 4 x 64 clocks, measured ~ 90 per MMA;
 // N = 64: 4 x 32): with TG = 3 a slot holds the three taps (kh, 0..2) of a kernel row, so the issuer waits and commits once per
@@ -58,7 +65,7 @@ struct PatchCfg {
     static_assert(BN == 64 || BN == 128 || BN == 256, "patch conv output widths");
 };
 
-template <int BN, bool PAIR, bool SUBPIX = false, int TG = 1>
+template <int BN, bool PAIR, int SUBPIX = 0, int TG = 1>      // SUBPIX: 0 = 3x3 conv, 1 = one sub-pixel phase, 2 = the two column phases of a row parity
 __global__ void __launch_bounds__(PatchCfg<BN, PAIR>::THREADS, 1)
 patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ PatchConvParams p) {
@@ -151,14 +158,14 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const long long c_start = PNPF_CLK();
         for (int u = unit0; u < total_units; u += unit_step) {
             for (int c = 0; c < nch; ++c) {
-                const int ntap = c < p.kchunks ? (SUBPIX ? 4 : 9) : 1;
+                const int ntap = c < p.kchunks ? (SUBPIX == 1 ? 4 : (SUBPIX == 2 ? 6 : 9)) : 1;
                 if constexpr (TG == 1) {
                     for (int t = 0; t < ntap; ++t) {
                         PNPF_TIMED_WAIT(&b_empty[slot], phase ^ 1, c_wait);
                         uint8_t* dst = b_ring + slot * Cfg::B_BYTES;
                         if (elect_one_sync()) {
                             // packed K order (pack_conv_weight): (kh, kw, cin) for the 3x3 part, then the 1x1 source channels
-                            const int tap = SUBPIX ? t : (t + tap_rot) % 9;      // SUBPIX: packed K order (i, j, cin), 4 taps
+                            const int tap = SUBPIX ? t : (t + tap_rot) % 9;      // SUBPIX: packed K order (i, j, cin), 4 or 6 taps
                             const int k0 = c < p.kchunks ? (tap * p.kchunks + c) * 64 : (9 * p.kchunks + (c - p.kchunks)) * 64;
                             if constexpr (PAIR) {
                                 const uint32_t fb = mapa_u32(smem_u32(&b_full[slot]), 0);
@@ -173,7 +180,7 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (++slot == p.nb) { slot = 0; phase ^= 1; }
                     }
                 } else {
-                    static_assert(TG == 1 || !SUBPIX, "tap groups are for the 3x3 form");
+                    static_assert(TG == 1 || SUBPIX != 1, "tap groups need three taps per kernel row");
                     for (int t0 = 0; t0 < ntap; t0 += TG) {
                         const int ng = min(TG, ntap - t0);           // the three taps of a kernel row, or the single 1x1 tap
                         PNPF_TIMED_WAIT(&b_empty[slot], phase ^ 1, c_wait);
@@ -223,15 +230,18 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     PNPF_TIMED_WAIT(&a_full[aslot], aphase, c_afull);
                     tc_fence_after();
                     const uint32_t pa = smem_u32(a_ring + aslot * p.patch_bytes);
-                    const int ntap = c < p.kchunks ? (SUBPIX ? 4 : 9) : 1;
+                    const int ntap = c < p.kchunks ? (SUBPIX == 1 ? 4 : (SUBPIX == 2 ? 6 : 9)) : 1;
                     if constexpr (TG == 1) {
                         for (int t = 0; t < ntap; ++t) {
                             PNPF_TIMED_WAIT(&b_full[bslot], bphase, c_bfull);
                             tc_fence_after();
                             int kh, kw;
-                            if constexpr (SUBPIX) {
+                            if constexpr (SUBPIX == 1) {
                                 kh = p.sp_a + (t >> 1);
                                 kw = p.sp_b + (t & 1);
+                            } else if constexpr (SUBPIX == 2) {
+                                kh = p.sp_a + t / 3;
+                                kw = t - 3 * (t / 3);
                             } else {
                                 const int tap = ntap == 9 ? (t + tap_rot) % 9 : 4;
                                 kh = tap / 3;
@@ -267,8 +277,8 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (elect_one_sync()) {
                                 for (int j = 0; j < ng; ++j) {
                                     const int t = t0 + j;
-                                    const int tap = ntap == 9 ? t : 4;
-                                    const int kh = tap / 3, kw = tap - 3 * kh;
+                                    const int tap = (ntap == 9 || SUBPIX == 2) ? t : 4;
+                                    const int kh = tap / 3 + (SUBPIX == 2 ? p.sp_a : 0), kw = tap - 3 * (tap / 3);
                                     const uint64_t adesc = make_smem_desc<128>(pa + static_cast<uint32_t>((kh * p.P + kw + a_shift) * 128));
                                     const uint64_t bdesc = make_smem_desc<128>(pb + static_cast<uint32_t>(j * Cfg::B_BYTES));
 #pragma unroll
@@ -317,7 +327,9 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int o = o0 + m;
             const int h = o / p.P, wp = o - h * p.P;
             const bool valid = (h < p.H) && (wp < p.W);
-            const long long pix = SUBPIX ? static_cast<long long>(2 * h + p.sp_a) * (2 * p.W) + 2 * wp + p.sp_b      // stride-2 lattice
+            // SUBPIX 1: stride-2 lattice of phase (a, b); SUBPIX 2: this warp set's column half IS column phase b
+            const int sp_b = SUBPIX == 2 ? (warp >= 7 ? 1 : 0) : p.sp_b;
+            const long long pix = SUBPIX ? static_cast<long long>(2 * h + p.sp_a) * (2 * p.W) + 2 * wp + sp_b
                                          : static_cast<long long>(h) * p.W + wp;
             {
                 const long long _t0 = PNPF_CLK();
@@ -328,7 +340,10 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-            for (int c0 = col_lo; c0 < col_lo + BN / 2; c0 += 32) epilogue_chunk32(p.epi, t_addr, img, pix, valid, c0, lane);
+            for (int c0 = col_lo; c0 < col_lo + BN / 2; c0 += 32) {
+                if constexpr (SUBPIX == 2) epilogue_chunk32(p.epi, t_addr + col_lo, img, pix, valid, c0 - col_lo, lane);   // channel = column - b C_out
+                else epilogue_chunk32(p.epi, t_addr, img, pix, valid, c0, lane);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

@@ -387,6 +387,11 @@ extern "C" int pnpf_finalize_weights(pnpf_engine* e) {
                         act16* ds = pk.b16(p + ".w_sp" + std::to_string(ph), (size_t)np * 4 * L.in_ch);
                         pack_conv_weight(ds, f.data(), L.out_ch, L.in_ch, 2, np, L.in_ch, nullptr, 0, 1.f);
                     }
+                    if (2 * np <= 256 && np == L.out_ch)            // two column phases per launch (SUBPIX = 2): [2*C_out][6*Cin] per row parity
+                        for (int a = 0; a < 2; ++a) {
+                            act16* ds = pk.b16(p + ".w_sp2a" + std::to_string(a), (size_t)2 * np * 6 * L.in_ch);
+                            pack_subpixel_pair_weights(ds, W(e, p + ".weight").data(), L.out_ch, L.in_ch, a);
+                        }
                 }
                 break;
             }
@@ -590,7 +595,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
             fprintf(stderr, "plan: %-44s %4dx%-4d Cin=%-3d C2=%-3d N=%-3d %s\n", name.c_str(), d.Hout, d.Wout, d.Cin, d.C2, d.n_valid, buf);
         }
         if (real) { if (int rc = prepare_conv(o.tc, d)) return rc; }
-        o.flops = 2.0 * d.Hout * d.Wout * (double)d.n_valid * ((double)(d.subpix ? 4 : d.ksize * d.ksize) * d.Cin + ((d.x2 && !d.x2_identity) ? d.C2 : 0));
+        o.flops = 2.0 * d.Hout * d.Wout * (double)d.n_valid * ((double)(d.subpix == 2 ? 8 : (d.subpix ? 4 : d.ksize * d.ksize)) * d.Cin + ((d.x2 && !d.x2_identity) ? d.C2 : 0));
         o.bytes = 2.0 * d.Hin * d.Win * d.Cin + (d.x2 ? 2.0 * d.Hout * d.Wout * d.C2 : 0.0) +   // Cin / C2 are concat totals
                   (d.residual ? 2.0 * d.Hout * d.Wout * d.n_valid : 0.0) +
                   (d.out_mode == 0 ? 2.0 : 4.0) * d.Hout * d.Wout * d.n_valid;
@@ -809,6 +814,22 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                     d.x = h.p; d.Hin = d.Win = d.Hout = d.Wout = side; d.Cin = L.in_ch; d.x_pitch = L.in_ch;
                     d.N_pad = round_n(L.out_ch); d.ksize = 3; d.stride = 1; d.subpix = 1;
                     d.out_mode = 0; d.out_img_stride = (long long)so * so * L.out_ch; d.out_row_stride = L.out_ch; d.n_valid = L.out_ch;
+                    // two column phases per launch (SUBPIX = 2: 2 x 3 taps, N = 2 C_out) when 2 C_out fits one MMA / the double-buffered TMEM
+                    static const bool no_pair_phase = getenv("PNPF_NO_SUBPIX2") != nullptr;      // A/B switch (tools/ab_env.py)
+                    ConvDesc d2 = d;
+                    d2.subpix = 2; d2.N_pad = 2 * round_n(L.out_ch);
+                    if (!no_pair_phase && round_n(L.out_ch) == L.out_ch && d2.N_pad <= 256 && patchconv_eligible(d2)) {
+                        Act y = new_h(L.out_ch, so, false);
+                        d2.out = y.p; d2.stats_out = y.stats;
+                        for (int a = 0; a < 2; ++a) {
+                            d2.sp_a = a; d2.sp_b = 0;
+                            if (real) { d2.w = wptr<act16>(e, p + ".w_sp2a" + std::to_string(a)); d2.bias = wptr<float>(e, p + ".b"); }
+                            const std::string nm = a == 1 ? p : p + ".rows0";
+                            if (int rc = add_conv(nm, d2, a == 1 ? y.p : nullptr, y.C, so)) return rc;
+                        }
+                        h = y;
+                        break;
+                    }
                     if (patchconv_eligible(d)) {
                         Act y = new_h(L.out_ch, so, false);
                         d.out = y.p; d.stats_out = y.stats;

@@ -41,4 +41,4 @@ def test_unet_with_subpixel_up_matches_oracle():
     assert torch.isfinite(v).all()
     rel = ((v - ref).norm() / ref.norm()).item()
     assert rel < 4e-2, rel
-    assert sum("subpix" in s for s in impls) == 12, "the sub-pixel plan (3 up convs x 4 phases) was not selected"
+    assert sum("subpix" in s for s in impls) == 8, "the sub-pixel plan (4 single phases at C_out = 256, 2 x two-phase launches at 128 and 64) was not selected"
