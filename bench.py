@@ -298,7 +298,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     net = synth.NETS[c["net"]]
     side, B, S, T = net["input_height"], c["b_per_gpu"], c["S"], c["T"]
