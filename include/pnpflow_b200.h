@@ -174,6 +174,10 @@ int pnpf_gn_conv2d_nhwc(const void* xa, int Ca, const void* xb, int Cb, int B, i
  * host_w [Cout,Cin,3,3] folded into the 2x2 weights host_out [Cout,Cin,2,2] that output pixels (2h+a, 2w+b) apply to the
  * low-resolution pixels (h-1+a+i, w-1+b+j).  Host-only (no GPU needed). */
 int pnpf_fold_subpixel_weights(const float* host_w, int Cout, int Cin, int a, int b, float* host_out);
+/* The packed operand of the two-column-phase launch for output-row parity a (0 / 1): host_out [2*Cout][6*Cin] (fp16 values
+ * widened to fp32): row b*Cout + o, K index (i*3 + c)*Cin + ch holds W_ab[o][ch][i][c - b] when c - b is 0 or 1, else 0, so that
+ * out[(2h+a, 2w+b), o] = sum_{i,c,ch} host_out[b*Cout+o][(i*3+c)*Cin+ch] * x[h-1+a+i, w-1+c, ch].  Host-only (no GPU needed). */
+int pnpf_pack_subpixel_pair_weights(const float* host_w, int Cout, int Cin, int a, float* host_out);
 /* conv3x3(nearest_x2(x)) + bias computed as four sub-pixel phases on the low-resolution tensor (patch-streaming kernel,
  * the form the U-Net plan uses for the three up convs).  x: device fp16 [B,H,W,Cin]; out: device fp16 [B,2H,2W,Cout];
  * W <= 128, Cin % 64 == 0, Cout in {64,128,256}.  Synchronous. */

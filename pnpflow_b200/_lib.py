@@ -62,6 +62,7 @@ SYMBOLS = {
     "pnpf_step": (_I, [_VP, C.POINTER(OperatorC), _I, _VP, _VP, _VP, _F, _F, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "pnpf_conv2d_nhwc": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _I, _VP]),
     "pnpf_gn_conv2d_nhwc": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _I, _I, _VP, _I, _VP]),
+    "pnpf_pack_subpixel_pair_weights": (_I, [_VP, _I, _I, _I, _VP]),
     "pnpf_gemm_nt": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "pnpf_attn_core_nhwc": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "pnpf_fold_subpixel_weights": (_I, [_VP, _I, _I, _I, _I, _VP]),

@@ -91,6 +91,14 @@ extern "C" int pnpf_fold_subpixel_weights(const float* host_w, int Cout, int Cin
     return 0;
 }
 
+extern "C" int pnpf_pack_subpixel_pair_weights(const float* host_w, int Cout, int Cin, int a, float* host_out) {
+    PNPF_REQUIRE(host_w && host_out && Cout > 0 && Cin > 0 && (a == 0 || a == 1), "pack_subpixel_pair_weights: bad arguments");
+    std::vector<act16> packed((size_t)2 * Cout * 6 * Cin);
+    pack_subpixel_pair_weights(packed.data(), host_w, Cout, Cin, a);
+    for (size_t i = 0; i < packed.size(); ++i) host_out[i] = __half2float(packed[i]);
+    return 0;
+}
+
 extern "C" int pnpf_upconv2x_nhwc(const void* x, int B, int H, int W, int Cin, const float* host_w, const float* host_bias, int Cout,
                                   void* out, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);

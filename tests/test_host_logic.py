@@ -126,7 +126,7 @@ def test_as_engine_operator_accepts_foreign_plugins():
 def test_subpixel_weight_fold_equals_nearest_upsample_plus_conv3x3():
     """models.py:41-47 (Upsample = F.interpolate(scale 2, nearest) -> 3x3 conv) restated as four 2x2 convolutions on the
     low-resolution tensor with the weights folded by the C ABI's host-side pnpf_fold_subpixel_weights (the opt-in
-    PNPF_SUBPIXEL_UP=1 plan): output pixel (2h+a, 2w+b) = sum_ij W_ab[i,j] * x[h-1+a+i, w-1+b+j]."""
+    sub-pixel plan of the up convs): output pixel (2h+a, 2w+b) = sum_ij W_ab[i,j] * x[h-1+a+i, w-1+b+j]."""
     import torch.nn.functional as F
     from pnpflow_b200 import _lib
     lib = _lib.load()
@@ -203,3 +203,30 @@ def test_scatter_gather_noise_and_masks_world2_gloo(B):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_subpixel_pair_weight_packing_equals_nearest_upsample_plus_conv3x3():
+    """The operand of the two-column-phase launch (SUBPIX = 2 of pnpf_patchconv.cuh: both column phases b of an output-row parity a as
+    a 2 x 3-tap convolution with N = 2*Cout): evaluated as a plain sum on the CPU it must reproduce models.py:41-47."""
+    import torch.nn.functional as F
+    from pnpflow_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(6)
+    O, I, H, W = 4, 3, 5, 6
+    w = (torch.randn(O, I, 3, 3, generator=g) * 0.25).half().float()            # fp16-exact weights; the folded sums round once more
+    x = torch.randn(2, I, H, W, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w.double(), padding=1)
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for a in (0, 1):
+        packed = torch.empty(2 * O, 6 * I, dtype=torch.float32)
+        _lib.check(lib.pnpf_pack_subpixel_pair_weights(w.contiguous().data_ptr(), O, I, a, packed.data_ptr()))
+        wp = packed.double().view(2, O, 2, 3, I)                                  # [b][o][i][c][ch]
+        for b in (0, 1):
+            acc = torch.zeros(2, O, H, W, dtype=torch.float64)
+            for i in (0, 1):
+                for c in (0, 1, 2):
+                    patch = xp[:, :, a + i:a + i + H, c:c + W]                    # x[h-1+a+i, w-1+c]
+                    acc += torch.einsum("oc,bchw->bohw", wp[b, :, i, c, :], patch)
+            out[:, :, a::2, b::2] = acc
+    assert (out - ref).abs().max() < 2e-3          # fp16 rounding of the folded (summed) weights

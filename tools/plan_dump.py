@@ -1,6 +1,6 @@
 """Print the U-Net launch plan (which kernel every conv of the net gets) WITHOUT a GPU: the size-query plan of
 pnpf_workspace_bytes runs the same shape analysis as the real plan.
-usage: [PNPF_PATCH_GN=1] [PNPF_SUBPIXEL_UP=1] python tools/plan_dump.py [afhq256|celeba128] [batch]"""
+usage: [PNPF_NO_SUBPIX2=1 | PNPF_NO_SUBPIXEL=1 | ...] python tools/plan_dump.py [afhq256|celeba128] [batch]"""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 os.environ["PNPF_PLAN_DUMP"] = "1"
