@@ -7,8 +7,8 @@ res = []
 for rowb in (128, 64):
     K = rowb // 2
     g = torch.Generator().manual_seed(0)
-    A = torch.randn(256, K, generator=g).cuda().half()
-    B = torch.randn(32, K, generator=g).cuda().half()
+    A = torch.randn(256, K, generator=g).cuda().bfloat16()
+    B = torch.randn(32, K, generator=g).cuda().bfloat16()
     for off in (0, 1, 2, 3, 4, 7, 8, 9, 13):
         for mode in ("zero", "addr"):
             base_off = 0 if mode == "zero" else ((off * rowb) >> 7) & 7
