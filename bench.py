@@ -126,6 +126,18 @@ def ncu_traffic(kernel_prefix):
     return None, None
 
 
+def ncu_durations(prefix):
+    """gpu__time_duration of the committed ncu capture of the per-pixel kernels (tools/ncu_pnp.py: cfg4 sizes, 16 images, S = 5)."""
+    tp = os.path.join(ROOT, "profiles", "r02_pnp_pixel_ncu.json")
+    if not os.path.exists(tp):
+        return []
+    try:
+        return [float(l[k]) for l in json.load(open(tp))["launches"] if l.get("kernel", "").startswith(prefix)
+                for k in l if k.startswith("gpu__time_duration")]
+    except Exception:
+        return []
+
+
 def time_hbm_kernels(sess, x, y, pk, K=10):
     """The per-pixel kernels of one PnP step timed ALONE with CUDA events, L2 flushed (a 256 MB write)
     before every launch; achieved = algorithmic bytes / time against the measured copy bandwidth."""
@@ -158,6 +170,12 @@ def time_hbm_kernels(sess, x, y, pk, K=10):
         row = {"kernel": name, "ms": ms, "algorithmic_bytes": by, "achieved": by / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                "frac": by / (ms * 1e-3) / 1e9 / pk["hbm"], "traffic": tr, "traffic_source": src,
                "note": "one launch timed alone with CUDA events (includes ~2 us of launch latency on a 10-30 us kernel)"}
+        # the same kernel under ncu (no launch latency in the number; only comparable at the captured size = cfg4's 16 images, S = 5)
+        if sess.n == 16 * 3 * 256 * 256 and S == 5 and (opname == "Superresolution" or not name.startswith("datafit")):
+            d = ncu_durations({"datafit_step": "datafit_diag", "interp": "interp", "push_accum": "push_accum"}[name.split("[")[0]])
+            if d:
+                row["ncu_duration_us"] = d[0]
+                row["frac_at_ncu_duration"] = by / (d[0] * 1e-6) / 1e9 / pk["hbm"]
         if opname == "GaussianDeblurring" and name.startswith("datafit"):
             row["note"] = ("two launches of the separable circular 61-tap filter: 244 FMA per pixel out of shared memory — bound by the "
                            "shared-memory pipe, not by HBM; the HBM fraction is reported for completeness")
