@@ -100,7 +100,7 @@ static bool patchconv_shape(const ConvDesc& d, PatchShape& r) {
     static const bool off = getenv("PNPF_NO_PATCH") != nullptr;          // A/B switch (tools/ab_env.py)
     if (off || !d.allow_rowconv || d.ksize != 3 || d.stride != 1 || d.Wout != d.Win || d.Hout != d.Hin || d.Wout > 128) return false;
     if (!(d.N_pad == 64 || d.N_pad == 128 || d.N_pad == 256) || d.c_base != 0 || d.xb || d.x2b || d.gn_gamma) return false;
-    if (d.Cin % 64 || d.C2 % 64 || d.Cin < 64) return false;
+    if (d.Cin % 64 || d.C2 % 64 || d.Cin < 64 || d.x_cvalid) return false;
     if (d.subpix && (d.x2 || d.C2 || d.residual || d.out_mode != 0)) return false;
     if (d.subpix == 2 && (d.N_pad != 2 * d.n_valid || d.N_pad > 256)) return false;       // two column phases: 2 * C_out accumulator columns
     r.P = d.Wout + 2;
@@ -161,7 +161,7 @@ static int try_prepare_rowconv(TcOp& op, const ConvDesc& d) {
     fill_epi(r.epi, d);
     op.kind = 1; op.BK = BK; op.BN = BN;
     const long long Ktot = 9LL * d.Cin + (d.x2 ? d.C2 : 0);
-    if (int e = make_act_tmap(&op.tmA, d.x, d.Cin - d.Cb, d.x_pitch, d.Win, d.Hin, d.B, BK, 130, 1, 1)) return e;
+    if (int e = make_act_tmap(&op.tmA, d.x, d.x_cvalid > 0 ? d.x_cvalid : d.Cin - d.Cb, d.x_pitch, d.Win, d.Hin, d.B, BK, 130, 1, 1)) return e;
     op.tmAb = op.tmA;
     if (d.Cb) { if (int e = make_act_tmap(&op.tmAb, d.xb, d.Cb, d.xb_pitch, d.Win, d.Hin, d.B, BK, 130, 1, 1)) return e; }
     op.tmA2 = op.tmA;
@@ -246,7 +246,7 @@ int prepare_conv(TcOp& op, const ConvDesc& d) {
     op.BK = BK;
     op.BN = BN;
     const long long Ktot = (long long)p.ntaps * d.Cin + (d.x2 ? d.C2 : 0);
-    if (int e = make_act_tmap(&op.tmA, d.x, d.c_base + d.Cin, d.x_pitch, d.Win, d.Hin, d.B, BK, p.TW, p.TH, d.stride)) return e;
+    if (int e = make_act_tmap(&op.tmA, d.x, d.x_cvalid > 0 ? d.x_cvalid : d.c_base + d.Cin, d.x_pitch, d.Win, d.Hin, d.B, BK, p.TW, p.TH, d.stride)) return e;
     if (d.x2) {
         if (int e = make_act_tmap(&op.tmA2, d.x2, d.C2, d.x2_pitch, d.Wout, d.Hout, d.B, BK, p.TW, p.TH, 1)) return e;
     } else {

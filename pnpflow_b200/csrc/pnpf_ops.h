@@ -29,6 +29,8 @@ struct ConvDesc {
     int B = 0, Hin = 0, Win = 0, Cin = 0;
     long long x_pitch = 0;
     int c_base = 0;
+    int x_cvalid = 0;               // > 0: the buffer holds only this many channels (pitch >= x_cvalid); channels [x_cvalid, Cin) of the
+                                    // K chunk are zero-filled by the TMA unit (out-of-bounds fill) — the 3-channel network input
     // optional second source for a fused 1x1 (extra K) at OUTPUT resolution: fp16 NHWC [B][Hout][Wout][x2_pitch]
     const act16* x2 = nullptr;
     int C2 = 0;

@@ -15,7 +15,11 @@ using namespace pnpf;
 
 namespace {
 
-constexpr int CIN_PAD = 32;       // input image channels are zero-padded to one 32-channel K chunk
+constexpr int CIN_PAD = 32;       // K chunk of begin_conv: the image channels are zero-padded to 32 (weights) ...
+// ... but the bf16/fp16 NHWC copy of the network input only STORES cin_store() channels per pixel (8: one 16-byte vector); the TMA
+// unit zero-fills channels [cin_store, 32) of every box (ConvDesc::x_cvalid), so the shim writes and begin_conv reads 16 instead of
+// 64 bytes per pixel (335 -> 84 MB per evaluation at 256^2, batch 80)
+static int cin_store(const pnpf_unet_config& c) { return c.input_channels <= 8 ? 8 : 16; }
 constexpr int GROUPS = 32;        // models.py:33-38
 constexpr float GN_EPS = 1e-6f;
 
@@ -537,7 +541,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
                 break;
         }
     }
-    act16* in_nhwc = A.take<act16>((size_t)Bm * side0 * side0 * CIN_PAD);
+    act16* in_nhwc = A.take<act16>((size_t)Bm * side0 * side0 * cin_store(c));
     float* tproj = A.take<float>((size_t)Bm * e->total_proj);
     double* stats = A.take<double>((size_t)Bm * stats_elems);
     const size_t stats_bytes = (size_t)Bm * stats_elems * sizeof(double);
@@ -596,7 +600,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
         }
         if (real) { if (int rc = prepare_conv(o.tc, d)) return rc; }
         o.flops = 2.0 * d.Hout * d.Wout * (double)d.n_valid * ((double)(d.subpix == 2 ? 8 : (d.subpix ? 4 : d.ksize * d.ksize)) * d.Cin + ((d.x2 && !d.x2_identity) ? d.C2 : 0));
-        o.bytes = 2.0 * d.Hin * d.Win * d.Cin + (d.x2 ? 2.0 * d.Hout * d.Wout * d.C2 : 0.0) +   // Cin / C2 are concat totals
+        o.bytes = 2.0 * d.Hin * d.Win * (d.x_cvalid > 0 ? d.x_cvalid : d.Cin) + (d.x2 ? 2.0 * d.Hout * d.Wout * d.C2 : 0.0) +   // Cin / C2 are concat totals
                   (d.residual ? 2.0 * d.Hout * d.Wout * d.n_valid : 0.0) +
                   (d.out_mode == 0 ? 2.0 : 4.0) * d.Hout * d.Wout * d.n_valid;
         flops += o.flops;
@@ -623,8 +627,8 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
     };
 
     { Op o; o.kind = Op::MEMSET; o.name = "zero_gn_stats"; ops.push_back(o); }
-    { Op o; o.kind = Op::IN_SHIM; o.name = "input_nchw_to_nhwc"; o.bytes = (4.0 * c.input_channels + 2.0 * CIN_PAD) * side0 * side0;
-      set_out(o, in_nhwc, CIN_PAD, side0); ops.push_back(o); }
+    { Op o; o.kind = Op::IN_SHIM; o.name = "input_nchw_to_nhwc"; o.bytes = (4.0 * c.input_channels + 2.0 * cin_store(c)) * side0 * side0;
+      set_out(o, in_nhwc, cin_store(c), side0); ops.push_back(o); }
     { Op o; o.kind = Op::TEMB; o.name = "time_embedding"; ops.push_back(o); }
 
     std::vector<Act> hs;
@@ -637,7 +641,7 @@ static int build_plan(pnpf_engine* e, uint8_t* base, int Bm, size_t* need) {
             case LayerSpec::CONV: {
                 Act y = new_h(L.out_ch, side, true);
                 ConvDesc d;
-                d.x = in_nhwc; d.Hin = d.Win = d.Hout = d.Wout = side; d.Cin = CIN_PAD; d.x_pitch = CIN_PAD;
+                d.x = in_nhwc; d.Hin = d.Win = d.Hout = d.Wout = side; d.Cin = CIN_PAD; d.x_pitch = cin_store(c); d.x_cvalid = cin_store(c);
                 d.N_pad = round_n(L.out_ch); d.ksize = 3; d.stride = 1;
                 if (real) { d.w = wptr<act16>(e, p + ".w"); d.bias = wptr<float>(e, p + ".b"); }
                 d.stats_out = y.stats;
@@ -938,7 +942,7 @@ static int run_ops(pnpf_engine* e, const float* x, const float* t, float* v, int
                 PNPF_CHECK_CUDA(cudaMemsetAsync(e->stats_arena, 0, e->stats_bytes, st));
                 break;
             case Op::IN_SHIM:
-                rc = launch_nchw_to_nhwc_pad(x, batch, c.input_channels, HW0, e->in_nhwc, CIN_PAD, st);
+                rc = launch_nchw_to_nhwc_pad(x, batch, c.input_channels, HW0, e->in_nhwc, cin_store(c), st);
                 break;
             case Op::TEMB: {
                 TembWeights w;
