@@ -165,10 +165,8 @@ int launch_conv_gemm(int BK, int BN, const CUtensorMap& tmA, const CUtensorMap& 
     const bool pairable = p.b_batched ? (p.tiles_h * p.tiles_w) % 2 == 0 : m_tiles % 2 == 0;
     // Measured (profiles/r01_ab_experiments.md): with pairs the MMA issue runs at the tensor rate and the kernel becomes bound by
     // the L2 -> shared-memory fill (every input pixel is fetched once per tap): BN = 256 gains 5-6 %, BN = 128 (activation
-    // traffic dominates, not halved by pairing) loses 4 % -> pairs for BN = 256 only (PNPF_PAIR_128=1 forces them for 128).
-    static const bool pair128 = getenv("PNPF_PAIR_128") != nullptr;
+    // traffic dominates, not halved by pairing) loses 4 % -> pairs for BN = 256 only.
     if (!no_pair && BK == 64 && pairable) {
-        if (BN == 128 && pair128) return launch_t<64, 128, true>(tmA, tmA2, tmB_half, p, stream);
         if (BN == 256) return launch_t<64, 256, true>(tmA, tmA2, tmB_half, p, stream);
     }
 #define PNPF_CASE(bk, bn) \
