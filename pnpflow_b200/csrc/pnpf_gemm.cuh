@@ -239,7 +239,10 @@ struct GemmCfg {
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int THREADS = 192;
+    // warps: 0 TMA producer, 1 MMA issuer, 2..5 epilogue set 0, 6..9 epilogue set 1 (BN >= 64: each set drains BN / 2 columns —
+    // the epilogue is a per-warp latency chain and a K = 256 1x1 conv is only 16 MMAs per tile, so one set was the bottleneck 8:1)
+    static constexpr int EPI_SETS = BN >= 64 ? 2 : 1;
+    static constexpr int THREADS = (2 + 4 * EPI_SETS) * 32;
     static_assert(BK == 32 || BK == 64, "BK");
     static_assert(BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
     static_assert(!PAIR || BN >= 128, "CTA pairs are used for the wide tiles only");
@@ -296,7 +299,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], PAIR ? 8 : 4);          // pair: the epilogue warps of BOTH CTAs release the leader's accumulator
+            mbar_init(&tempty_bar[a], (PAIR ? 8 : 4) * Cfg::EPI_SETS);          // pair: the epilogue warps of BOTH CTAs release the leader's accumulator
         }
         fence_barrier_init();
     }
@@ -404,7 +407,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
     } else {
-        // ===================== epilogue warps 2..5 =====================
+        // ===================== epilogue warps 2..5 (and 6..9: second half of the columns) =====================
         const int quarter = warp & 3;                             // TMEM lane quarter this warp may access
         const int m = quarter * 32 + lane;                        // accumulator row == pixel within the tile
         const int th = m / p.TW, tw = m - th * p.TW;
@@ -427,6 +430,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+            if constexpr (Cfg::EPI_SETS == 2) {
+                const int set = (warp - 2) >> 2;
+#pragma unroll 1
+                for (int c0 = set * (BN / 2); c0 < (set + 1) * (BN / 2); c0 += 32)      // t_addr - nt * BN: chunk32 adds the GLOBAL column
+                    epilogue_chunk32(p.epi, t_addr - static_cast<uint32_t>(nt * BN), img, pix, valid, nt * BN + c0, lane);
+            } else {
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 uint32_t r[16];
@@ -444,6 +453,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     atomicAdd(p.epi.stats + (static_cast<long long>(img) * p.epi.n_valid + c) * 2 + (lane & 1), static_cast<double>(tot));
                 }
                 if (act) epilogue_store16(p.epi, img, pix, col0, v);
+            }
             }
             tc_fence_before();
             __syncwarp();

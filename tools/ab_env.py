@@ -1,5 +1,5 @@
 """A/B harness on ONE box: time one U-Net evaluation (AFHQ 256^2 net, batch 80 by default) under several environment settings
-and/or library builds, each variant in its own process, the list run twice.
+and/or library builds, each variant in its own process, the list run twice.  AB_NET=celeba128 AB_BATCH=320 times the 128^2 net.
 usage: python tools/ab_env.py "NAME:ENV1=1,ENV2=1[,PNPF_LIB=ab/x.so]" ...      (a bare NAME: is the default build)"""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,9 +8,10 @@ import sys
 sys.path.insert(0, %r)
 import torch, pnpflow_b200 as P
 from pnpflow_b200 import synth
-net = synth.NETS["afhq256"]; B = int(sys.argv[2])
+import os
+net = synth.NETS[os.environ.get("AB_NET", "afhq256")]; B = int(sys.argv[2]); side = net["input_height"]
 eng = P.UNetEngine(net, synth.random_state_dict(net), max_batch=B)
-x = torch.randn(B, 3, 256, 256, device="cuda"); t = torch.full((B,), 0.5, device="cuda")
+x = torch.randn(B, 3, side, side, device="cuda"); t = torch.full((B,), 0.5, device="cuda")
 xb, tb, v, replay = eng.graphed(B)          # CUDA-graph replay = what PnPFlowSession.step runs
 xb.copy_(x); tb.copy_(t)
 for _ in range(3): replay()
