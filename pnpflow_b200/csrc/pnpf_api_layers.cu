@@ -72,6 +72,8 @@ extern "C" int pnpf_conv2d_nhwc(const void* x, int B, int Hin, int Win, int Cin,
             printf("PATCH_DBG tiles %lld | patch producer: total %lld wait_empty %lld | weight producer: total %lld wait_empty %lld | mma: total %lld "
                    "wait_patch %lld wait_weights %lld wait_tempty %lld | epi: total %lld wait_tfull %lld\n", h[2], h[0], h[1], h[12], h[13], h[4], h[5], h[7], h[6],
                    h[8], h[9]);
+        if (op.kind == 2)
+            printf("   epi: tile decode %lld chunks (tcgen05.ld, bias / residual, statistics, stores) %lld fence + arrive %lld\n", h[24], h[25], h[26]);
         if (op.kind == 1)
             printf("   mma: issue %lld commit %lld | epi0: tmem_ld %lld tmem_st+arrive %lld math+stage %lld store %lld stats_flush %lld\n", h[16], h[17], h[18],
                    h[19], h[22], h[23], h[20]);

@@ -458,7 +458,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if constexpr (PAIR) mbar_arrive_cluster(tempty_remote + acc * 8);
+                if constexpr (PAIR) mbar_arrive_cluster(tempty_remote + acc * 8);     // relaxed: see pnpf_ptx.cuh
                 else mbar_arrive(&tempty_bar[acc]);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }

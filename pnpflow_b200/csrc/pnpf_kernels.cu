@@ -280,45 +280,69 @@ int launch_softmax_rows(const float* S, act16* P, long long rows, int L, cudaStr
 // =================================================================================================
 __device__ __forceinline__ float swishf(float x) { return x / (1.f + expf(-x)); }
 
-__global__ void temb_kernel(TembWeights w, const float* __restrict__ t, float* __restrict__ out) {
-    // grid (image, chunk of 256 projection outputs): every block recomputes the two small dense layers (20K MAC)
-    extern __shared__ float sm[];                     // emb[ch] | h[temb_ch] | s[temb_ch]
-    float* emb = sm;
-    float* h = sm + w.ch;
-    float* sv = h + w.temb_ch;
-    const int img = blockIdx.x;
-    const float tt = t[img];
+constexpr int TEMB_IMGS = 8;                          // images per block: every weight load serves 8 images
+__global__ void temb_kernel(TembWeights w, const float* __restrict__ t, int B, float* __restrict__ out) {
+    // grid (group of TEMB_IMGS images, chunk of 256 projection outputs): every block recomputes the two small dense layers of
+    // its images (20K MAC each); per image the arithmetic and its order are those of a one-image block
+    extern __shared__ float sm[];                     // per image: emb[ch] | h[temb_ch] | s[temb_ch]
+    const int per = w.ch + 2 * w.temb_ch;
+    const int img0 = blockIdx.x * TEMB_IMGS;
     const int half = w.ch / 2;
-    for (int i = threadIdx.x; i < w.ch; i += blockDim.x) {
-        const float a = tt * w.freqs[i % half];
-        emb[i] = (i < half) ? sinf(a) : cosf(a);
+    for (int i = threadIdx.x; i < TEMB_IMGS * w.ch; i += blockDim.x) {
+        const int g = i / w.ch, c = i - g * w.ch;
+        const float tt = t[min(img0 + g, B - 1)];
+        const float a = tt * w.freqs[c % half];
+        sm[g * per + c] = (c < half) ? sinf(a) : cosf(a);
     }
     __syncthreads();
     for (int o = threadIdx.x; o < w.temb_ch; o += blockDim.x) {
-        float acc = w.b0[o];
-        for (int k = 0; k < w.ch; ++k) acc = fmaf(__ldg(w.w0_t + k * w.temb_ch + o), emb[k], acc);
-        h[o] = swishf(acc);
+        float acc[TEMB_IMGS];
+#pragma unroll
+        for (int g = 0; g < TEMB_IMGS; ++g) acc[g] = w.b0[o];
+        for (int k = 0; k < w.ch; ++k) {
+            const float wv = __ldg(w.w0_t + k * w.temb_ch + o);
+#pragma unroll
+            for (int g = 0; g < TEMB_IMGS; ++g) acc[g] = fmaf(wv, sm[g * per + k], acc[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < TEMB_IMGS; ++g) sm[g * per + w.ch + o] = swishf(acc[g]);
     }
     __syncthreads();
     for (int o = threadIdx.x; o < w.temb_ch; o += blockDim.x) {
-        float acc = w.b2[o];
-        for (int k = 0; k < w.temb_ch; ++k) acc = fmaf(__ldg(w.w2_t + k * w.temb_ch + o), h[k], acc);
-        sv[o] = swishf(acc);                          // ResidualBlock applies act(temb) before temb_proj (models.py:101)
+        float acc[TEMB_IMGS];
+#pragma unroll
+        for (int g = 0; g < TEMB_IMGS; ++g) acc[g] = w.b2[o];
+        for (int k = 0; k < w.temb_ch; ++k) {
+            const float wv = __ldg(w.w2_t + k * w.temb_ch + o);
+#pragma unroll
+            for (int g = 0; g < TEMB_IMGS; ++g) acc[g] = fmaf(wv, sm[g * per + w.ch + k], acc[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < TEMB_IMGS; ++g)           // ResidualBlock applies act(temb) before temb_proj (models.py:101)
+            sm[g * per + w.ch + w.temb_ch + o] = swishf(acc[g]);
     }
     __syncthreads();
     const int o = blockIdx.y * blockDim.x + threadIdx.x;
     if (o < w.total_proj) {
-        float acc = w.bp[o];
-#pragma unroll 8
-        for (int k = 0; k < w.temb_ch; ++k) acc = fmaf(__ldg(w.wp_t + (long long)k * w.total_proj + o), sv[k], acc);
-        out[(long long)img * w.total_proj + o] = acc;
+        float acc[TEMB_IMGS];
+#pragma unroll
+        for (int g = 0; g < TEMB_IMGS; ++g) acc[g] = w.bp[o];
+#pragma unroll 4
+        for (int k = 0; k < w.temb_ch; ++k) {
+            const float wv = __ldg(w.wp_t + (long long)k * w.total_proj + o);
+#pragma unroll
+            for (int g = 0; g < TEMB_IMGS; ++g) acc[g] = fmaf(wv, sm[g * per + w.ch + w.temb_ch + k], acc[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < TEMB_IMGS; ++g)
+            if (img0 + g < B) out[(long long)(img0 + g) * w.total_proj + o] = acc[g];
     }
 }
 
 int launch_temb(const TembWeights& w, const float* t, int B, float* out, cudaStream_t st) {
-    const size_t smem = (w.ch + 2 * w.temb_ch) * sizeof(float);
-    dim3 grid(B, (w.total_proj + 255) / 256);
-    temb_kernel<<<grid, 256, smem, st>>>(w, t, out);
+    const size_t smem = (size_t)TEMB_IMGS * (w.ch + 2 * w.temb_ch) * sizeof(float);
+    dim3 grid((B + TEMB_IMGS - 1) / TEMB_IMGS, (w.total_proj + 255) / 256);
+    temb_kernel<<<grid, 256, smem, st>>>(w, t, B, out);
     PNPF_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

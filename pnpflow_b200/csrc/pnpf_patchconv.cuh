@@ -319,9 +319,11 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int acc = 0;
         uint32_t acc_phase = 0;
         long long c_tfull = 0;
+        [[maybe_unused]] long long c_top = 0, c_body = 0, c_tail = 0;     // cycle counters (-DPNPF_ROWCONV_CLOCKS builds only)
         const long long c_start = PNPF_CLK();
         const uint32_t tempty_remote = PAIR ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
         for (int u = unit0; u < total_units; u += unit_step) {
+            const long long kt0 = PNPF_CLK();
             int img, o0, h_first;
             decode(u, img, o0, h_first);
             const int o = o0 + m;
@@ -331,11 +333,14 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int sp_b = SUBPIX == 2 ? (warp >= 7 ? 1 : 0) : p.sp_b;
             const long long pix = SUBPIX ? static_cast<long long>(2 * h + p.sp_a) * (2 * p.W) + 2 * wp + sp_b
                                          : static_cast<long long>(h) * p.W + wp;
+            long long kt1;
             {
                 const long long _t0 = PNPF_CLK();
+                c_top += _t0 - kt0;
                 if (lane == 0) mbar_wait(&tfull_bar[acc], acc_phase);
                 __syncwarp();
-                c_tfull += PNPF_CLK() - _t0;
+                kt1 = PNPF_CLK();
+                c_tfull += kt1 - _t0;
             }
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
@@ -344,15 +349,21 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if constexpr (SUBPIX == 2) epilogue_chunk32(p.epi, t_addr + col_lo, img, pix, valid, c0 - col_lo, lane);   // channel = column - b C_out
                 else epilogue_chunk32(p.epi, t_addr, img, pix, valid, c0, lane);
             }
+            const long long kt2 = PNPF_CLK();
+            c_body += kt2 - kt1;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if constexpr (PAIR) mbar_arrive_cluster(tempty_remote + acc * 8);
+                if constexpr (PAIR) mbar_arrive_cluster(tempty_remote + acc * 8);     // relaxed: see pnpf_ptx.cuh
                 else mbar_arrive(&tempty_bar[acc]);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            c_tail += PNPF_CLK() - kt2;
         }
-        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { p.dbg[8] = PNPF_CLK() - c_start; p.dbg[9] = c_tfull; }
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) {
+            p.dbg[8] = PNPF_CLK() - c_start; p.dbg[9] = c_tfull;
+            p.dbg[24] = c_top; p.dbg[25] = c_body; p.dbg[26] = c_tail;
+        }
     }
     tc_fence_before();
     if constexpr (PAIR) {

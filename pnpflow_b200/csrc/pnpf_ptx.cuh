@@ -172,8 +172,18 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
 }
+// Remote arrive of the epilogue warps on the leader CTA's "accumulator drained" barrier.  RELAXED on purpose: the default
+// (.release.cluster) compiles to MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the SYNCS.ARRIVE, i.e. the warp
+// waits for every global store / atomic of its tile to be acknowledged (~ 2000 clocks per tile, cycle counters in
+// profiles/r02_ab_experiments.md section 16) before the MMA issuer may reuse the accumulator.  Nothing written through the generic
+// proxy is handed over by this barrier: the accumulator is in registers once tcgen05.wait::ld has returned, and the tcgen05 fences
+// on both sides order the tensor-memory accesses.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+#ifdef PNPF_RELEASE_CLUSTER_ARRIVE
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {   // the same warp of BOTH CTAs, same dst offset

@@ -18,8 +18,10 @@ def timed(fn):
     print(f"    {e0.elapsed_time(e1):.3f} ms (incl. host-side weight packing of the layer API)", flush=True)
 
 
+# DBG_SHAPES="H,W,Cin,Cout,C2,res;..." replaces the built-in list of plain convs (and skips the fused-GroupNorm variants)
+CUSTOM = [tuple(int(v) for v in sh.split(",")) for sh in os.environ.get("DBG_SHAPES", "").split(";") if sh]
 print("=== plain convs: B H W Cin Cout C2 res", flush=True)
-for (H, W, Cin, Cout, C2, res) in () if ONLY_GN else ((256, 256, 32, 32, 0, 0), (256, 256, 32, 32, 0, 1), (256, 256, 32, 32, 32, 0), (256, 256, 64, 32, 0, 0),
+for (H, W, Cin, Cout, C2, res) in () if ONLY_GN else CUSTOM if CUSTOM else ((256, 256, 32, 32, 0, 0), (256, 256, 32, 32, 0, 1), (256, 256, 32, 32, 32, 0), (256, 256, 64, 32, 0, 0),
                                    (128, 128, 64, 64, 0, 0), (128, 128, 64, 64, 0, 1), (128, 128, 64, 64, 64, 0), (128, 128, 128, 64, 0, 0),
                                    (128, 128, 64, 64, 128, 0),
                                    (64, 64, 128, 128, 0, 0), (64, 64, 128, 128, 0, 1), (64, 64, 256, 128, 0, 0), (64, 64, 128, 128, 256, 0),
@@ -34,7 +36,7 @@ for (H, W, Cin, Cout, C2, res) in () if ONLY_GN else ((256, 256, 32, 32, 0, 0), 
     timed(lambda: _lib.check(lib.pnpf_conv2d_nhwc(x.data_ptr(), B, H, W, Cin, w.data_ptr(), None, Cout, 3, 1, x2.data_ptr() if C2 else None, C2,
                                                   w2.data_ptr() if C2 else None, r.data_ptr() if res else None, out.data_ptr(), 0, None)))
 print("=== fused GroupNorm variants", flush=True)
-for (H, W, Ca, Cb, Cout) in ((256, 256, 32, 0, 32), (256, 256, 32, 32, 32), (256, 256, 64, 32, 32), (128, 128, 64, 0, 64), (128, 128, 64, 64, 64),
+for (H, W, Ca, Cb, Cout) in () if CUSTOM else ((256, 256, 32, 0, 32), (256, 256, 32, 32, 32), (256, 256, 64, 32, 32), (128, 128, 64, 0, 64), (128, 128, 64, 64, 64),
                              (128, 128, 64, 32, 64)):
     xa = torch.randn(B, H, W, Ca, device="cuda").half()
     xb = torch.randn(B, H, W, Cb, device="cuda").half() if Cb else None
