@@ -269,23 +269,34 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (++bslot == p.nb) { bslot = 0; bphase ^= 1; }
                         }
                     } else {
-                        for (int t0 = 0; t0 < ntap; t0 += TG) {
+                        static_assert(TG == 3, "a weight-ring slot holds one kernel row");
+                        constexpr uint32_t dhi = smem_desc_hi<128>();
+                        for (int g = 0, t0 = 0; t0 < ntap; ++g, t0 += TG) {
                             const int ng = min(TG, ntap - t0);
                             PNPF_TIMED_WAIT(&b_full[bslot], bphase, c_bfull);
                             tc_fence_after();
-                            const uint32_t pb = smem_u32(b_ring + bslot * (TG * Cfg::B_BYTES));
                             if (elect_one_sync()) {
-                                for (int j = 0; j < ng; ++j) {
-                                    const int t = t0 + j;
-                                    const int tap = (ntap == 9 || SUBPIX == 2) ? t : 4;
-                                    const int kh = tap / 3 + (SUBPIX == 2 ? p.sp_a : 0), kw = tap - 3 * (tap / 3);
-                                    const uint64_t adesc = make_smem_desc<128>(pa + static_cast<uint32_t>((kh * p.P + kw + a_shift) * 128));
-                                    const uint64_t bdesc = make_smem_desc<128>(pb + static_cast<uint32_t>(j * Cfg::B_BYTES));
+                                // first tap of the group: kernel row g (SUBPIX 2: sp_a + g), column 0; the fused 1x1 chunk has the
+                                // centre tap only.  Descriptor low words advance by 8 per pixel row of the patch (128 B), by
+                                // B_BYTES / 16 per weight tile and by 2 per 16-element K step: compile-time immediates below.
+                                const int kh0 = ntap == 1 ? 1 : g + (SUBPIX == 2 ? p.sp_a : 0);
+                                const int kw0 = ntap == 1 ? 1 : 0;
+                                const uint32_t a_lo = smem_desc_lo<128>(pa) + static_cast<uint32_t>((kh0 * p.P + kw0 + a_shift) * 8);
+                                const uint32_t b_lo = smem_desc_lo<128>(smem_u32(b_ring + bslot * (TG * Cfg::B_BYTES)));
+                                const uint32_t accum0 = (c | g) ? 1u : 0u;
+                                if (ng == TG) {
 #pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk) {
-                                        if constexpr (PAIR) umma_f16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
-                                        else umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | t | kk) ? 1u : 0u);
-                                    }
+                                    for (int j = 0; j < TG; ++j)
+#pragma unroll
+                                        for (int kk = 0; kk < 4; ++kk)
+                                            umma_f16_lohi<PAIR>(d_tmem, a_lo + 8 * j + 2 * kk, b_lo + j * (Cfg::B_BYTES >> 4) + 2 * kk, dhi, idesc,
+                                                                (j | kk) ? 1u : accum0);
+                                } else {
+                                    for (int j = 0; j < ng; ++j)
+#pragma unroll
+                                        for (int kk = 0; kk < 4; ++kk)
+                                            umma_f16_lohi<PAIR>(d_tmem, a_lo + 8 * j + 2 * kk, b_lo + j * (Cfg::B_BYTES >> 4) + 2 * kk, dhi, idesc,
+                                                                (j | kk) ? 1u : accum0);
                                 }
                                 const bool last = t0 + ng == ntap;
                                 if constexpr (PAIR) {

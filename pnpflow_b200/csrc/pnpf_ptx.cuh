@@ -241,6 +241,40 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     d |= layout << 61;
     return d;
 }
+// The same descriptor as two 32-bit halves: the high word is a constant and the low word is (address >> 4) plus flags, so the
+// descriptor of a tile at a byte offset `off` inside the same swizzle atom row space is lo + (off >> 4) — ONE 32-bit add per MMA in
+// the issuing thread instead of a 64-bit add with carry (the issuer is a single-thread instruction chain: every instruction it
+// does not execute is ~ 5 clocks per MMA).
+template <int kRowBytes>
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr) {
+    return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
+}
+template <int kRowBytes>
+__host__ __device__ constexpr uint32_t smem_desc_hi() {
+    static_assert(kRowBytes == 128 || kRowBytes == 64, "unsupported swizzle span");
+    return static_cast<uint32_t>((8 * kRowBytes) >> 4) | (1u << 14) | ((kRowBytes == 128 ? 2u : 4u) << 29);
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (PAIR)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
 // Instruction descriptor for kind::f16 with FP16 A/B (both K-major), FP32 accumulator, dense, no negate.
 // [4,6) c_format=1(F32)  [7,10) a_format=0(F16; 1 would be BF16)  [10,13) b_format=0(F16)  [17,23) N>>3  [24,29) M>>4
 __host__ __device__ constexpr uint32_t make_idesc_act16(int M, int N) {
