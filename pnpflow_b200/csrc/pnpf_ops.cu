@@ -100,7 +100,9 @@ static bool patchconv_shape(const ConvDesc& d, PatchShape& r) {
     static const bool off = getenv("PNPF_NO_PATCH") != nullptr;          // A/B switch (tools/ab_env.py)
     if (off || !d.allow_rowconv || d.ksize != 3 || d.stride != 1 || d.Wout != d.Win || d.Hout != d.Hin || d.Wout > 128) return false;
     if (!(d.N_pad == 64 || d.N_pad == 128 || d.N_pad == 256) || d.c_base != 0 || d.xb || d.x2b || d.gn_gamma) return false;
-    if (d.Cin % 64 || d.C2 % 64 || d.Cin < 64 || d.x_cvalid) return false;
+    // channel counts that are odd multiples of 32 ride in 64-channel chunks whose upper half the TMA unit zero-fills (no sub-pixel form)
+    if (d.Cin % 32 || d.C2 % 32 || d.Cin < 32 || d.x_cvalid) return false;
+    if (d.subpix && d.Cin % 64) return false;
     if (d.subpix && (d.x2 || d.C2 || d.residual || d.out_mode != 0)) return false;
     if (d.subpix == 2 && (d.N_pad != 2 * d.n_valid || d.N_pad > 256)) return false;       // two column phases: 2 * C_out accumulator columns
     r.P = d.Wout + 2;
@@ -184,7 +186,7 @@ static int try_prepare_patchconv(TcOp& op, const ConvDesc& d) {
     PatchConvParams& q = op.pp;
     memset(&q, 0, sizeof(q));
     q.H = d.Hout; q.W = d.Wout; q.P = sh.P; q.NR = sh.NR; q.n_img = d.B; q.tiles_per_img = sh.tiles_per_img;
-    q.kchunks = d.Cin / 64; q.kchunks2 = d.x2 ? d.C2 / 64 : 0;
+    q.kchunks = (d.Cin + 63) / 64; q.kchunks2 = d.x2 ? (d.C2 + 63) / 64 : 0; q.cin = d.Cin;
     q.patch_bytes = sh.patch_bytes; q.na = sh.na; q.nb = sh.nb;
     op.patch_nb_pair = sh.nb_pair;
     op.patch_subpix = d.subpix;

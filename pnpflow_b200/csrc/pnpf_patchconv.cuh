@@ -42,7 +42,9 @@ struct PatchConvParams {
     int H, W, P;           // P = W + 2
     int NR;                // patch rows
     int n_img, tiles_per_img;
-    int kchunks;           // C_in / 64
+    int kchunks;           // ceil(C_in / 64): a trailing half chunk (C_in % 64 == 32) is zero-filled by the TMA unit in the patch, so
+                           // whatever the weight box holds beyond this tap's C_in columns (the next tap's weights) is multiplied by 0
+    int cin;               // C_in: the packed K index of (tap, channel) is tap * C_in + channel
     int kchunks2;          // channel chunks of the fused 1x1 source (extra K through tmA2, centre tap only); 0 = none
     int patch_bytes;       // NR * P * 128 rounded up to 1024
     int na, nb;            // ring depths: patches, weight tiles
@@ -166,7 +168,7 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (elect_one_sync()) {
                             // packed K order (pack_conv_weight): (kh, kw, cin) for the 3x3 part, then the 1x1 source channels
                             const int tap = SUBPIX ? t : (t + tap_rot) % 9;      // SUBPIX: packed K order (i, j, cin), 4 or 6 taps
-                            const int k0 = c < p.kchunks ? (tap * p.kchunks + c) * 64 : (9 * p.kchunks + (c - p.kchunks)) * 64;
+                            const int k0 = c < p.kchunks ? tap * p.cin + c * 64 : 9 * p.cin + (c - p.kchunks) * 64;
                             if constexpr (PAIR) {
                                 const uint32_t fb = mapa_u32(smem_u32(&b_full[slot]), 0);
                                 if (rank == 0) mbar_arrive_expect_tx(&b_full[slot], 2 * Cfg::B_BYTES);
@@ -190,13 +192,13 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 const uint32_t fb = mapa_u32(smem_u32(&b_full[slot]), 0);
                                 if (rank == 0) mbar_arrive_expect_tx(&b_full[slot], 2 * ng * Cfg::B_BYTES);
                                 for (int j = 0; j < ng; ++j) {
-                                    const int k0 = c < p.kchunks ? ((t0 + j) * p.kchunks + c) * 64 : (9 * p.kchunks + (c - p.kchunks)) * 64;
+                                    const int k0 = c < p.kchunks ? (t0 + j) * p.cin + c * 64 : 9 * p.cin + (c - p.kchunks) * 64;
                                     tma_load_3d_pair(dst + j * Cfg::B_BYTES, &tmB, fb, k0, static_cast<int>(rank) * Cfg::B_ROWS, 0);
                                 }
                             } else {
                                 mbar_arrive_expect_tx(&b_full[slot], ng * Cfg::B_BYTES);
                                 for (int j = 0; j < ng; ++j) {
-                                    const int k0 = c < p.kchunks ? ((t0 + j) * p.kchunks + c) * 64 : (9 * p.kchunks + (c - p.kchunks)) * 64;
+                                    const int k0 = c < p.kchunks ? (t0 + j) * p.cin + c * 64 : 9 * p.cin + (c - p.kchunks) * 64;
                                     tma_load_3d(dst + j * Cfg::B_BYTES, &tmB, &b_full[slot], k0, 0, 0);
                                 }
                             }

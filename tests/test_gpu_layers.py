@@ -120,6 +120,8 @@ def test_rowconv_fused_groupnorm_two_sources(B, H, W, Ca, Cb, Cout, silu, bf16ou
     (1, 8, 8, 256, 256, 0, False, False), (4, 32, 32, 512, 256, 0, False, True), (2, 64, 64, 128, 128, 256, False, True),
     (5, 16, 16, 256, 256, 384, False, False), (2, 24, 40, 64, 128, 0, True, False), (6, 32, 32, 256, 256, 0, True, True),
     (2, 128, 128, 192, 64, 0, False, True), (3, 64, 64, 64, 64, 192, False, False), (2, 32, 32, 64, 64, 0, True, True),
+    # channel counts that are odd multiples of 32: the trailing half chunk is zero-filled by the TMA unit (128^2 net, level 1)
+    (2, 64, 64, 32, 64, 0, False, True), (3, 64, 64, 96, 64, 0, True, False), (2, 64, 64, 64, 64, 96, False, True), (1, 32, 32, 160, 128, 32, False, False),
 ])
 def test_patchconv_narrow_maps(B, H, W, Cin, Cout, C2, res, bf16out):
     """3x3 stride-1 convs with W <= 128 and C_out 128/256 route to the patch-streaming kernel (padded-linear tiles, one
