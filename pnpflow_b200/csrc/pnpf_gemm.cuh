@@ -120,8 +120,9 @@ __device__ __forceinline__ int colsum16_col(int lane) {
 // both chunks is issued BEFORE the accumulator wait, invalid lanes load from pixel 0 and are masked afterwards (no divergent
 // branch), and the two statistics butterflies are independent instruction streams the scheduler interleaves — the epilogue
 // is a per-warp latency chain, so halving the number of chains per tile is what shortens it.
-__device__ __forceinline__ void epilogue_chunk32(const EpiParams& p, uint32_t t_addr, int img, long long pix, bool valid, int col0, int lane) {
-    const bool on0 = col0 < p.n_valid, on1 = col0 + 16 < p.n_valid;             // warp-uniform
+// values of the two chunks: accumulator + bias + time-embedding row + residual (invalid lanes read pixel 0 and are masked later)
+__device__ __forceinline__ void epilogue_values32(const EpiParams& p, uint32_t t_addr, int img, long long pix, bool valid, int col0, bool on0, bool on1,
+                                                  float (&v)[2][16]) {
     const long long pix_s = valid ? pix : 0;
     float4 b[2][4], bi[2][4];
     uint4 rs[2][2];
@@ -161,7 +162,6 @@ __device__ __forceinline__ void epilogue_chunk32(const EpiParams& p, uint32_t t_
     tmem_ld_x16(t_addr + col0, r[0]);
     tmem_ld_x16(t_addr + col0 + 16, r[1]);
     tmem_ld_wait();
-    float v[2][16];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -182,6 +182,11 @@ __device__ __forceinline__ void epilogue_chunk32(const EpiParams& p, uint32_t t_
             }
         }
     }
+}
+__device__ __forceinline__ void epilogue_chunk32(const EpiParams& p, uint32_t t_addr, int img, long long pix, bool valid, int col0, int lane) {
+    const bool on0 = col0 < p.n_valid, on1 = col0 + 16 < p.n_valid;             // warp-uniform
+    float v[2][16];
+    epilogue_values32(p, t_addr, img, pix, valid, col0, on0, on1, v);
     if (p.stats) {
         const float t0 = warp_colsum16(v[0], valid && on0, lane);
         const float t1 = warp_colsum16(v[1], valid && on1, lane);
@@ -192,6 +197,73 @@ __device__ __forceinline__ void epilogue_chunk32(const EpiParams& p, uint32_t t_
     }
     if (valid && on0) epilogue_store16(p, img, pix, col0, v[0]);
     if (valid && on1) epilogue_store16(p, img, pix, col0 + 16, v[1]);
+}
+
+// The same 32 columns for fp16 NHWC outputs, through a per-warp 2 KB staging tile (32 pixels x 64 bytes, 16-byte chunks XOR-swizzled
+// by (pixel >> 1) & 3: conflict-free in both phases): a lane writes its own pixel's 64 bytes, then reads 16 bytes of pixels
+// rd_pix, 8 + rd_pix, 16 + rd_pix, 24 + rd_pix — so every global store instruction writes 8 whole 64-byte pixel rows (32 LSU
+// transactions per chunk instead of 128), and the GroupNorm statistics are summed in the read phase: a lane holds 8 channels of 4
+// pixels (on the fp16 values the consumer will normalise, like the row kernel), 48 shuffles instead of the 124 + 248 selects of the
+// two butterflies.  pix_rd / vmask_rd: output pixel index and validity of the four pixels this lane stores.
+__device__ __forceinline__ void epilogue_chunk32_staged(const EpiParams& p, uint32_t t_addr, int img, long long pix, bool valid, int col0, int lane,
+                                                        uint32_t stage_w, const int (&pix_rd)[4], uint32_t vmask_rd) {
+    float v[2][16];
+    epilogue_values32(p, t_addr, img, pix, valid, col0, true, true, v);
+    const uint32_t st_wr = stage_w + lane * 64, sw = static_cast<uint32_t>((lane >> 1) & 3);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float* f = &v[k >> 1][(k & 1) * 8];
+        const uint4 u = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(st_wr + ((static_cast<uint32_t>(k) ^ sw) << 4)), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+    }
+    __syncwarp();
+    const int rd_chunk = lane & 3, rd_pix = lane >> 2;
+    uint4 o4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int pr = i * 8 + rd_pix;
+        const uint32_t a = stage_w + pr * 64 + ((static_cast<uint32_t>(rd_chunk) ^ static_cast<uint32_t>((pr >> 1) & 3)) << 4);
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(o4[i].x), "=r"(o4[i].y), "=r"(o4[i].z), "=r"(o4[i].w) : "r"(a) : "memory");
+    }
+    act16* obase = reinterpret_cast<act16*>(p.out) + img * p.out_img_stride + col0 + rd_chunk * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (vmask_rd & (1u << i)) *reinterpret_cast<uint4*>(obase + static_cast<long long>(pix_rd[i]) * p.out_row_stride) = o4[i];
+    if (p.stats) {
+        float ssum[8], ssq[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ssum[e] = ssq[e] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool ok = (vmask_rd >> i) & 1u;
+            const uint32_t ww[4] = {o4[i].x, o4[i].y, o4[i].z, o4[i].w};
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+                const float2 t = unpack2(ww[e2]);
+                const float f0 = ok ? t.x : 0.f, f1 = ok ? t.y : 0.f;
+                ssum[2 * e2] += f0;
+                ssq[2 * e2] = fmaf(f0, f0, ssq[2 * e2]);
+                ssum[2 * e2 + 1] += f1;
+                ssq[2 * e2 + 1] = fmaf(f1, f1, ssq[2 * e2 + 1]);
+            }
+        }
+        // the 8 lanes with the same rd_chunk hold partial sums of the same 8 channels: xor-reduce over lane bits 2..4
+#pragma unroll
+        for (int bit = 4; bit <= 16; bit <<= 1)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                ssum[e] += __shfl_xor_sync(0xffffffffu, ssum[e], bit);
+                ssq[e] += __shfl_xor_sync(0xffffffffu, ssq[e], bit);
+            }
+        float ts = 0.f, tq = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (rd_pix == e) { ts = ssum[e]; tq = ssq[e]; }
+        double* sp = p.stats + (static_cast<long long>(img) * p.n_valid + col0 + rd_chunk * 8 + rd_pix) * 2;    // lane -> channel 8 rd_chunk + rd_pix
+        atomicAdd(sp, static_cast<double>(ts));
+        atomicAdd(sp + 1, static_cast<double>(tq));
+    }
+    __syncwarp();                                      // the tile is rewritten by the next chunk
 }
 
 struct GemmParams {

@@ -94,7 +94,7 @@ bool rowconv_eligible(const ConvDesc& d) {
     return rowconv_shape(d, r);
 }
 // Patch-streaming kernel: shape analysis.
-struct PatchShape { int P, NR, patch_bytes, na, nb, nb_pair, tiles_per_img; };
+struct PatchShape { int P, NR, patch_bytes, na, nb, nb_pair, tiles_per_img, stage_bytes; };
 constexpr int PATCH_SMEM_MAX = 227 * 1024;
 static bool patchconv_shape(const ConvDesc& d, PatchShape& r) {
     static const bool off = getenv("PNPF_NO_PATCH") != nullptr;          // A/B switch (tools/ab_env.py)
@@ -111,7 +111,11 @@ static bool patchconv_shape(const ConvDesc& d, PatchShape& r) {
     r.tiles_per_img = (d.Hout * r.P + 127) / 128;
     // rings: weight tiles of the non-pair variant (the larger) must fit: >= 2 patches + >= 4 weight tiles
     const int b_bytes = d.N_pad * 128;
-    const int budget = PATCH_SMEM_MAX - 1024 - 512;
+    // fp16 NHWC outputs of the narrower tiles leave through 8 x 2 KB staging tiles (coalesced stores + cheaper statistics: the
+    // BN <= 128 layers are shared-memory / epilogue bound; BN = 256 is tensor-bound and keeps its ring depth)
+    static const bool no_stage = getenv("PNPF_NO_PATCH_STAGE") != nullptr;       // A/B switch (tools/ab_env.py)
+    r.stage_bytes = (!no_stage && d.N_pad <= 128 && !d.subpix && d.out_mode == 0 && d.n_valid == d.N_pad && d.out_col_stride <= 1 && r.P >= 10) ? 8 * 2048 : 0;
+    const int budget = PATCH_SMEM_MAX - 1024 - 512 - r.stage_bytes;
     r.na = 3;
     while (r.na > 2 && budget - r.na * r.patch_bytes < 4 * b_bytes) --r.na;
     r.nb = (budget - r.na * r.patch_bytes) / b_bytes;
@@ -187,7 +191,7 @@ static int try_prepare_patchconv(TcOp& op, const ConvDesc& d) {
     memset(&q, 0, sizeof(q));
     q.H = d.Hout; q.W = d.Wout; q.P = sh.P; q.NR = sh.NR; q.n_img = d.B; q.tiles_per_img = sh.tiles_per_img;
     q.kchunks = (d.Cin + 63) / 64; q.kchunks2 = d.x2 ? (d.C2 + 63) / 64 : 0; q.cin = d.Cin;
-    q.patch_bytes = sh.patch_bytes; q.na = sh.na; q.nb = sh.nb;
+    q.patch_bytes = sh.patch_bytes; q.na = sh.na; q.nb = sh.nb; q.stage_bytes = sh.stage_bytes;
     op.patch_nb_pair = sh.nb_pair;
     op.patch_subpix = d.subpix;
     q.sp_a = d.sp_a; q.sp_b = d.sp_b;
@@ -340,7 +344,7 @@ static int launch_patch_t(const TcOp& op, cudaStream_t stream) {
     PatchConvParams q = op.pp;
     if (PAIR) q.nb = op.patch_nb_pair;
     q.nb /= TG;                                       // ring depth in slots of TG weight tiles
-    const int smem = q.na * q.patch_bytes + q.nb * TG * Cfg::B_BYTES + 512 + 1024;
+    const int smem = q.na * q.patch_bytes + q.nb * TG * Cfg::B_BYTES + q.stage_bytes + 512 + 1024;
     static DeviceCache cache;
     int max_clusters = 0;
     if (!cache.lookup(&max_clusters)) {

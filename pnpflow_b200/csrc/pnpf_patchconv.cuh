@@ -48,6 +48,7 @@ struct PatchConvParams {
     int kchunks2;          // channel chunks of the fused 1x1 source (extra K through tmA2, centre tap only); 0 = none
     int patch_bytes;       // NR * P * 128 rounded up to 1024
     int na, nb;            // ring depths: patches, weight tiles
+    int stage_bytes;       // 8 x 2 KB output staging tiles of the epilogue warps (fp16 NHWC outputs of BN <= 128), else 0
     long long* dbg;
     EpiParams epi;
     int sp_a, sp_b;        // SUBPIX: phase (row, column parity of the output pixels this launch produces)
@@ -76,7 +77,8 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;                                    // [na] patches
     uint8_t* b_ring = smem + p.na * p.patch_bytes;             // [nb] weight tiles
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + p.nb * (TG * Cfg::B_BYTES));      // nb slots of TG weight tiles
+    uint8_t* stage = b_ring + p.nb * (TG * Cfg::B_BYTES);      // nb slots of TG weight tiles, then the epilogue's staging tiles
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(stage + p.stage_bytes);
     uint64_t* a_empty = a_full + Cfg::MAX_A;
     uint64_t* b_full = a_empty + Cfg::MAX_A;
     uint64_t* b_empty = b_full + Cfg::MAX_B;
@@ -357,10 +359,31 @@ patchconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+            bool staged = false;
+            if constexpr (SUBPIX == 0 && BN <= 128) staged = p.stage_bytes != 0;
+            if (staged) {
+                // the four pixels this lane stores in the read phase of the staging tile: positions quarter * 32 + 8 i + (lane >> 2)
+                int pix_rd[4];
+                uint32_t vmask_rd = 0;
+                const int o_rd = o0 + quarter * 32 + (lane >> 2);
+                int h_rd = o_rd / p.P, wp_rd = o_rd - h_rd * p.P;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    pix_rd[i] = h_rd * p.W + wp_rd;
+                    if (h_rd < p.H && wp_rd < p.W) vmask_rd |= 1u << i;
+                    wp_rd += 8;                                     // P >= 10: at most one row wrap per step
+                    if (wp_rd >= p.P) { wp_rd -= p.P; ++h_rd; }
+                }
+                const uint32_t stage_w = smem_u32(stage) + static_cast<uint32_t>(warp < 6 ? warp - 2 : warp - 3) * 2048u;
 #pragma unroll 1
-            for (int c0 = col_lo; c0 < col_lo + BN / 2; c0 += 32) {
-                if constexpr (SUBPIX == 2) epilogue_chunk32(p.epi, t_addr + col_lo, img, pix, valid, c0 - col_lo, lane);   // channel = column - b C_out
-                else epilogue_chunk32(p.epi, t_addr, img, pix, valid, c0, lane);
+                for (int c0 = col_lo; c0 < col_lo + BN / 2; c0 += 32)
+                    epilogue_chunk32_staged(p.epi, t_addr, img, pix, valid, c0, lane, stage_w, pix_rd, vmask_rd);
+            } else {
+#pragma unroll 1
+                for (int c0 = col_lo; c0 < col_lo + BN / 2; c0 += 32) {
+                    if constexpr (SUBPIX == 2) epilogue_chunk32(p.epi, t_addr + col_lo, img, pix, valid, c0 - col_lo, lane);   // channel = column - b C_out
+                    else epilogue_chunk32(p.epi, t_addr, img, pix, valid, c0, lane);
+                }
             }
             const long long kt2 = PNPF_CLK();
             c_body += kt2 - kt1;
