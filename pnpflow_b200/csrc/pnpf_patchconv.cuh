@@ -15,7 +15,7 @@
 // PAIR: two CTAs (cta_group::2) take the SAME tile of two consecutive images — one MMA instruction carries one A descriptor
 // for both CTAs, so their patch origins must coincide — and each stages half of every weight tile (see pnpf_gemm.cuh).
 //
-// SUBPIX (opt-in, PNPF_SUBPIXEL_UP=1): one PHASE of "nearest-neighbour x2 upsampling followed by a 3x3 conv" (models.py:41-47)
+// SUBPIX (default since round 2; PNPF_NO_SUBPIXEL=1 turns it off): one PHASE of "nearest-neighbour x2 upsampling followed by a 3x3 conv" (models.py:41-47)
 // computed directly on the LOW-resolution tensor.  Output pixel (2h+a, 2w+b) only sees the 2x2 low-resolution pixels
 // (h-1+a+i, w-1+b+j), i,j in {0,1}, with the 3x3 weights folded into 2x2 (fold_subpixel_weights): four launches (a,b) with
 // 4 taps each replace one launch with 9 taps on a 4x larger tensor — 2.25x fewer FLOPs, and the upsampled tensor is never
@@ -29,10 +29,16 @@
 // L2 -> shared-memory patch fill: 66 KB per 16 short MMAs), every MMA is N = 128 / 256 wide instead of 64 / 128, a thread's two
 // output pixels are adjacent (2 C_out contiguous values), and an up conv is two launches instead of four.
 //
-// TG (opt-in, PNPF_PATCH_TG=3): taps per weight-ring slot.  The MMA issuer pays a barrier wait and a tcgen05.commit per weight
+// TG = 3 (default since round 2; PNPF_PATCH_TG1=1 is the A/B off-switch): taps per weight-ring slot.  The MMA issuer pays a barrier wait and a tcgen05.commit per weight
 // slot (~ 100 clocks), which is exposed when the four MMAs of a tap are short (N = 128: 4 x 64 clocks, measured ~ 90 per MMA;
 // N = 64: 4 x 32): with TG = 3 a slot holds the three taps (kh, 0..2) of a kernel row, so the issuer waits and commits once per
-// 12 MMAs.  Same arithmetic in the same order.
+// 12 MMAs.  Same arithmetic in the same order.  The group's twelve descriptors are one 32-bit low word plus compile-time immediates
+// (umma_f16_lohi): 59 issuer clocks per MMA instead of 84 (profiles/r02_ab_experiments.md section 18).
+//
+// Epilogue: eight warps (two column halves).  BN <= 128, fp16 NHWC output: 32 columns at a time through a per-warp 2 KB staging tile
+// (epilogue_chunk32_staged: whole 64-byte pixel rows per store instruction, GroupNorm statistics summed in the read phase); otherwise
+// per-lane stores and the shuffle butterfly (epilogue_chunk32).  The accumulator-drained arrive of the CTA-pair form is RELAXED
+// (mbar_arrive_cluster in pnpf_ptx.cuh: the release form is a GPU-scope fence per tile).
 #pragma once
 #include "pnpf_gemm.cuh"
 
@@ -62,8 +68,8 @@ struct PatchCfg {
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int MAX_A = 4, MAX_B = 12;
     // warps: 0 patch producer, 1 MMA issuer, 2..5 epilogue (columns [0, BN/2)), 6 weight producer, 7..10 epilogue (columns
-    // [BN/2, BN)).  The epilogue is a per-warp latency chain (tcgen05.ld, bias / residual loads, statistics butterfly,
-    // stores) of ~1200 clocks per 16 columns: with one warp set a 128 x 128 tile took longer to drain than to compute.
+    // [BN/2, BN)).  The epilogue is a per-warp latency chain (tcgen05.ld, bias / residual loads, statistics, stores):
+    // with one warp set a 128 x 128 tile took longer to drain than to compute.
     static constexpr int THREADS = 11 * 32;
     static_assert(BN == 64 || BN == 128 || BN == 256, "patch conv output widths");
 };
